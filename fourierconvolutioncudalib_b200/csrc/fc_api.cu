@@ -1,0 +1,407 @@
+// extern "C" boundary: the reference's exported functions (include/convolution3Dfft.h) plus the
+// extensions of include/fcb200_ext.h.  Host orchestration only; all arithmetic is in fft_kernels.cu.
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "convolution3Dfft.h"
+#include "fc_plan.h"
+#include "fcb200_ext.h"
+
+using namespace fcb200;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<int> g_error_mode{0};  // 0: throw std::runtime_error (reference convention); 1: record only
+
+// Runs `fn`, records the message of any exception for fcb200_last_error() and rethrows it as
+// std::runtime_error -- the reference's convention for recoverable failures
+// (/root/reference/src/book.h:112-123; its tests catch it, tests/test_gpu_convolve.cpp:237-247).
+template <typename F>
+auto guarded(F&& fn) -> decltype(fn())
+{
+    try {
+        g_last_error.clear();
+        return fn();
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        cudaGetLastError();  // clear non-sticky errors so later calls can proceed
+        if (g_error_mode.load() == 1) return decltype(fn())();
+        throw std::runtime_error(g_last_error);
+    }
+}
+
+void check_dims(const int* imDim, const int* kernelDim)
+{
+    if (!imDim) throw std::runtime_error("fcb200: imDim is NULL");
+    for (int i = 0; i < 3; ++i)
+        if (imDim[i] <= 0) throw std::runtime_error("fcb200: image extents must be positive");
+    if (kernelDim)
+        for (int i = 0; i < 3; ++i)
+            if (kernelDim[i] <= 0) throw std::runtime_error("fcb200: kernel extents must be positive");
+}
+
+// Is `p` device memory usable from device `dev`?  (extension: the reference only takes host pointers)
+bool is_device_ptr(const void* p, int dev)
+{
+    cudaPointerAttributes attr{};
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (attr.type == cudaMemoryTypeDevice) {
+        if (attr.device != dev) throw std::runtime_error("fcb200: device pointer belongs to another device");
+        return true;
+    }
+    return attr.type == cudaMemoryTypeManaged;
+}
+
+struct DeviceGuard {
+    int dev;
+    explicit DeviceGuard(int d) : dev(d) { FC_CUDA(cudaSetDevice(d)); }  // like the reference, devCUDA stays current
+};
+
+// Core of the in-place convolution.
+//   nx,ny,nz : geometry of the real volume as consumed (nx fastest)
+//   pdims    : (k0,k1,k2,d0,d1,d2) handed to the PSF placement (reference fftShiftKernel arguments)
+void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const int* pdims, int dev,
+                   bool force_async, cudaStream_t user_stream)
+{
+    DeviceGuard guard(dev);
+    for (int i = 0; i < 3; ++i)
+        if (pdims[i] > pdims[i + 3]) throw std::runtime_error("fcb200: kernel larger than image");
+    auto plan = get_plan(dev, nx, ny, nz);
+    std::lock_guard<std::mutex> lock(plan->mu);
+    ConvPlan& p = *plan;
+    const size_t ktaps = (size_t)pdims[0] * pdims[1] * pdims[2];
+
+    const bool im_dev = force_async || is_device_ptr(im, dev);
+    const bool k_dev = force_async || is_device_ptr(kernel, dev);
+    cudaStream_t st = force_async ? user_stream : (im_dev ? (cudaStream_t)0 : p.stream);
+
+    const float* d_kernel = kernel;
+    if (!k_dev) {
+        if (ktaps > p.kernel_cap) {
+            cudaFree(p.d_kernel);
+            p.d_kernel = nullptr;
+            FC_CUDA(cudaMalloc(&p.d_kernel, ktaps * sizeof(float)));
+            p.kernel_cap = ktaps;
+        }
+        FC_CUDA(cudaMemcpyAsync(p.d_kernel, kernel, ktaps * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_kernel = p.d_kernel;
+    }
+    run_psf_spectrum(p, d_kernel, pdims, st);
+
+    float* d_im = im;
+    if (!im_dev) {
+        if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+        FC_CUDA(cudaMemcpyAsync(p.d_real, im, p.real_bytes(), cudaMemcpyHostToDevice, st));
+        d_im = p.d_real;
+    } else if ((reinterpret_cast<uintptr_t>(im) & 7) != 0) {
+        throw std::runtime_error("fcb200: device image pointer must be 8-byte aligned");
+    }
+    run_convolve(p, d_im, st);
+    if (!im_dev) FC_CUDA(cudaMemcpyAsync(im, p.d_real, p.real_bytes(), cudaMemcpyDeviceToHost, st));
+    if (!force_async) FC_CUDA(cudaStreamSynchronize(st));
+}
+
+// natural-order host spectrum [nz][ny][xc]  <->  device layout [nz][ny][xcp] (kx in position order)
+std::vector<int> xperm(const ConvPlan& p)
+{
+    const Geometry& g = p.g;
+    std::vector<int> perm(g.xc);
+    if (g.odd) {
+        for (int k = 0; k < g.xc; ++k) perm[k] = k;
+    } else {
+        std::vector<int> rev, pos;
+        std::vector<float2> tw;
+        build_tables(g.M, p.px.radix, rev, pos, tw);
+        for (int k = 0; k < g.M; ++k) perm[k] = pos[k];
+        perm[g.M] = g.M;
+    }
+    return perm;
+}
+
+void download_spectrum(ConvPlan& p, const float2* d_spec, float* out, cudaStream_t st)
+{
+    const Geometry& g = p.g;
+    std::vector<float2> h((size_t)g.nz * g.ny * g.xcp);
+    FC_CUDA(cudaMemcpyAsync(h.data(), d_spec, h.size() * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> perm = xperm(p);
+    float2* o = reinterpret_cast<float2*>(out);
+    for (size_t r = 0; r < (size_t)g.nz * g.ny; ++r)
+        for (int k = 0; k < g.xc; ++k) o[r * g.xc + k] = h[r * g.xcp + perm[k]];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// reference ABI
+// ------------------------------------------------------------------------------------------------
+void convolution3DfftCUDAInPlace(imageType* im, int* imDim, imageType* kernel, int* kernelDim, int devCUDA)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        // reference: stack_shape = reverse(imDim) => nx = imDim[0]; placement gets (kernelDim, imDim)
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
+        convolve_core(im, imDim[0], imDim[1], imDim[2], kernel, pdims, devCUDA, false, nullptr);
+    });
+}
+
+void convolution3DfftCUDAInPlaceSaveMemory(imageType* im, int* imDim, imageType* kernel, int* kernelDim, int devCUDA)
+{
+    // Same contract and same numbers as InPlace ("SaveMemory").
+    convolution3DfftCUDAInPlace(im, imDim, kernel, kernelDim, devCUDA);
+}
+
+void fcb200_convolve_device_async(imageType* im_dev, const int* imDim, const imageType* kernel_dev,
+                                  const int* kernelDim, int devCUDA, void* stream)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
+        convolve_core(im_dev, imDim[0], imDim[1], imDim[2], kernel_dev, pdims, devCUDA, true, (cudaStream_t)stream);
+    });
+}
+
+// Legacy entry points: the reference versions were written for cuFFT's removed "native" layout and
+// are flagged as not ported (src/convolution3Dfft.cu:215, :298).  Implemented here with their
+// intended, self-consistent legacy convention (imDim[2] fastest for image, kernel and placement).
+imageType* convolution3DfftCUDA(imageType* im, int* imDim, imageType* kernel, int* kernelDim, int devCUDA)
+{
+    return guarded([&]() -> imageType* {
+        check_dims(imDim, kernelDim);
+        const size_t n = (size_t)imDim[0] * imDim[1] * imDim[2];
+        std::unique_ptr<imageType[]> out(new imageType[n]);
+        std::memcpy(out.get(), im, n * sizeof(imageType));
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
+        convolve_core(out.get(), imDim[2], imDim[1], imDim[0], kernel, pdims, devCUDA, false, nullptr);
+        return out.release();
+    });
+}
+
+imageType* convolution3DfftCUDA_test(imageType* im, int* imDim, imageType* kernel, int devCUDA)
+{
+    return guarded([&]() -> imageType* {
+        check_dims(imDim, nullptr);
+        const int nx = imDim[2], ny = imDim[1], nz = imDim[0];
+        const size_t n = (size_t)nx * ny * nz;
+        std::unique_ptr<imageType[]> out(new imageType[n]);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, nx, ny, nz);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        ConvPlan& p = *plan;
+        cudaStream_t st = p.stream;
+        if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+        // kernel is already image-sized and used as is (no shift), reference :253, :270
+        FC_CUDA(cudaMemcpyAsync(p.d_real, kernel, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        run_forward(p, p.d_real, p.d_H, 3, st);
+        FC_CUDA(cudaMemcpyAsync(p.d_real, im, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        run_convolve(p, p.d_real, st);
+        FC_CUDA(cudaMemcpyAsync(out.get(), p.d_real, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        FC_CUDA(cudaStreamSynchronize(st));
+        return out.release();
+    });
+}
+
+void fcb200_free_result(imageType* p) { delete[] p; }
+
+// ---- device queries (reference: src/standardCUDAfunctions.cu:13-71) ---------------------------
+int getNumDevicesCUDA(void)
+{
+    return guarded([&] {
+        int count = 0;
+        FC_CUDA(cudaGetDeviceCount(&count));
+        return count;
+    });
+}
+
+int getCUDAcomputeCapabilityMajorVersion(int devCUDA)
+{
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, devCUDA) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;  // the reference returns 0 when the query fails (unchecked cuDeviceComputeCapability)
+    }
+    return v;
+}
+
+int getCUDAcomputeCapabilityMinorVersion(int devCUDA)
+{
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, devCUDA) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return v;
+}
+
+int selectDeviceWithHighestComputeCapability(void)
+{
+    return guarded([&] {
+        int n = 0;
+        FC_CUDA(cudaGetDeviceCount(&n));
+        int best = 0, value = -1;  // first device wins ties; -1 when there is none (reference :13-33)
+        for (int d = 0; d < n; ++d) {
+            int meta = 10 * getCUDAcomputeCapabilityMajorVersion(d) + getCUDAcomputeCapabilityMinorVersion(d);
+            if (meta > best) {
+                best = meta;
+                value = d;
+            }
+        }
+        return value;
+    });
+}
+
+void getNameDeviceCUDA(int devCUDA, char* name)
+{
+    guarded([&] {
+        cudaDeviceProp prop;
+        FC_CUDA(cudaGetDeviceProperties(&prop, devCUDA));
+        std::memcpy(name, prop.name, sizeof(char) * 256);  // exactly 256 bytes, reference :58-64
+    });
+}
+
+long long int getMemDeviceCUDA(int devCUDA)
+{
+    return guarded([&] {
+        cudaDeviceProp prop;
+        FC_CUDA(cudaGetDeviceProperties(&prop, devCUDA));
+        return (long long int)prop.totalGlobalMem;
+    });
+}
+
+int cuda_version(void) { return CUDART_VERSION; }
+
+long long fcb200_workspace_bytes(const int* imDim)
+{
+    Geometry g = make_geometry(imDim[0], imDim[1], imDim[2]);
+    const long long spec = (long long)g.nz * g.ny * g.xcp * (long long)sizeof(float2);
+    const long long tables = 16LL * ((long long)g.M + g.ny + g.nz) + 8LL * (g.M + 1);
+    return 2 * spec + tables;
+}
+
+int gpu_mem_needed_mb(int* shape, int len)
+{
+    return guarded([&] {
+        if (!shape || len < 1 || len > 3) throw std::runtime_error("fcb200: gpu_mem_needed_mb needs len in {1,2,3}");
+        // cufftEstimate{1,2,3}d(shape...) treats the LAST extent as the fastest one (reference :587-603)
+        int dims[3] = {1, 1, 1};
+        for (int i = 0; i < len; ++i) dims[i] = shape[len - 1 - i];
+        check_dims(dims, nullptr);
+        return (int)(fcb200_workspace_bytes(dims) / (1 << 20));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// extensions
+// ------------------------------------------------------------------------------------------------
+const char* fcb200_last_error(void) { return g_last_error.c_str(); }
+void fcb200_set_error_mode(int mode) { g_error_mode.store(mode == 1 ? 1 : 0); }
+
+int fcb200_plan_radices(int L, int* radices, int* generic)
+{
+    return guarded([&] {
+        if (L < 1) throw std::runtime_error("fcb200: L must be >= 1");
+        bool gen = false;
+        std::vector<int> r = factorize(L, &gen);
+        for (size_t i = 0; i < r.size(); ++i) radices[i] = r[i];
+        if (generic) *generic = gen ? 1 : 0;
+        return (int)r.size();
+    });
+}
+
+void fcb200_plan_tables(int L, int* rev, int* pos, float* tw)
+{
+    guarded([&] {
+        bool gen = false;
+        std::vector<int> r = factorize(L, &gen), hrev, hpos;
+        std::vector<float2> htw;
+        build_tables(L, r, hrev, hpos, htw);
+        if (rev) std::memcpy(rev, hrev.data(), sizeof(int) * L);
+        if (pos) std::memcpy(pos, hpos.data(), sizeof(int) * L);
+        if (tw) std::memcpy(tw, htw.data(), sizeof(float2) * L);
+    });
+}
+
+int fcb200_spectrum_pitch(int nx) { return make_geometry(nx, 1, 1).xcp; }
+
+long long fcb200_psf_active_rows(const int* imDim, const int* kernelDim, int* rows, long long cap)
+{
+    return guarded([&] {
+        check_dims(imDim, kernelDim);
+        std::vector<int> r = psf_active_rows(imDim, kernelDim, imDim[0]);
+        if (rows)
+            for (long long i = 0; i < (long long)r.size() && i < cap; ++i) rows[i] = r[(size_t)i];
+        return (long long)r.size();
+    });
+}
+
+void fcb200_debug_rfft3(const imageType* im, const int* imDim, float* spec, int passes, int devCUDA)
+{
+    guarded([&] {
+        check_dims(imDim, nullptr);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2]);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        ConvPlan& p = *plan;
+        if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+        FC_CUDA(cudaMemcpyAsync(p.d_real, im, p.real_bytes(), cudaMemcpyHostToDevice, p.stream));
+        run_forward(p, p.d_real, p.d_spec, passes, p.stream);
+        download_spectrum(p, p.d_spec, spec, p.stream);
+    });
+}
+
+void fcb200_debug_irfft3(const float* spec, const int* imDim, imageType* out, int devCUDA)
+{
+    guarded([&] {
+        check_dims(imDim, nullptr);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2]);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        ConvPlan& p = *plan;
+        const Geometry& g = p.g;
+        std::vector<float2> h((size_t)g.nz * g.ny * g.xcp, make_float2(0.f, 0.f));
+        std::vector<int> perm = xperm(p);
+        const float2* s = reinterpret_cast<const float2*>(spec);
+        for (size_t r = 0; r < (size_t)g.nz * g.ny; ++r)
+            for (int k = 0; k < g.xc; ++k) h[r * g.xcp + perm[k]] = s[r * g.xc + k];
+        if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+        FC_CUDA(cudaMemcpyAsync(p.d_spec, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice, p.stream));
+        run_inverse(p, p.d_spec, p.d_real, p.stream);
+        FC_CUDA(cudaMemcpyAsync(out, p.d_real, p.real_bytes(), cudaMemcpyDeviceToHost, p.stream));
+        FC_CUDA(cudaStreamSynchronize(p.stream));
+    });
+}
+
+void fcb200_debug_psf_spectrum(const imageType* kernel, const int* kernelDim, const int* imDim, float* spec, int devCUDA)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2]);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        ConvPlan& p = *plan;
+        const size_t ktaps = (size_t)kernelDim[0] * kernelDim[1] * kernelDim[2];
+        if (ktaps > p.kernel_cap) {
+            cudaFree(p.d_kernel);
+            p.d_kernel = nullptr;
+            FC_CUDA(cudaMalloc(&p.d_kernel, ktaps * sizeof(float)));
+            p.kernel_cap = ktaps;
+        }
+        FC_CUDA(cudaMemcpyAsync(p.d_kernel, kernel, ktaps * sizeof(float), cudaMemcpyHostToDevice, p.stream));
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
+        run_psf_spectrum(p, p.d_kernel, pdims, p.stream);
+        download_spectrum(p, p.d_H, spec, p.stream);
+    });
+}
+
+void fcb200_release(void) { release_all_plans(); }
+void fcb200_profile_enable(int on) { profile_enable(on); }
+int fcb200_profile_read(float* ms_sum, long long* counts, int n) { return profile_read(ms_sum, counts, n); }
+long long fcb200_launch_count(void) { return launch_count(); }

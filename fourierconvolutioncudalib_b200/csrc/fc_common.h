@@ -1,0 +1,60 @@
+// Shared declarations of the B200-native FFT convolution library (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+
+namespace fcb200 {
+
+constexpr int kMaxStages = 16;
+constexpr int kMaxDynSmem = 227 * 1024;   // usable shared memory per CTA on sm_100a
+constexpr int kColThreads = 256;          // CTA size of every FFT kernel
+
+// Device view of a 1D transform plan (passed to kernels by value).
+struct AxisPlanDev {
+    int L;                    // transform length
+    int ns;                   // number of stages
+    int radix[kMaxStages];    // stage radices, product == L
+    int generic;              // 1 when a radix outside {2,3,4,5,7,8} is present (needs two tile buffers)
+    const float2* tw;         // L roots: exp(-2*pi*i*t/L), computed in double
+    const int* rev;           // rev[p]  = frequency held at position p after the forward transform
+    const int* pos;           // pos[k]  = position that holds frequency k (inverse permutation)
+};
+
+// Geometry of one convolution problem as the kernels see it.
+//   real volume  : [nz][ny][nx] floats, nx fastest (reference: imDim = {nx, ny, nz},
+//                  /root/reference/src/convolution3Dfft.cu:417-421)
+//   spectrum     : [nz][ny][xcp] float2, xc = nx/2+1 valid bins per row, xcp = xc rounded up to 4
+//                  (32-byte sector alignment of every row); kx is stored in *engine position order*
+//                  for even nx (position M = nx/2 is the Nyquist bin), natural order for odd nx;
+//                  ky and kz are in natural order.
+struct Geometry {
+    int nx, ny, nz;
+    int xc, xcp;
+    int M;        // length of the complex transform used along x: nx/2 (even nx) or nx (odd nx)
+    int odd;      // nx odd
+};
+
+// PSF placement parameters (fftShiftKernel as called by the reference,
+// /root/reference/src/convolution3Dfft.cu:128-166 with the arguments of :454-461).
+struct PsfGather {
+    const float* kernel;  // k0*k1*k2 taps (device)
+    int k0, k1, k2;
+    int d0, d1, d2;
+};
+
+inline void throw_cuda(cudaError_t err, const char* what, const char* file, int line)
+{
+    if (err != cudaSuccess) {
+        std::ostringstream msg;
+        msg << cudaGetErrorString(err) << " (" << what << ") in " << file << " at line " << line;
+        throw std::runtime_error(msg.str());
+    }
+}
+#define FC_CUDA(expr) ::fcb200::throw_cuda((expr), #expr, __FILE__, __LINE__)
+#define FC_CUDA_KERNEL() ::fcb200::throw_cuda(cudaPeekAtLastError(), "kernel launch", __FILE__, __LINE__)
+
+}  // namespace fcb200

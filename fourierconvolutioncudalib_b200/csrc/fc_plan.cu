@@ -1,0 +1,488 @@
+// Planner, plan cache and pass sequencing (host C++).
+//
+// The reference creates and destroys two cuFFT plans and four device buffers inside every call
+// (/root/reference/src/convolution3Dfft.cu:442-559).  Here a plan (twiddle / permutation tables,
+// spectrum workspace, stream) is built once per (device, shape) and cached, thread-safe.
+#include "fc_plan.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace fcb200 {
+
+// ------------------------------------------------------------------------------------------------
+// pure host planning
+// ------------------------------------------------------------------------------------------------
+std::vector<int> factorize(int L, bool* generic)
+{
+    std::vector<int> out;
+    bool gen = false;
+    int n = L;
+    static const int fast[] = {8, 4, 2, 3, 5, 7};
+    for (int r : fast)
+        while (n > 1 && n % r == 0) {
+            out.push_back(r);
+            n /= r;
+        }
+    for (int p = 11; n > 1; p += 2) {
+        if ((long long)p * p > n) p = n;  // remaining cofactor is prime
+        while (n % p == 0) {
+            out.push_back(p);
+            n /= p;
+            gen = true;
+        }
+    }
+    if (out.empty()) out.push_back(1);
+    if ((int)out.size() > kMaxStages) throw std::runtime_error("fcb200: transform length has too many factors");
+    if (generic) *generic = gen;
+    return out;
+}
+
+void build_tables(int L, const std::vector<int>& radix, std::vector<int>& rev, std::vector<int>& pos,
+                  std::vector<float2>& tw)
+{
+    rev.assign(L, 0);
+    pos.assign(L, 0);
+    tw.resize(L);
+    for (int p = 0; p < L; ++p) {
+        int k = 0, mul = 1, rem = p, Li = L;
+        for (int R : radix) {
+            int S = Li / R;
+            int m = rem / S;
+            rem -= m * S;
+            k += m * mul;
+            mul *= R;
+            Li = S;
+        }
+        rev[p] = k;
+        pos[k] = p;
+    }
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int t = 0; t < L; ++t) {
+        // exact symmetries first so the eight principal roots are exact in float
+        double ang = two_pi * (double)t / (double)L;
+        double c = std::cos(ang), s = -std::sin(ang);
+        if (4 * (long long)t == L) { c = 0.0; s = -1.0; }
+        if (2 * (long long)t == L) { c = -1.0; s = 0.0; }
+        if (4 * (long long)t == 3LL * L) { c = 0.0; s = 1.0; }
+        tw[t] = make_float2((float)c, (float)s);
+    }
+}
+
+Geometry make_geometry(int nx, int ny, int nz)
+{
+    Geometry g{};
+    g.nx = nx;
+    g.ny = ny;
+    g.nz = nz;
+    g.xc = nx / 2 + 1;
+    g.xcp = (g.xc + 3) & ~3;
+    g.odd = nx & 1;
+    g.M = g.odd ? nx : nx / 2;
+    return g;
+}
+
+std::vector<int> psf_active_rows(const int* dims, const int* kdims, int nx)
+{
+    const long long d0 = dims[0], d1 = dims[1], d2 = dims[2];
+    const int k0 = kdims[0], k1 = kdims[1], k2 = kdims[2];
+    const long long nrows = d0 * d1 * d2 / nx;
+    std::vector<unsigned char> hit((size_t)nrows, 0);
+    for (int a = 0; a < k0; ++a) {
+        long long aq = a - k0 / 2;
+        if (aq < 0) aq += d0;
+        for (int b = 0; b < k1; ++b) {
+            long long bq = b - k1 / 2;
+            if (bq < 0) bq += d1;
+            for (int c = 0; c < k2; ++c) {
+                long long cq = c - k2 / 2;
+                if (cq < 0) cq += d2;
+                long long flat = cq + d2 * (bq + d1 * aq);
+                hit[(size_t)(flat / nx)] = 1;
+            }
+        }
+    }
+    std::vector<int> rows;
+    for (long long r = 0; r < nrows; ++r)
+        if (hit[(size_t)r]) rows.push_back((int)r);
+    return rows;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device plan
+// ------------------------------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+long long launch_count() { return g_launches.load(); }
+void count_launches(int n) { g_launches.fetch_add(n); }
+
+// ---- optional per-pass timing with CUDA events on the launching stream (bench.py roofline) ----
+static std::atomic<int> g_profile{0};
+struct PassEvent {
+    int id;
+    cudaEvent_t a, b;
+};
+static std::mutex g_prof_mu;
+static std::vector<PassEvent> g_prof_events;
+
+void profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+
+int profile_read(float* ms_sum, long long* counts, int n)
+{
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    for (int i = 0; i < n; ++i) {
+        ms_sum[i] = 0.f;
+        counts[i] = 0;
+    }
+    for (PassEvent& e : g_prof_events) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess &&
+            e.id >= 0 && e.id < n) {
+            ms_sum[e.id] += ms;
+            counts[e.id] += 1;
+        }
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_prof_events.clear();
+    return kNumPassIds;
+}
+
+struct PassTimer {
+    int id;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    PassTimer(int id_, cudaStream_t st_) : id(id_), st(st_)
+    {
+        if (g_profile.load()) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~PassTimer()
+    {
+        if (a) {
+            cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lock(g_prof_mu);
+            g_prof_events.push_back({id, a, b});
+        }
+    }
+};
+
+static void make_axis(AxisPlan& a, int L)
+{
+    a.L = L;
+    a.radix = factorize(L, &a.generic);
+    std::vector<int> rev, pos;
+    std::vector<float2> tw;
+    build_tables(L, a.radix, rev, pos, tw);
+    FC_CUDA(cudaMalloc(&a.d_tw, sizeof(float2) * L));
+    FC_CUDA(cudaMalloc(&a.d_rev, sizeof(int) * L));
+    FC_CUDA(cudaMalloc(&a.d_pos, sizeof(int) * L));
+    FC_CUDA(cudaMemcpy(a.d_tw, tw.data(), sizeof(float2) * L, cudaMemcpyHostToDevice));
+    FC_CUDA(cudaMemcpy(a.d_rev, rev.data(), sizeof(int) * L, cudaMemcpyHostToDevice));
+    FC_CUDA(cudaMemcpy(a.d_pos, pos.data(), sizeof(int) * L, cudaMemcpyHostToDevice));
+    a.dev.L = L;
+    a.dev.ns = (int)a.radix.size();
+    for (int i = 0; i < kMaxStages; ++i) a.dev.radix[i] = i < a.dev.ns ? a.radix[i] : 1;
+    a.dev.generic = a.generic ? 1 : 0;
+    a.dev.tw = a.d_tw;
+    a.dev.rev = a.d_rev;
+    a.dev.pos = a.d_pos;
+}
+
+static void free_axis(AxisPlan& a)
+{
+    cudaFree(a.d_tw);
+    cudaFree(a.d_rev);
+    cudaFree(a.d_pos);
+    a.d_tw = nullptr;
+    a.d_rev = a.d_pos = nullptr;
+}
+
+ConvPlan::~ConvPlan()
+{
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    free_axis(px);
+    free_axis(py);
+    free_axis(pz);
+    cudaFree(d_twx);
+    cudaFree(d_spec);
+    cudaFree(d_H);
+    cudaFree(d_real);
+    cudaFree(d_kernel);
+    cudaFree(d_rows);
+    if (stream) cudaStreamDestroy(stream);
+    if (prev >= 0) cudaSetDevice(prev);
+}
+
+struct PlanKey {
+    int dev, nx, ny, nz;
+    bool operator<(const PlanKey& o) const
+    {
+        if (dev != o.dev) return dev < o.dev;
+        if (nx != o.nx) return nx < o.nx;
+        if (ny != o.ny) return ny < o.ny;
+        return nz < o.nz;
+    }
+};
+
+static std::mutex g_cache_mu;
+static std::map<PlanKey, std::shared_ptr<ConvPlan>> g_cache;
+static unsigned long long g_tick = 0;
+
+static size_t max_cached_plans()
+{
+    const char* e = std::getenv("FCB200_MAX_PLANS");
+    if (e) {
+        long v = std::strtol(e, nullptr, 10);
+        if (v >= 0) return (size_t)v;
+    }
+    return 4;
+}
+
+static void evict_lru_locked(size_t keep)
+{
+    while (g_cache.size() > keep) {
+        auto victim = g_cache.end();
+        for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+            if (it->second.use_count() == 1 && (victim == g_cache.end() || it->second->last_use < victim->second->last_use))
+                victim = it;
+        if (victim == g_cache.end()) break;
+        g_cache.erase(victim);
+    }
+}
+
+static std::shared_ptr<ConvPlan> build_plan(int device, int nx, int ny, int nz)
+{
+    auto p = std::make_shared<ConvPlan>();
+    p->device = device;
+    p->g = make_geometry(nx, ny, nz);
+    make_axis(p->px, p->g.M);
+    make_axis(p->py, ny);
+    make_axis(p->pz, nz);
+    if (!x_pass_supported(p->g, p->px.dev))
+        throw std::runtime_error("fcb200: fastest image extent too large for the shared-memory x pass");
+    p->txp_y = col_pick_txp(p->py.dev);
+    p->txp_z = col_pick_txp(p->pz.dev);
+    if (p->txp_y == 0 || p->txp_z == 0)
+        throw std::runtime_error("fcb200: image extent too large for the shared-memory column pass");
+    if (!p->g.odd) {
+        std::vector<float2> twx(p->g.M + 1);
+        const double two_pi = 6.283185307179586476925286766559;
+        for (int k = 0; k <= p->g.M; ++k) {
+            double ang = two_pi * (double)k / (double)nx;
+            twx[k] = make_float2((float)std::cos(ang), (float)(-std::sin(ang)));
+        }
+        FC_CUDA(cudaMalloc(&p->d_twx, sizeof(float2) * twx.size()));
+        FC_CUDA(cudaMemcpy(p->d_twx, twx.data(), sizeof(float2) * twx.size(), cudaMemcpyHostToDevice));
+    }
+    FC_CUDA(cudaMalloc(&p->d_spec, p->spec_bytes()));
+    FC_CUDA(cudaMalloc(&p->d_H, p->spec_bytes()));
+    FC_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    return p;
+}
+
+std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz)
+{
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    PlanKey key{device, nx, ny, nz};
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) {
+        it->second->last_use = ++g_tick;
+        return it->second;
+    }
+    std::shared_ptr<ConvPlan> p;
+    try {
+        p = build_plan(device, nx, ny, nz);
+    } catch (const std::runtime_error&) {
+        // most likely out of device memory: drop every idle cached plan and retry once
+        cudaGetLastError();
+        evict_lru_locked(0);
+        p = build_plan(device, nx, ny, nz);
+    }
+    p->last_use = ++g_tick;
+    g_cache[key] = p;
+    size_t keep = max_cached_plans();
+    evict_lru_locked(keep == 0 ? 1 : keep);
+    return p;
+}
+
+void release_all_plans()
+{
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    g_cache.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass sequencing
+// ------------------------------------------------------------------------------------------------
+static ColArgs y_args(ConvPlan& p, float2* data)
+{
+    ColArgs a{};
+    a.data = data;
+    a.H = nullptr;
+    a.P = p.py.dev;
+    a.stride = p.g.xcp;
+    a.groupStride = (long long)p.g.ny * p.g.xcp;
+    a.txp = p.txp_y;
+    a.tilesPerGroup = (p.g.xcp + 2 * a.txp - 1) / (2 * a.txp);
+    a.rowLen = p.g.xcp;
+    a.scale = 1.f;
+    return a;
+}
+
+static ColArgs z_args(ConvPlan& p, float2* data)
+{
+    ColArgs a{};
+    const long long C = (long long)p.g.ny * p.g.xcp;
+    if (C > 0x7fffffffLL) throw std::runtime_error("fcb200: plane too large");
+    a.data = data;
+    a.H = nullptr;
+    a.P = p.pz.dev;
+    a.stride = C;
+    a.groupStride = 0;
+    a.txp = p.txp_z;
+    a.tilesPerGroup = (int)((C + 2 * a.txp - 1) / (2 * a.txp));
+    a.rowLen = (int)C;
+    a.scale = 1.f;
+    return a;
+}
+
+static XArgs x_args(ConvPlan& p)
+{
+    XArgs a{};
+    a.g = p.g;
+    a.P = p.px.dev;
+    a.twx = p.d_twx;
+    a.nrows = (long long)p.g.ny * p.g.nz;
+    a.rowList = nullptr;
+    return a;
+}
+
+void run_forward(ConvPlan& p, const float* d_real, float2* dst, int passes, cudaStream_t st)
+{
+    XArgs xa = x_args(p);
+    xa.in_real = d_real;
+    xa.spec = dst;
+    {
+        PassTimer t(kPassXFwd, st);
+        launch_x_fwd(xa, false, st);
+    }
+    count_launches(1);
+    if (passes >= 2) {
+        PassTimer t(kPassYFwd, st);
+        launch_col(y_args(p, dst), 0, p.g.nz, st);
+        count_launches(1);
+    }
+    if (passes >= 3) {
+        PassTimer t(kPassPsfZ, st);
+        launch_col(z_args(p, dst), 0, 1, st);
+        count_launches(1);
+    }
+}
+
+void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
+{
+    if (std::memcmp(p.psf_key, pdims, sizeof(int) * 6) != 0 || p.d_rows == nullptr) {
+        std::vector<int> rows = psf_active_rows(pdims + 3, pdims, p.g.nx);
+        if (rows.size() > p.rows_cap) {
+            // make sure no earlier launch still reads the old list
+            FC_CUDA(cudaStreamSynchronize(st));
+            cudaFree(p.d_rows);
+            p.d_rows = nullptr;
+            FC_CUDA(cudaMalloc(&p.d_rows, sizeof(int) * rows.size()));
+            p.rows_cap = rows.size();
+        } else {
+            FC_CUDA(cudaStreamSynchronize(st));
+        }
+        FC_CUDA(cudaMemcpy(p.d_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice));
+        p.n_rows = (long long)rows.size();
+        std::memcpy(p.psf_key, pdims, sizeof(int) * 6);
+    }
+    {
+        PassTimer t(kPassPsfClear, st);
+        FC_CUDA(cudaMemsetAsync(p.d_H, 0, p.spec_bytes(), st));
+    }
+    XArgs xa = x_args(p);
+    xa.spec = p.d_H;
+    xa.nrows = p.n_rows;
+    xa.rowList = p.d_rows;
+    xa.psf.kernel = d_kernel;
+    xa.psf.k0 = pdims[0];
+    xa.psf.k1 = pdims[1];
+    xa.psf.k2 = pdims[2];
+    xa.psf.d0 = pdims[3];
+    xa.psf.d1 = pdims[4];
+    xa.psf.d2 = pdims[5];
+    {
+        PassTimer t(kPassPsfX, st);
+        launch_x_fwd(xa, true, st);
+    }
+    {
+        PassTimer t(kPassPsfY, st);
+        launch_col(y_args(p, p.d_H), 0, p.g.nz, st);
+    }
+    {
+        PassTimer t(kPassPsfZ, st);
+        launch_col(z_args(p, p.d_H), 0, 1, st);
+    }
+    count_launches(3);
+}
+
+void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st)
+{
+    launch_col(z_args(p, spec), 1, 1, st);
+    {
+        PassTimer t(kPassYInv, st);
+        launch_col(y_args(p, spec), 1, p.g.nz, st);
+    }
+    XArgs xa = x_args(p);
+    xa.spec = spec;
+    xa.out_real = d_real;
+    {
+        PassTimer t(kPassXInv, st);
+        launch_x_inv(xa, st);
+    }
+    count_launches(3);
+}
+
+void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st)
+{
+    XArgs xa = x_args(p);
+    xa.in_real = d_real;
+    xa.spec = p.d_spec;
+    {
+        PassTimer t(kPassXFwd, st);
+        launch_x_fwd(xa, false, st);
+    }
+    {
+        PassTimer t(kPassYFwd, st);
+        launch_col(y_args(p, p.d_spec), 0, p.g.nz, st);
+    }
+    ColArgs za = z_args(p, p.d_spec);
+    za.H = p.d_H;
+    // reference: scale = 1.0f/(float)(size_img), src/convolution3Dfft.cu:531
+    za.scale = 1.0f / (float)((size_t)p.g.nx * (size_t)p.g.ny * (size_t)p.g.nz);
+    {
+        PassTimer t(kPassZFused, st);
+        launch_col(za, 2, 1, st);
+    }
+    {
+        PassTimer t(kPassYInv, st);
+        launch_col(y_args(p, p.d_spec), 1, p.g.nz, st);
+    }
+    xa.out_real = d_real;
+    {
+        PassTimer t(kPassXInv, st);
+        launch_x_inv(xa, st);
+    }
+    count_launches(5);
+}
+
+}  // namespace fcb200

@@ -1,0 +1,82 @@
+// Host-side planner and plan cache of the B200-native FFT convolution library.
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "fc_common.h"
+#include "fft_kernels.h"
+
+namespace fcb200 {
+
+// ---- pure host planning (no CUDA calls; unit-tested on the CPU) -----------------------------------
+std::vector<int> factorize(int L, bool* generic);
+void build_tables(int L, const std::vector<int>& radix, std::vector<int>& rev, std::vector<int>& pos,
+                  std::vector<float2>& tw);
+Geometry make_geometry(int nx, int ny, int nz);
+// rows (z*ny + y) of the padded PSF volume that hold >= 1 tap under the reference placement
+std::vector<int> psf_active_rows(const int* dims /*d0,d1,d2 as passed to fftShiftKernel*/, const int* kdims,
+                                 int nx /*fastest extent of the consumed volume*/);
+
+// ---- device-side plan -------------------------------------------------------------------------
+struct AxisPlan {
+    int L = 0;
+    std::vector<int> radix;
+    bool generic = false;
+    float2* d_tw = nullptr;
+    int* d_rev = nullptr;
+    int* d_pos = nullptr;
+    AxisPlanDev dev{};
+};
+
+struct ConvPlan {
+    int device = 0;
+    Geometry g{};
+    AxisPlan px, py, pz;
+    float2* d_twx = nullptr;     // exp(-2*pi*i*k/nx), k = 0..nx/2
+    int txp_y = 8, txp_z = 8;
+    // workspace
+    float2* d_spec = nullptr;    // image spectrum   [nz][ny][xcp]
+    float2* d_H = nullptr;       // PSF spectrum     [nz][ny][xcp]
+    float* d_real = nullptr;     // staging for host-pointer calls [nz][ny][nx]
+    float* d_kernel = nullptr;   // PSF taps staging
+    size_t kernel_cap = 0;
+    // PSF pruning lists, cached per kernel shape / placement dims
+    int psf_key[6] = {0, 0, 0, 0, 0, 0};
+    int* d_rows = nullptr;
+    long long n_rows = 0;
+    size_t rows_cap = 0;
+    cudaStream_t stream = nullptr;   // used for host-pointer calls
+    std::mutex mu;
+    unsigned long long last_use = 0;
+    size_t spec_bytes() const { return (size_t)g.nz * g.ny * g.xcp * sizeof(float2); }
+    size_t real_bytes() const { return (size_t)g.nz * g.ny * g.nx * sizeof(float); }
+    ~ConvPlan();
+};
+
+// Returns the cached plan for (device, nx, ny, nz), creating it (tables + workspace) if needed.
+// The caller must hold plan->mu while using the workspace.
+std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz);
+void release_all_plans();
+long long launch_count();
+void count_launches(int n);
+
+// pass ids for the optional CUDA-event profile (fcb200_profile_*)
+enum PassId { kPassPsfClear = 0, kPassPsfX, kPassPsfY, kPassPsfZ, kPassXFwd, kPassYFwd, kPassZFused, kPassYInv,
+              kPassXInv, kNumPassIds };
+void profile_enable(int on);
+int profile_read(float* ms_sum, long long* counts, int n);
+
+// ---- pipeline pieces (all enqueue on `st`) -------------------------------------------------------
+// PSF spectrum into plan.d_H.  pdims = the six ints handed to fftShiftKernel by the reference
+// (k0,k1,k2,d0,d1,d2); d_kernel = taps on the device.
+void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st);
+// Spectrum of a dense image-sized volume into dst (used for the image and for the legacy
+// convolution3DfftCUDA_test whose kernel is already image-sized).
+void run_forward(ConvPlan& p, const float* d_real, float2* dst, int passes, cudaStream_t st);
+// Image path: d_real (device, dense) is convolved in place with the PSF spectrum in plan.d_H.
+void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st);
+void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st);
+
+}  // namespace fcb200

@@ -1,0 +1,37 @@
+// Kernel argument blocks and launchers (see fft_kernels.cu).
+#pragma once
+#include "fc_common.h"
+
+namespace fcb200 {
+
+struct XArgs {
+    const float* in_real;   // forward, image loader: [rows][nx]
+    float* out_real;        // inverse: [rows][nx]
+    float2* spec;           // [rows][xcp]
+    Geometry g;
+    AxisPlanDev P;          // complex transform of length g.M
+    const float2* twx;      // exp(-2*pi*i*k/nx), k = 0..nx/2 (even nx only)
+    long long nrows;        // rows to process (length of rowList when given, else ny*nz)
+    const int* rowList;     // optional: global row index of each processed row (PSF pruning)
+    PsfGather psf;          // PSF loader only
+};
+
+struct ColArgs {
+    float2* data;           // transformed in place
+    const float2* H;        // fused mode: PSF spectrum, same layout as data
+    AxisPlanDev P;
+    long long stride;       // float2 elements between consecutive transform positions
+    long long groupStride;  // float2 elements between tile groups (z planes for the y pass)
+    int tilesPerGroup;
+    int rowLen;             // float2 elements per group row (xcp for y, ny*xcp for z); even
+    int txp;                // column pairs per tile
+    float scale;            // fused mode: 1/N
+};
+
+bool x_pass_supported(const Geometry& g, const AxisPlanDev& P);
+int col_pick_txp(const AxisPlanDev& P);
+void launch_x_fwd(const XArgs& a, bool psf, cudaStream_t st);
+void launch_x_inv(const XArgs& a, cudaStream_t st);
+void launch_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
+
+}  // namespace fcb200

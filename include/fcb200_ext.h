@@ -1,0 +1,53 @@
+/* Extensions of the B200-native library that have no counterpart in the reference ABI.
+ * They exist for (1) device-resident, stream-ordered use (benchmarks, multi-GPU tile scheduling),
+ * (2) CPU-side tests of the planner, (3) pass-level debugging / parity tests.
+ * Plain C ABI: pointers and sizes only. */
+#ifndef FCB200_EXT_H
+#define FCB200_EXT_H
+
+#include "convolution3Dfft.h"
+
+/* Same arithmetic as convolution3DfftCUDAInPlace (reference src/convolution3Dfft.cu:399-578) on
+ * DEVICE pointers, enqueued on `stream` (a cudaStream_t; NULL = legacy default stream) without any
+ * host synchronisation.  The PSF spectrum is recomputed on every call, like the reference does. */
+FUNCTION_PREFIX void fcb200_convolve_device_async(imageType* im_dev, const int* imDim, const imageType* kernel_dev,
+                                                 const int* kernelDim, int devCUDA, void* stream);
+
+/* Planner introspection (pure host code; callable without a GPU).
+ * fcb200_plan_radices: writes the stage radices of a length-L transform (at most 16), returns the
+ * number of stages; *generic is 1 when a radix outside {2,3,4,5,7,8} is needed. */
+FUNCTION_PREFIX int fcb200_plan_radices(int L, int* radices, int* generic);
+/* rev[p]: frequency at position p after the forward transform; pos = inverse permutation;
+ * tw: L interleaved (re,im) roots exp(-2*pi*i*t/L).  Any pointer may be NULL. */
+FUNCTION_PREFIX void fcb200_plan_tables(int L, int* rev, int* pos, float* tw);
+/* Spectrum row pitch (complex elements) used for a volume whose fastest extent is nx. */
+FUNCTION_PREFIX int fcb200_spectrum_pitch(int nx);
+/* Bytes of device workspace a cached plan for imDim holds (spectrum + PSF spectrum + tables). */
+FUNCTION_PREFIX long long fcb200_workspace_bytes(const int* imDim);
+/* Rows (z*d1+y) of the padded PSF volume that hold at least one tap (PSF pruning); returns count.
+ * rows may be NULL. */
+FUNCTION_PREFIX long long fcb200_psf_active_rows(const int* imDim, const int* kernelDim, int* rows, long long cap);
+
+/* Pass-level debug entry points (host pointers).  Spectra are [d2][d1][d0/2+1] interleaved complex
+ * in NATURAL frequency order, i.e. numpy.fft.rfftn of the [d2][d1][d0] volume.
+ * passes: 1 = x only, 2 = x and y, 3 = full 3D. */
+FUNCTION_PREFIX void fcb200_debug_rfft3(const imageType* im, const int* imDim, float* spec, int passes, int devCUDA);
+/* Unnormalised inverse of the full 3D spectrum (what cufftExecC2R returns: N * irfftn). */
+FUNCTION_PREFIX void fcb200_debug_irfft3(const float* spec, const int* imDim, imageType* out, int devCUDA);
+/* Full 3D spectrum of the placed PSF (zero-pad + circular shift fused into the x pass). */
+FUNCTION_PREFIX void fcb200_debug_psf_spectrum(const imageType* kernel, const int* kernelDim, const int* imDim,
+                                              float* spec, int devCUDA);
+
+/* Per-pass device timing with CUDA events recorded on the launching stream around every pass.
+ * Pass ids: 0 psf_clear, 1 psf_x, 2 psf_y, 3 psf_z, 4 x_fwd, 5 y_fwd, 6 z_fused, 7 y_inv, 8 x_inv.
+ * fcb200_profile_read waits for the recorded events, writes the summed milliseconds and launch counts
+ * per pass id (n entries), resets the record and returns the number of pass ids (9). */
+FUNCTION_PREFIX void fcb200_profile_enable(int on);
+FUNCTION_PREFIX int fcb200_profile_read(float* ms_sum, long long* counts, int n);
+
+/* Frees every cached plan and its device workspace on all devices. */
+FUNCTION_PREFIX void fcb200_release(void);
+/* Number of kernels this library has launched since load (for benchmark accounting). */
+FUNCTION_PREFIX long long fcb200_launch_count(void);
+
+#endif /* FCB200_EXT_H */

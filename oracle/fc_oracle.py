@@ -1,0 +1,121 @@
+"""CPU oracle for the 3D FFT-convolution hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product path (fourierconvolutioncudalib_b200) never does; it fails
+loudly when its CUDA library is missing.
+
+What is restated here (reference = /root/reference, StephanPreibisch/FourierConvolutionCUDALib):
+
+* place_psf()            -- fftShiftKernel as *called* by convolution3DfftCUDAInPlace
+                            (src/convolution3Dfft.cu:128-166, call site :454-461)
+* convolve_inplace_ref() -- convolution3DfftCUDAInPlace end to end (src/convolution3Dfft.cu:399-578):
+                            R2C(image) * R2C(placed PSF) * 1/N -> C2R, on the grid the caller passed.
+                            The FFT itself lives in NVIDIA cuFFT (closed source, not in /root/reference;
+                            the reference pins no version; this image ships cuFFT 11.4.1 / CUDA 12.9).
+                            Its published contract -- unnormalised forward/inverse DFT -- is restated with
+                            numpy's pocketfft in float64.
+* direct_convolve()      -- tests/test_algorithms.hpp:10-58 (the reference test-suite's CPU oracle),
+                            numpy version for small cases; the C version is oracle/direct_convolve.c.
+* zero_padd helpers      -- tests/padd_utils.h:12-38,99-115,157-171
+* l2norm()               -- tests/test_utils.hpp:75-88 (note: divides by N, not sqrt(N))
+
+Pinning status: pinned.  tests/test_oracle.py checks this module against the closed-form /
+direct-convolution expectations the reference's own tests use (tests/test_gpu_convolve.cpp,
+tests/test_gpu_numerical_stability.cpp) and tests/test_parity_gpu.py checks it -- and the CUDA
+product -- against the reference's own cuFFT build (oracle/_ref, built by oracle/Makefile from the
+sources under /root/reference) on the GPU box.
+"""
+import numpy as np
+
+
+def place_psf(kernel, kernel_dim, im_dim):
+    """Zero-padded, circularly shifted PSF exactly as the reference builds it.
+
+    kernel: flat float array of k0*k1*k2 values; kernel_dim=(k0,k1,k2); im_dim=(d0,d1,d2).
+    Returns the flat float64 array S of d0*d1*d2 values (src/convolution3Dfft.cu:139-165 with the
+    arguments of :454-461: (k0,k1,k2, d0,d1,d2) -- legacy convention, index 2 fastest -- while the
+    result is later consumed with d0 fastest, :474-486).
+    """
+    k0, k1, k2 = (int(v) for v in kernel_dim)
+    d0, d1, d2 = (int(v) for v in im_dim)
+    kernel = np.asarray(kernel).reshape(-1)
+    K = k0 * k1 * k2
+    assert kernel.size == K
+    t = np.arange(K, dtype=np.int64)
+    c = t % k2
+    aux = (t - c) // k2
+    b = aux % k1
+    a = (aux - b) // k1
+    a = a - k0 // 2
+    b = b - k1 // 2
+    c = c - k2 // 2
+    a = np.where(a < 0, a + d0, a)
+    b = np.where(b < 0, b + d1, b)
+    c = np.where(c < 0, c + d2, c)
+    pos = c + d2 * (b + d1 * a)
+    S = np.zeros(d0 * d1 * d2, dtype=np.float64)
+    # the reference scatters with one thread per tap; positions are distinct when k_i <= d_i
+    S[pos] = kernel.astype(np.float64)
+    return S
+
+
+def convolve_inplace_ref(im, im_dim, kernel, kernel_dim):
+    """float64 model of convolution3DfftCUDAInPlace; returns the flat result (same layout as im)."""
+    d0, d1, d2 = (int(v) for v in im_dim)
+    I3 = np.asarray(im, dtype=np.float64).reshape(d2, d1, d0)          # d0 fastest (:417-421,:500-510)
+    S3 = place_psf(kernel, kernel_dim, im_dim).reshape(d2, d1, d0)     # same strides (:474-486)
+    F = np.fft.rfftn(I3) * np.fft.rfftn(S3)                            # :523-536 (scale folded below)
+    out = np.fft.irfftn(F, s=I3.shape, axes=(0, 1, 2))                               # numpy divides by N == scale at :531
+    return out.reshape(-1)
+
+
+def direct_convolve(image, kernel, offset):
+    """tests/test_algorithms.hpp:10-58 on [z][y][x] arrays; float32 accumulate like the reference."""
+    image = np.asarray(image, dtype=np.float32)
+    kernel = np.asarray(kernel, dtype=np.float32)
+    res = np.array(image, dtype=np.float32, copy=True)
+    hk = [s // 2 for s in kernel.shape]
+    flipped = kernel[::-1, ::-1, ::-1]
+    Z, Y, X = image.shape
+    for z in range(offset[0], Z - offset[0]):
+        for y in range(offset[1], Y - offset[1]):
+            for x in range(offset[2], X - offset[2]):
+                acc = np.float32(0)
+                win = image[z - hk[0]:z - hk[0] + kernel.shape[0],
+                            y - hk[1]:y - hk[1] + kernel.shape[1],
+                            x - hk[2]:x - hk[2] + kernel.shape[2]]
+                # same accumulation order as the reference loop nest (kz, ky, kx)
+                for v in (flipped * win).reshape(-1):
+                    acc = np.float32(acc + v)
+                res[z, y, x] = acc
+    return res
+
+
+def zero_padd_extents(image_shape, kernel_shape, factor=1):
+    """tests/padd_utils.h:12-24,99-108: extent_i = image_i + 2*factor*(kernel_i/2)."""
+    return tuple(int(i) + 2 * factor * (int(k) // 2) for i, k in zip(image_shape, kernel_shape))
+
+
+def zero_padd_offsets(kernel_shape, factor=1):
+    """tests/padd_utils.h:26-38,110-114: offset_i = (kernel_i/2)*factor."""
+    return tuple((int(k) // 2) * factor for k in kernel_shape)
+
+
+def zero_padd(image, kernel_shape, factor=1):
+    """tests/padd_utils.h:157-171: embed image in a zero volume at the offsets."""
+    ext = zero_padd_extents(image.shape, kernel_shape, factor)
+    off = zero_padd_offsets(kernel_shape, factor)
+    out = np.zeros(ext, dtype=image.dtype)
+    out[off[0]:off[0] + image.shape[0], off[1]:off[1] + image.shape[1], off[2]:off[2] + image.shape[2]] = image
+    return out, off
+
+
+def crop(padded, off, shape):
+    return padded[off[0]:off[0] + shape[0], off[1]:off[1] + shape[1], off[2]:off[2] + shape[2]]
+
+
+def l2norm(reference, data):
+    """tests/test_utils.hpp:75-88: sqrt(sum (a-b)^2) / N  (N, not sqrt(N))."""
+    a = np.asarray(reference, dtype=np.float32).reshape(-1).astype(np.float64)
+    b = np.asarray(data, dtype=np.float32).reshape(-1).astype(np.float64)
+    return float(np.sqrt(np.sum((b - a) ** 2)) / a.size)

@@ -1,0 +1,62 @@
+"""CPU tests of the FFT engine's math (numpy model) and of the C planner behind the C ABI."""
+import numpy as np
+import pytest
+
+import engine_model as em
+
+LENGTHS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 19, 21, 30, 35, 46, 64, 66, 106, 130, 132, 148, 158, 168,
+           218, 256, 286, 300, 346, 384, 512, 560]
+
+
+@pytest.mark.parametrize("L", [2, 3, 4, 5, 7, 8, 12, 30, 35, 64, 66, 130, 158, 300])
+def test_inplace_dif_and_mirror_inverse(L):
+    rng = np.random.default_rng(L)
+    r = em.factorize(L)
+    x = rng.standard_normal(L) + 1j * rng.standard_normal(L)
+    y = em.fwd_inplace(x, r)
+    assert np.allclose(y, np.fft.fft(x)[em.rev_positions(L, r)])
+    assert np.allclose(em.inv_inplace(y, r), L * x)
+
+
+@pytest.mark.parametrize("n", [2, 4, 6, 10, 16, 30, 64, 70, 130, 512])
+def test_packed_r2c_c2r(n):
+    rng = np.random.default_rng(n)
+    r = em.factorize(n // 2)
+    x = rng.standard_normal(n)
+    X, P = em.r2c_even(x, r)
+    assert np.allclose(np.concatenate([X[P], X[n // 2:]]), np.fft.rfft(x))
+    assert np.allclose(em.c2r_even(X, n, r), n * x)
+
+
+def test_swizzle_is_conflict_free():
+    for p0 in range(0, 256, 8):
+        assert len({em.swz(p0 + i) for i in range(8)}) == 8
+    for a in range(0, 256, 16):
+        assert len({em.swz(a + 2 * i) for i in range(8)}) == 8
+        assert len({em.swz(a + 2 * i + 1) for i in range(8)}) == 8
+
+
+@pytest.mark.parametrize("L", LENGTHS)
+def test_c_planner_matches_model(fc, L):
+    radices, generic = fc.plan_radices(L)
+    assert radices == em.factorize(L)
+    assert int(np.prod(radices)) == L
+    assert generic == any(r not in (1, 2, 3, 4, 5, 7, 8) for r in radices)
+    rev, pos, tw = fc.plan_tables(L)
+    assert np.array_equal(rev, em.rev_positions(L, radices))
+    assert np.array_equal(pos[rev], np.arange(L))
+    assert np.abs(tw - em.twiddles(L)).max() < 1e-7
+
+
+def test_principal_roots_are_exact(fc):
+    _, _, tw = fc.plan_tables(512)
+    assert tw[0] == 1 and tw[128] == -1j and tw[256] == -1 and tw[384] == 1j
+
+
+def test_psf_active_rows_match_oracle_placement(fc):
+    from oracle import fc_oracle as fo
+    for imDim, kDim in (([16, 16, 16], [3, 3, 3]), ([15, 19, 21], [3, 3, 3]), ([46, 46, 106], [31, 31, 91]),
+                        ([20, 12, 10], [5, 4, 3])):
+        S = fo.place_psf(np.ones(int(np.prod(kDim)), np.float32), kDim, imDim)
+        rows = np.unique(np.nonzero(S)[0] // imDim[0])
+        assert np.array_equal(rows, fc.psf_active_rows(imDim, kDim))
