@@ -48,12 +48,21 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+            return
+        # nvidia-smi needs a moment before its first line; wait so the timed region is covered
+        t0 = time.time()
+        while time.time() - t0 < 5.0 and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.05)
 
-    def stop(self):
+    def mark(self):
+        """byte offset of the log now (samples after it were taken after this call)"""
+        return os.path.getsize(self.f.name) if self.p is not None else 0
+
+    def stop(self, start_offset=0):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -63,7 +72,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        self.f.seek(0)
+        self.f.seek(start_offset)
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.f.read().splitlines():
@@ -200,6 +209,7 @@ def run_ours(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier_sync(world)
+    clock_mark = sampler.mark() if rank == 0 else 0
     launches0 = fc.launch_count()
     e0.record()
     for _ in range(args.steps):
@@ -208,7 +218,6 @@ def run_ours(args):
     barrier_sync(world)
     launches = fc.launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1), world, device)
-    clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * n / (ms_step * 1e-3) / 1e6
 
@@ -261,6 +270,8 @@ def run_ours(args):
            "h2d_bytes_per_step": 4 * n + 4 * psf.size, "d2h_bytes_per_step": 4 * n,
            "api": "convolution3DfftCUDAInPlace(host pinned buffers)", "checksum": checksum}
 
+    # clocks were sampled every 50 ms from the start of the timed loop to the end of the e2e loop
+    clocks = sampler.stop(clock_mark) if rank == 0 else None
     line = None
     if rank == 0:
         cpu = cpu_baseline_sample() if (world == 1 and not args.no_cpu_baseline) else None
@@ -343,7 +354,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -217,6 +217,8 @@ ConvPlan::~ConvPlan()
     cudaFree(d_real);
     cudaFree(d_kernel);
     cudaFree(d_rows);
+    cudaFree(d_planes);
+    cudaFree(d_plane_mask);
     if (stream) cudaStreamDestroy(stream);
     if (prev >= 0) cudaSetDevice(prev);
 }
@@ -334,7 +336,15 @@ static ColArgs y_args(ConvPlan& p, float2* data)
     a.tilesPerGroup = (p.g.xcp + 2 * a.txp - 1) / (2 * a.txp);
     a.rowLen = p.g.xcp;
     a.scale = 1.f;
+    a.groupList = nullptr;
+    a.rowMask = nullptr;
     return a;
+}
+
+static void col_pass(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
+{
+    if (a.txp == 8 && col_fast_supported(a.P)) launch_col_fast(a, mode, ngroups, st);
+    else launch_col(a, mode, ngroups, st);
 }
 
 static ColArgs z_args(ConvPlan& p, float2* data)
@@ -351,6 +361,8 @@ static ColArgs z_args(ConvPlan& p, float2* data)
     a.tilesPerGroup = (int)((C + 2 * a.txp - 1) / (2 * a.txp));
     a.rowLen = (int)C;
     a.scale = 1.f;
+    a.groupList = nullptr;
+    a.rowMask = nullptr;
     return a;
 }
 
@@ -377,37 +389,46 @@ void run_forward(ConvPlan& p, const float* d_real, float2* dst, int passes, cuda
     count_launches(1);
     if (passes >= 2) {
         PassTimer t(kPassYFwd, st);
-        launch_col(y_args(p, dst), 0, p.g.nz, st);
+        col_pass(y_args(p, dst), 0, p.g.nz, st);
         count_launches(1);
     }
     if (passes >= 3) {
         PassTimer t(kPassPsfZ, st);
-        launch_col(z_args(p, dst), 0, 1, st);
+        col_pass(z_args(p, dst), 0, 1, st);
         count_launches(1);
     }
 }
 
 void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
 {
+    // PSF pruning: only z planes that receive a tap are non-zero before the z pass.  The x pass runs
+    // on every row of those planes (rows without taps transform to zeros, so nothing needs clearing),
+    // the y pass on those planes only, and the z pass reads only those planes.
     if (std::memcmp(p.psf_key, pdims, sizeof(int) * 6) != 0 || p.d_rows == nullptr) {
-        std::vector<int> rows = psf_active_rows(pdims + 3, pdims, p.g.nx);
+        std::vector<int> arows = psf_active_rows(pdims + 3, pdims, p.g.nx);
+        std::vector<unsigned char> mask((size_t)p.g.nz, 0);
+        for (int r : arows) mask[(size_t)(r / p.g.ny)] = 1;
+        std::vector<int> planes, rows;
+        for (int z = 0; z < p.g.nz; ++z)
+            if (mask[(size_t)z]) {
+                planes.push_back(z);
+                for (int y = 0; y < p.g.ny; ++y) rows.push_back(z * p.g.ny + y);
+            }
+        FC_CUDA(cudaStreamSynchronize(st));  // earlier launches on this stream may still read the old lists
         if (rows.size() > p.rows_cap) {
-            // make sure no earlier launch still reads the old list
-            FC_CUDA(cudaStreamSynchronize(st));
             cudaFree(p.d_rows);
             p.d_rows = nullptr;
             FC_CUDA(cudaMalloc(&p.d_rows, sizeof(int) * rows.size()));
             p.rows_cap = rows.size();
-        } else {
-            FC_CUDA(cudaStreamSynchronize(st));
         }
+        if (!p.d_planes) FC_CUDA(cudaMalloc(&p.d_planes, sizeof(int) * p.g.nz));
+        if (!p.d_plane_mask) FC_CUDA(cudaMalloc(&p.d_plane_mask, (size_t)p.g.nz));
         FC_CUDA(cudaMemcpy(p.d_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice));
+        FC_CUDA(cudaMemcpy(p.d_planes, planes.data(), sizeof(int) * planes.size(), cudaMemcpyHostToDevice));
+        FC_CUDA(cudaMemcpy(p.d_plane_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice));
         p.n_rows = (long long)rows.size();
+        p.n_planes = (int)planes.size();
         std::memcpy(p.psf_key, pdims, sizeof(int) * 6);
-    }
-    {
-        PassTimer t(kPassPsfClear, st);
-        FC_CUDA(cudaMemsetAsync(p.d_H, 0, p.spec_bytes(), st));
     }
     XArgs xa = x_args(p);
     xa.spec = p.d_H;
@@ -426,21 +447,25 @@ void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cuda
     }
     {
         PassTimer t(kPassPsfY, st);
-        launch_col(y_args(p, p.d_H), 0, p.g.nz, st);
+        ColArgs ya = y_args(p, p.d_H);
+        ya.groupList = p.d_planes;
+        col_pass(ya, 0, p.n_planes, st);
     }
     {
         PassTimer t(kPassPsfZ, st);
-        launch_col(z_args(p, p.d_H), 0, 1, st);
+        ColArgs za = z_args(p, p.d_H);
+        za.rowMask = p.d_plane_mask;
+        col_pass(za, 0, 1, st);
     }
     count_launches(3);
 }
 
 void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st)
 {
-    launch_col(z_args(p, spec), 1, 1, st);
+    col_pass(z_args(p, spec), 1, 1, st);
     {
         PassTimer t(kPassYInv, st);
-        launch_col(y_args(p, spec), 1, p.g.nz, st);
+        col_pass(y_args(p, spec), 1, p.g.nz, st);
     }
     XArgs xa = x_args(p);
     xa.spec = spec;
@@ -463,7 +488,7 @@ void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st)
     }
     {
         PassTimer t(kPassYFwd, st);
-        launch_col(y_args(p, p.d_spec), 0, p.g.nz, st);
+        col_pass(y_args(p, p.d_spec), 0, p.g.nz, st);
     }
     ColArgs za = z_args(p, p.d_spec);
     za.H = p.d_H;
@@ -471,11 +496,11 @@ void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st)
     za.scale = 1.0f / (float)((size_t)p.g.nx * (size_t)p.g.ny * (size_t)p.g.nz);
     {
         PassTimer t(kPassZFused, st);
-        launch_col(za, 2, 1, st);
+        col_pass(za, 2, 1, st);
     }
     {
         PassTimer t(kPassYInv, st);
-        launch_col(y_args(p, p.d_spec), 1, p.g.nz, st);
+        col_pass(y_args(p, p.d_spec), 1, p.g.nz, st);
     }
     xa.out_real = d_real;
     {

@@ -44,9 +44,12 @@ struct ConvPlan {
     size_t kernel_cap = 0;
     // PSF pruning lists, cached per kernel shape / placement dims
     int psf_key[6] = {0, 0, 0, 0, 0, 0};
-    int* d_rows = nullptr;
+    int* d_rows = nullptr;       // rows (z*ny+y) the PSF x pass processes: every row of every active plane
     long long n_rows = 0;
     size_t rows_cap = 0;
+    int* d_planes = nullptr;     // z planes that hold >= 1 tap
+    int n_planes = 0;
+    unsigned char* d_plane_mask = nullptr;   // [nz] 1 = plane active
     cudaStream_t stream = nullptr;   // used for host-pointer calls
     std::mutex mu;
     unsigned long long last_use = 0;

@@ -1,0 +1,335 @@
+// Fast strided-axis (y / z) passes for sm_100a: the first stage reads its butterfly inputs straight
+// from global memory into registers, the last stage writes its outputs straight to global memory,
+// so the shared-memory tile is touched by only 2(ns-1) tile transfers instead of 2ns+2.
+//
+// Tile = L positions x 16 pencils (8 float4 column pairs, one 128-byte line per position).  Each
+// quarter-warp (8 lanes = 8 column pairs) reads or writes one full 128-byte line of global memory
+// per access, whatever the row order, so natural frequency order in global memory is free.
+//
+// Fused mode (image z pass): forward stages, then  last forward stage -> x H * 1/N -> first inverse
+// stage  in registers (modulateAndNormalize_kernel of /root/reference/src/convolution3Dfft.cu:41-62
+// fused between the two transforms), then the inverse stages.  The image spectrum makes no extra
+// trip through HBM.
+//
+// Loads are issued in batches of ~16 float4 per thread before any arithmetic so that a CTA keeps
+// its whole tile in flight (HBM latency x bandwidth needs ~44 KB in flight per SM).
+#include "fft_engine.cuh"
+#include "fft_kernels.h"
+
+namespace fcb200 {
+
+namespace {
+
+template <int R>
+struct Batch {
+    static constexpr int U = (R >= 7) ? 2 : (R == 5 ? 3 : (R >= 3 ? 4 : 8));
+};
+
+__device__ __forceinline__ float4 ldg_stream(const float2* p)
+{
+    return __ldcs(reinterpret_cast<const float4*>(p));   // read-once data: evict-first
+}
+
+template <int R>
+__device__ __forceinline__ void split(const float4* v, float* ar, float* ai, float* br, float* bi)
+{
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        ar[k] = v[k].x;
+        ai[k] = v[k].y;
+        br[k] = v[k].z;
+        bi[k] = v[k].w;
+    }
+}
+
+// ---- first forward stage: global (natural rows) -> registers -> smem -----------------------------
+template <int R>
+__device__ __forceinline__ void first_fwd(const float2* __restrict__ base, long long stride, float4* __restrict__ sm,
+                                          const float2* __restrict__ tw, int L, int cp, int w, int W,
+                                          const unsigned char* __restrict__ rowMask)
+{
+    constexpr int U = Batch<R>::U;
+    const int S = L / R;  // Li == L, beta == 0, j == b
+    for (int b0 = w; b0 < S; b0 += U * W) {
+        float4 v[U][R];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = b0 + u * W;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int row = j + k * S;
+                v[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < S && (rowMask == nullptr || rowMask[row])) v[u][k] = ldg_stream(base + (size_t)row * stride);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = b0 + u * W;
+            if (j < S) {
+                float ar[R], ai[R], br[R], bi[R];
+                split<R>(v[u], ar, ai, br, bi);
+                Dft<R>::run(ar, ai);
+                Dft<R>::run(br, bi);
+#pragma unroll
+                for (int m = 1; m < R; ++m) {
+                    const float2 t = tw[j * m];
+                    cmul(ar[m], ai[m], t.x, t.y);
+                    cmul(br[m], bi[m], t.x, t.y);
+                }
+#pragma unroll
+                for (int m = 0; m < R; ++m) sm[(j + m * S) * 8 + cp] = make_float4(ar[m], ai[m], br[m], bi[m]);
+            }
+        }
+    }
+}
+
+// ---- first inverse stage: global (natural rows) -> registers -> smem (positions) ---------------
+template <int R>
+__device__ __forceinline__ void first_inv(const float2* __restrict__ base, long long stride, float4* __restrict__ sm,
+                                          const int* __restrict__ rev, int L, int cp, int w, int W)
+{
+    constexpr int U = Batch<R>::U;
+    const int nb = L / R;
+    const int fs = L / R;  // frequency step between the R inputs of one butterfly
+    for (int b0 = w; b0 < nb; b0 += U * W) {
+        float4 v[U][R];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int b = b0 + u * W;
+            if (b < nb) {
+                const int k0 = __ldg(rev + b * R);
+#pragma unroll
+                for (int k = 0; k < R; ++k) v[u][k] = ldg_stream(base + (size_t)(k0 + k * fs) * stride);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int b = b0 + u * W;
+            if (b < nb) {
+                float ar[R], ai[R], br[R], bi[R];
+                split<R>(v[u], ar, ai, br, bi);
+                Dft<R>::run(ai, ar);
+                Dft<R>::run(bi, br);
+#pragma unroll
+                for (int m = 0; m < R; ++m) sm[(b * R + m) * 8 + cp] = make_float4(ar[m], ai[m], br[m], bi[m]);
+            }
+        }
+    }
+}
+
+// ---- last forward stage: smem (positions) -> registers -> global (natural rows) ----------------
+template <int R>
+__device__ __forceinline__ void last_fwd(float2* __restrict__ base, long long stride, const float4* __restrict__ sm,
+                                         const int* __restrict__ rev, int L, int cp, int w, int W)
+{
+    const int nb = L / R;
+    const int fs = L / R;
+    for (int b = w; b < nb; b += W) {
+        float ar[R], ai[R], br[R], bi[R];
+        const int k0 = __ldg(rev + b * R);
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const float4 v = sm[(b * R + k) * 8 + cp];
+            ar[k] = v.x;
+            ai[k] = v.y;
+            br[k] = v.z;
+            bi[k] = v.w;
+        }
+        Dft<R>::run(ar, ai);
+        Dft<R>::run(br, bi);
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+            *reinterpret_cast<float4*>(base + (size_t)(k0 + m * fs) * stride) = make_float4(ar[m], ai[m], br[m], bi[m]);
+    }
+}
+
+// ---- last inverse stage: smem -> registers -> global (natural rows) -----------------------------
+template <int R>
+__device__ __forceinline__ void last_inv(float2* __restrict__ base, long long stride, const float4* __restrict__ sm,
+                                         const float2* __restrict__ tw, int L, int cp, int w, int W)
+{
+    const int S = L / R;  // Li == L, j == b
+    for (int j = w; j < S; j += W) {
+        float ar[R], ai[R], br[R], bi[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const float4 v = sm[(j + k * S) * 8 + cp];
+            ar[k] = v.x;
+            ai[k] = v.y;
+            br[k] = v.z;
+            bi[k] = v.w;
+        }
+#pragma unroll
+        for (int k = 1; k < R; ++k) {
+            const float2 t = tw[j * k];
+            cmulc(ar[k], ai[k], t.x, t.y);
+            cmulc(br[k], bi[k], t.x, t.y);
+        }
+        Dft<R>::run(ai, ar);
+        Dft<R>::run(bi, br);
+#pragma unroll
+        for (int m = 0; m < R; ++m)
+            *reinterpret_cast<float4*>(base + (size_t)(j + m * S) * stride) = make_float4(ar[m], ai[m], br[m], bi[m]);
+    }
+}
+
+// ---- fused middle: last forward stage, multiply by H and 1/N, first inverse stage --------------
+template <int R>
+__device__ __forceinline__ void mid_fused(const float2* __restrict__ hbase, long long stride, float4* __restrict__ sm,
+                                          const int* __restrict__ rev, int L, int cp, int w, int W, float c)
+{
+    constexpr int U = Batch<R>::U;
+    const int nb = L / R;
+    const int fs = L / R;
+    for (int b0 = w; b0 < nb; b0 += U * W) {
+        float4 h[U][R];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int b = b0 + u * W;
+            if (b < nb) {
+                const int k0 = __ldg(rev + b * R);
+#pragma unroll
+                for (int k = 0; k < R; ++k) h[u][k] = ldg_stream(hbase + (size_t)(k0 + k * fs) * stride);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int b = b0 + u * W;
+            if (b < nb) {
+                float ar[R], ai[R], br[R], bi[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const float4 v = sm[(b * R + k) * 8 + cp];
+                    ar[k] = v.x;
+                    ai[k] = v.y;
+                    br[k] = v.z;
+                    bi[k] = v.w;
+                }
+                Dft<R>::run(ar, ai);
+                Dft<R>::run(br, bi);
+                // Dst = c * (Src * Dst), Src = PSF spectrum (reference mulAndScale, :41-45)
+#pragma unroll
+                for (int m = 0; m < R; ++m) {
+                    const float4 hh = h[u][m];
+                    const float xr = c * (hh.x * ar[m] - hh.y * ai[m]);
+                    const float xi = c * (hh.y * ar[m] + hh.x * ai[m]);
+                    const float yr = c * (hh.z * br[m] - hh.w * bi[m]);
+                    const float yi = c * (hh.w * br[m] + hh.z * bi[m]);
+                    ar[m] = xr;
+                    ai[m] = xi;
+                    br[m] = yr;
+                    bi[m] = yi;
+                }
+                Dft<R>::run(ai, ar);
+                Dft<R>::run(bi, br);
+#pragma unroll
+                for (int m = 0; m < R; ++m) sm[(b * R + m) * 8 + cp] = make_float4(ar[m], ai[m], br[m], bi[m]);
+            }
+        }
+    }
+}
+
+#define FC_RADIX_SWITCH(R, CALL)            \
+    switch (R) {                            \
+        case 2: { constexpr int RR = 2; CALL; } break; \
+        case 3: { constexpr int RR = 3; CALL; } break; \
+        case 4: { constexpr int RR = 4; CALL; } break; \
+        case 5: { constexpr int RR = 5; CALL; } break; \
+        case 7: { constexpr int RR = 7; CALL; } break; \
+        default: { constexpr int RR = 8; CALL; } break; \
+    }
+
+template <bool INV>
+__device__ __forceinline__ void mid_stage(int R, float4* sm, const float2* tw, int L, int Li, int cp, int w, int W)
+{
+    FC_RADIX_SWITCH(R, (stage_smem<RR, INV, false>(sm, tw, L, Li, cp, w, W, 8)));
+}
+
+}  // namespace
+
+// MODE 0 forward, 1 inverse, 2 fused (forward, x H x scale, inverse).  Requires a plan with
+// ns >= 2 stages, all radices in {2,3,4,5,7,8}, and a tile of 8 column pairs.
+template <int MODE>
+__global__ void __launch_bounds__(kColThreads, 2) col_fast_kernel(ColArgs a)
+{
+    extern __shared__ float4 smem[];
+    const int L = a.P.L;
+    const int ns = a.P.ns;
+    float4* sm = smem;
+    float2* tw_s = reinterpret_cast<float2*>(sm + (size_t)L * 8);
+
+    const int t = threadIdx.x;
+    const int cp = t & 7, w = t >> 3, W = blockDim.x >> 3;
+    const int gi = blockIdx.x / a.tilesPerGroup;
+    const int tt = blockIdx.x - gi * a.tilesPerGroup;
+    const long long group = a.groupList ? (long long)a.groupList[gi] : (long long)gi;
+    const int col0 = tt * 16;
+    const int npairs = min(8, (a.rowLen - col0) >> 1);
+    const bool active = cp < npairs;
+    const size_t off = (size_t)group * a.groupStride + col0 + 2 * cp;
+    float2* base = a.data + off;
+
+    for (int i = t; i < L; i += blockDim.x) tw_s[i] = __ldg(a.P.tw + i);
+    __syncthreads();
+
+    const int Rf = a.P.radix[0];
+    const int Rl = a.P.radix[ns - 1];
+
+    if (MODE == 0 || MODE == 2) {
+        if (active) FC_RADIX_SWITCH(Rf, (first_fwd<RR>(base, a.stride, sm, tw_s, L, cp, w, W, a.rowMask)));
+        __syncthreads();
+        int Li = L / Rf;
+        for (int s = 1; s < ns - 1; ++s) {
+            const int R = a.P.radix[s];
+            if (active) mid_stage<false>(R, sm, tw_s, L, Li, cp, w, W);
+            Li /= R;
+            __syncthreads();
+        }
+        if (MODE == 0) {
+            if (active) FC_RADIX_SWITCH(Rl, (last_fwd<RR>(base, a.stride, sm, a.P.rev, L, cp, w, W)));
+            return;
+        }
+        if (active) FC_RADIX_SWITCH(Rl, (mid_fused<RR>(a.H + off, a.stride, sm, a.P.rev, L, cp, w, W, a.scale)));
+        __syncthreads();
+    } else {
+        if (active) FC_RADIX_SWITCH(Rl, (first_inv<RR>(base, a.stride, sm, a.P.rev, L, cp, w, W)));
+        __syncthreads();
+    }
+    // inverse stages ns-2 .. 1 in shared memory, then stage 0 to global
+    int Li = Rl;
+    for (int s = ns - 2; s >= 1; --s) {
+        const int R = a.P.radix[s];
+        Li *= R;
+        if (active) mid_stage<true>(R, sm, tw_s, L, Li, cp, w, W);
+        __syncthreads();
+    }
+    if (active) FC_RADIX_SWITCH(Rf, (last_inv<RR>(base, a.stride, sm, tw_s, L, cp, w, W)));
+}
+
+bool col_fast_supported(const AxisPlanDev& P)
+{
+    if (P.generic || P.ns < 2) return false;
+    const size_t need = (size_t)P.L * 8 * sizeof(float4) + (size_t)P.L * sizeof(float2);
+    return need <= (size_t)kMaxDynSmem;
+}
+
+void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
+{
+    const size_t smem = (size_t)a.P.L * 8 * sizeof(float4) + (size_t)a.P.L * sizeof(float2);
+    const long long grid = ngroups * a.tilesPerGroup;
+    if (grid == 0) return;
+    if (grid > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
+    auto go = [&](auto kernel) {
+        if (smem > 48 * 1024)
+            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<(unsigned)grid, kColThreads, smem, st>>>(a);
+    };
+    switch (mode) {
+        case 0: go(col_fast_kernel<0>); break;
+        case 1: go(col_fast_kernel<1>); break;
+        default: go(col_fast_kernel<2>); break;
+    }
+    FC_CUDA_KERNEL();
+}
+
+}  // namespace fcb200

@@ -59,6 +59,21 @@ __device__ __forceinline__ int xslot(int lrow, int pos)
     return pos * 16 + ((((lrow >> 1) ^ swz8(pos)) << 1) | (lrow & 1));
 }
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 __device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* tw_g, int L)
 {
     for (int i = threadIdx.x; i < L; i += blockDim.x) tw_s[i] = __ldg(tw_g + i);
@@ -98,10 +113,14 @@ __global__ void __launch_bounds__(kColThreads) x_fwd_kernel(XArgs a)
             const long long li = row0 + lrow;
             const long long grow = (li < a.nrows) ? (a.rowList ? (long long)a.rowList[li] : li) : -1;
             float2 v = make_float2(0.f, 0.f);
+            if (LOADER == 0 && !g.odd && pos < npos && grow >= 0) {
+                // asynchronous 8-byte copies: every thread keeps all its loads in flight, no registers
+                cp_async8(&A2[xslot(lrow, pos)], reinterpret_cast<const float2*>(a.in_real + grow * g.nx) + pos);
+                continue;
+            }
             if (pos < npos && grow >= 0) {
                 if (LOADER == 0) {
-                    if (g.odd) v.x = __ldg(a.in_real + grow * g.nx + pos);
-                    else v = __ldg(reinterpret_cast<const float2*>(a.in_real + grow * g.nx) + pos);
+                    v.x = __ldg(a.in_real + grow * g.nx + pos);
                 } else {
                     if (g.odd) v.x = psf_tap(a.psf, grow * g.nx + pos);
                     else {
@@ -113,6 +132,7 @@ __global__ void __launch_bounds__(kColThreads) x_fwd_kernel(XArgs a)
             if (pos < npos) A2[xslot(lrow, pos)] = v;
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     float4* cur = engine_run<false, true>(a.P, A, B, tw_s, cp, w, W, 8, true);
@@ -210,6 +230,10 @@ __global__ void __launch_bounds__(kColThreads) x_inv_kernel(XArgs a)
             const int lrow = 2 * rp + rr;
             const long long grow = row0 + lrow;
             if (pos < g.xc) {
+                if (!g.odd && grow < a.nrows) {
+                    cp_async8(&A2[xslot(lrow, pos)], a.spec + grow * g.xcp + pos);
+                    continue;
+                }
                 float2 v = make_float2(0.f, 0.f);
                 if (grow < a.nrows) v = __ldg(a.spec + grow * g.xcp + pos);
                 if (!g.odd) {
@@ -221,6 +245,7 @@ __global__ void __launch_bounds__(kColThreads) x_inv_kernel(XArgs a)
             }
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     if (!g.odd) {
@@ -299,8 +324,9 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
 
     const int t = threadIdx.x;
     const int cp = t % txp, w = t / txp, W = blockDim.x / txp;
-    const long long group = blockIdx.x / a.tilesPerGroup;
-    const int tt = blockIdx.x - (int)group * a.tilesPerGroup;
+    const int gi = blockIdx.x / a.tilesPerGroup;
+    const int tt = blockIdx.x - gi * a.tilesPerGroup;
+    const long long group = a.groupList ? (long long)a.groupList[gi] : (long long)gi;
     const int col0 = tt * 2 * txp;
     const int npairs = min(txp, (a.rowLen - col0) >> 1);
     const bool active = cp < npairs;
@@ -311,11 +337,12 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
 
     if (active) {
         for (int r = w; r < L; r += W) {
-            const float4 v = *reinterpret_cast<const float4*>(base + (size_t)r * a.stride);
             const int p = (MODE == 1) ? __ldg(a.P.pos + r) : r;
-            A[p * txp + cp] = v;
+            if (a.rowMask != nullptr && a.rowMask[r] == 0) A[p * txp + cp] = make_float4(0.f, 0.f, 0.f, 0.f);
+            else cp_async16(&A[p * txp + cp], base + (size_t)r * a.stride);
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     float4* cur;

@@ -26,6 +26,8 @@ struct ColArgs {
     int rowLen;             // float2 elements per group row (xcp for y, ny*xcp for z); even
     int txp;                // column pairs per tile
     float scale;            // fused mode: 1/N
+    const int* groupList;   // optional: group index of each launched group (PSF pruning: active planes)
+    const unsigned char* rowMask;  // optional, forward only: rowMask[r]==0 => input row r is all zero, not read
 };
 
 bool x_pass_supported(const Geometry& g, const AxisPlanDev& P);
@@ -33,5 +35,8 @@ int col_pick_txp(const AxisPlanDev& P);
 void launch_x_fwd(const XArgs& a, bool psf, cudaStream_t st);
 void launch_x_inv(const XArgs& a, cudaStream_t st);
 void launch_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
+// fast path (fft_col_fast.cu): first/last stage fused with the global loads/stores
+bool col_fast_supported(const AxisPlanDev& P);
+void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
 
 }  // namespace fcb200
