@@ -109,33 +109,16 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
     if (!force_async) FC_CUDA(cudaStreamSynchronize(st));
 }
 
-// natural-order host spectrum [nz][ny][xc]  <->  device layout [nz][ny][xcp] (kx in position order)
-std::vector<int> xperm(const ConvPlan& p)
-{
-    const Geometry& g = p.g;
-    std::vector<int> perm(g.xc);
-    if (g.odd) {
-        for (int k = 0; k < g.xc; ++k) perm[k] = k;
-    } else {
-        std::vector<int> rev, pos;
-        std::vector<float2> tw;
-        build_tables(g.M, p.px.radix, rev, pos, tw);
-        for (int k = 0; k < g.M; ++k) perm[k] = pos[k];
-        perm[g.M] = g.M;
-    }
-    return perm;
-}
-
+// host spectrum [nz][ny][xc] (what numpy.fft.rfftn returns)  <->  device layout [nz][ny][xcp]
 void download_spectrum(ConvPlan& p, const float2* d_spec, float* out, cudaStream_t st)
 {
     const Geometry& g = p.g;
     std::vector<float2> h((size_t)g.nz * g.ny * g.xcp);
     FC_CUDA(cudaMemcpyAsync(h.data(), d_spec, h.size() * sizeof(float2), cudaMemcpyDeviceToHost, st));
     FC_CUDA(cudaStreamSynchronize(st));
-    std::vector<int> perm = xperm(p);
     float2* o = reinterpret_cast<float2*>(out);
     for (size_t r = 0; r < (size_t)g.nz * g.ny; ++r)
-        for (int k = 0; k < g.xc; ++k) o[r * g.xc + k] = h[r * g.xcp + perm[k]];
+        for (int k = 0; k < g.xc; ++k) o[r * g.xc + k] = h[r * g.xcp + k];
 }
 
 }  // namespace
@@ -367,10 +350,9 @@ void fcb200_debug_irfft3(const float* spec, const int* imDim, imageType* out, in
         ConvPlan& p = *plan;
         const Geometry& g = p.g;
         std::vector<float2> h((size_t)g.nz * g.ny * g.xcp, make_float2(0.f, 0.f));
-        std::vector<int> perm = xperm(p);
         const float2* s = reinterpret_cast<const float2*>(spec);
         for (size_t r = 0; r < (size_t)g.nz * g.ny; ++r)
-            for (int k = 0; k < g.xc; ++k) h[r * g.xcp + perm[k]] = s[r * g.xc + k];
+            for (int k = 0; k < g.xc; ++k) h[r * g.xcp + k] = s[r * g.xc + k];
         if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
         FC_CUDA(cudaMemcpyAsync(p.d_spec, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice, p.stream));
         run_inverse(p, p.d_spec, p.d_real, p.stream);

@@ -28,9 +28,8 @@ struct AxisPlanDev {
 //   real volume  : [nz][ny][nx] floats, nx fastest (reference: imDim = {nx, ny, nz},
 //                  /root/reference/src/convolution3Dfft.cu:417-421)
 //   spectrum     : [nz][ny][xcp] float2, xc = nx/2+1 valid bins per row, xcp = xc rounded up to 4
-//                  (32-byte sector alignment of every row); kx is stored in *engine position order*
-//                  for even nx (position M = nx/2 is the Nyquist bin), natural order for odd nx;
-//                  ky and kz are in natural order.
+//                  (32-byte sector alignment of every row); kx, ky and kz are all in natural order,
+//                  i.e. the buffer is numpy.fft.rfftn of the volume with padded rows.
 struct Geometry {
     int nx, ny, nz;
     int xc, xcp;

@@ -16,13 +16,17 @@
 #include "fft_engine.cuh"
 #include "fft_kernels.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace fcb200 {
 
 namespace {
 
-template <int R>
+// U butterflies of radix R are loaded together: about LOADS float4 in flight per thread
+template <int R, int LOADS>
 struct Batch {
-    static constexpr int U = (R >= 7) ? 2 : (R == 5 ? 3 : (R >= 3 ? 4 : 8));
+    static constexpr int U = (LOADS / R) < 1 ? 1 : (LOADS / R);
 };
 
 __device__ __forceinline__ float4 ldg_stream(const float2* p)
@@ -43,12 +47,12 @@ __device__ __forceinline__ void split(const float4* v, float* ar, float* ai, flo
 }
 
 // ---- first forward stage: global (natural rows) -> registers -> smem -----------------------------
-template <int R>
+template <int R, int LOADS>
 __device__ __forceinline__ void first_fwd(const float2* __restrict__ base, long long stride, float4* __restrict__ sm,
                                           const float2* __restrict__ tw, int L, int cp, int w, int W,
                                           const unsigned char* __restrict__ rowMask)
 {
-    constexpr int U = Batch<R>::U;
+    constexpr int U = Batch<R, LOADS>::U;
     const int S = L / R;  // Li == L, beta == 0, j == b
     for (int b0 = w; b0 < S; b0 += U * W) {
         float4 v[U][R];
@@ -84,11 +88,11 @@ __device__ __forceinline__ void first_fwd(const float2* __restrict__ base, long 
 }
 
 // ---- first inverse stage: global (natural rows) -> registers -> smem (positions) ---------------
-template <int R>
+template <int R, int LOADS>
 __device__ __forceinline__ void first_inv(const float2* __restrict__ base, long long stride, float4* __restrict__ sm,
                                           const int* __restrict__ rev, int L, int cp, int w, int W)
 {
-    constexpr int U = Batch<R>::U;
+    constexpr int U = Batch<R, LOADS>::U;
     const int nb = L / R;
     const int fs = L / R;  // frequency step between the R inputs of one butterfly
     for (int b0 = w; b0 < nb; b0 += U * W) {
@@ -174,11 +178,11 @@ __device__ __forceinline__ void last_inv(float2* __restrict__ base, long long st
 }
 
 // ---- fused middle: last forward stage, multiply by H and 1/N, first inverse stage --------------
-template <int R>
+template <int R, int LOADS>
 __device__ __forceinline__ void mid_fused(const float2* __restrict__ hbase, long long stride, float4* __restrict__ sm,
                                           const int* __restrict__ rev, int L, int cp, int w, int W, float c)
 {
-    constexpr int U = Batch<R>::U;
+    constexpr int U = Batch<R, LOADS>::U;
     const int nb = L / R;
     const int fs = L / R;
     for (int b0 = w; b0 < nb; b0 += U * W) {
@@ -249,8 +253,8 @@ __device__ __forceinline__ void mid_stage(int R, float4* sm, const float2* tw, i
 
 // MODE 0 forward, 1 inverse, 2 fused (forward, x H x scale, inverse).  Requires a plan with
 // ns >= 2 stages, all radices in {2,3,4,5,7,8}, and a tile of 8 column pairs.
-template <int MODE>
-__global__ void __launch_bounds__(kColThreads, 2) col_fast_kernel(ColArgs a)
+template <int MODE, int MAXT, int MINB, int LOADS>
+__global__ void __launch_bounds__(MAXT, MINB) col_fast_kernel(ColArgs a)
 {
     extern __shared__ float4 smem[];
     const int L = a.P.L;
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(kColThreads, 2) col_fast_kernel(ColArgs a)
     const int Rl = a.P.radix[ns - 1];
 
     if (MODE == 0 || MODE == 2) {
-        if (active) FC_RADIX_SWITCH(Rf, (first_fwd<RR>(base, a.stride, sm, tw_s, L, cp, w, W, a.rowMask)));
+        if (active) FC_RADIX_SWITCH(Rf, (first_fwd<RR, LOADS>(base, a.stride, sm, tw_s, L, cp, w, W, a.rowMask)));
         __syncthreads();
         int Li = L / Rf;
         for (int s = 1; s < ns - 1; ++s) {
@@ -289,10 +293,10 @@ __global__ void __launch_bounds__(kColThreads, 2) col_fast_kernel(ColArgs a)
             if (active) FC_RADIX_SWITCH(Rl, (last_fwd<RR>(base, a.stride, sm, a.P.rev, L, cp, w, W)));
             return;
         }
-        if (active) FC_RADIX_SWITCH(Rl, (mid_fused<RR>(a.H + off, a.stride, sm, a.P.rev, L, cp, w, W, a.scale)));
+        if (active) FC_RADIX_SWITCH(Rl, (mid_fused<RR, LOADS>(a.H + off, a.stride, sm, a.P.rev, L, cp, w, W, a.scale)));
         __syncthreads();
     } else {
-        if (active) FC_RADIX_SWITCH(Rl, (first_inv<RR>(base, a.stride, sm, a.P.rev, L, cp, w, W)));
+        if (active) FC_RADIX_SWITCH(Rl, (first_inv<RR, LOADS>(base, a.stride, sm, a.P.rev, L, cp, w, W)));
         __syncthreads();
     }
     // inverse stages ns-2 .. 1 in shared memory, then stage 0 to global
@@ -313,22 +317,47 @@ bool col_fast_supported(const AxisPlanDev& P)
     return need <= (size_t)kMaxDynSmem;
 }
 
+// Tuning knobs (read once from the environment; defaults chosen from the sweep in profiles/):
+//   FCB200_COL_VARIANT  0: <=128 regs, 16 loads in flight   1: <=80 regs, 8 loads   2: <=64 regs, 8 loads (512 thr)
+//   FCB200_COL_THREADS  CTA size (multiple of 32); 0 = derived from the transform length
+static int env_int(const char* name, int dflt)
+{
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
 void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
+    static const int variant = env_int("FCB200_COL_VARIANT", 0);
+    static const int threads_env = env_int("FCB200_COL_THREADS", 0);
     const size_t smem = (size_t)a.P.L * 8 * sizeof(float4) + (size_t)a.P.L * sizeof(float2);
     const long long grid = ngroups * a.tilesPerGroup;
     if (grid == 0) return;
     if (grid > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
+    int threads = threads_env;
+    if (threads <= 0) {
+        // one radix-8 butterfly per worker and stage: L/8 workers of 8 lanes, within [128, maxT]
+        threads = ((a.P.L + 31) / 32) * 32;
+    }
+    const int maxT = (variant == 2) ? 512 : 256;
+    threads = std::max(64, std::min(threads, maxT));
     auto go = [&](auto kernel) {
         if (smem > 48 * 1024)
             FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<(unsigned)grid, kColThreads, smem, st>>>(a);
+        kernel<<<(unsigned)grid, threads, smem, st>>>(a);
     };
-    switch (mode) {
-        case 0: go(col_fast_kernel<0>); break;
-        case 1: go(col_fast_kernel<1>); break;
-        default: go(col_fast_kernel<2>); break;
+#define FC_GO(M)                                                     \
+    switch (variant) {                                               \
+        case 1: go(col_fast_kernel<M, 256, 3, 8>); break;            \
+        case 2: go(col_fast_kernel<M, 512, 2, 8>); break;            \
+        default: go(col_fast_kernel<M, 256, 2, 16>); break;          \
     }
+    switch (mode) {
+        case 0: FC_GO(0); break;
+        case 1: FC_GO(1); break;
+        default: FC_GO(2); break;
+    }
+#undef FC_GO
     FC_CUDA_KERNEL();
 }
 

@@ -42,8 +42,10 @@ __device__ __forceinline__ void stage_smem(float4* __restrict__ buf, const float
     const int S = Li / R;
     const int nb = L / R;
     const int tstep = L / Li;
+    const float invS = 1.0f / (float)S;
     for (int b = w; b < nb; b += W) {
-        const int beta = b / S;
+        // b / S without an integer division: exact for b < 2^16 (checked exhaustively on the host)
+        const int beta = __float2int_rz(((float)b + 0.5f) * invS);
         const int j = b - beta * S;
         const int base = beta * Li + j;
         float ar[R], ai[R], br[R], bi[R];
@@ -93,10 +95,11 @@ __device__ __forceinline__ void stage_generic(const float4* __restrict__ src, fl
     const int S = Li / p;
     const int tstep = L / Li;
     const int rstep = L / p;
+    const float invS = 1.0f / (float)S, invLi = 1.0f / (float)Li;
     for (int o = w; o < L; o += W) {
-        const int beta = o / Li;
+        const int beta = __float2int_rz(((float)o + 0.5f) * invLi);
         const int r = o - beta * Li;
-        const int m = r / S;
+        const int m = __float2int_rz(((float)r + 0.5f) * invS);
         const int j = r - m * S;
         const int base = beta * Li + j;
         // forward: y_m = w_Li^{j m} * sum_k x_k w_p^{k m}

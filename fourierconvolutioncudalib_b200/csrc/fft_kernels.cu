@@ -3,9 +3,10 @@
 //   x_fwd_kernel   real rows -> half spectrum rows (R2C along x); image loader or PSF gather loader
 //                  (PSF zero-pad + circular shift of /root/reference/src/convolution3Dfft.cu:128-166
 //                  fused into the load, never materialising the padded PSF)
-//   col_kernel     strided-axis complex passes (y and z): forward, inverse, or fused
+//   col_kernel     strided-axis complex passes (y and z), generic version: forward, inverse, or fused
 //                  forward -> x H * 1/N -> inverse (modulateAndNormalize_kernel of
-//                  /root/reference/src/convolution3Dfft.cu:41-62 fused between the two z transforms)
+//                  /root/reference/src/convolution3Dfft.cu:41-62 fused between the two z transforms);
+//                  the fast version lives in fft_col_fast.cu
 //   x_inv_kernel   half spectrum rows -> real rows (C2R along x)
 //
 // Together they replace cufftExecR2C x2 + modulateAndNormalize_kernel + cufftExecC2R
@@ -13,6 +14,9 @@
 // :561-575), which do not exist here: the X passes read and write dense rows directly.
 #include "fft_engine.cuh"
 #include "fft_kernels.h"
+
+#include <algorithm>
+#include <cstdlib>
 
 namespace fcb200 {
 
@@ -53,12 +57,6 @@ __device__ __forceinline__ float psf_tap(const PsfGather& g, long long flat)
     return __ldg(g.kernel + (c + g.k2 * (b + g.k1 * a)));
 }
 
-// float2 slot of (local row, position) in the swizzled X-pass tile (16 float2 per tile row)
-__device__ __forceinline__ int xslot(int lrow, int pos)
-{
-    return pos * 16 + ((((lrow >> 1) ^ swz8(pos)) << 1) | (lrow & 1));
-}
-
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -80,123 +78,127 @@ __device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* tw_g, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// X forward: R2C along x for 16 rows per CTA
+// X passes.  16 rows per CTA, two shared-memory tiles:
+//   row tile    [16 rows][P float2], P odd: filled / drained with lanes running along x (coalesced,
+//               conflict-free), read / written column-wise with lanes running along rows
+//               (conflict-free because P is odd);
+//   engine tile [L positions][16 rows] float2 = [L][8] float4: the layout of fft_engine.cuh.
+// Moving data between the two tiles is the transposition; kx comes out in natural order.
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int x_row_pitch(int L, int xc) { return (L > xc ? L : xc) | 1; }
+
+// engine tile viewed as float2: (position, local row)
+__device__ __forceinline__ int eidx(int pos, int lrow) { return pos * 16 + lrow; }
+
+struct XSmem {
+    float2* rowt;
+    float4* A;
+    float4* B;
+    float2* tw;
+    int P;
+};
+
+__device__ __forceinline__ XSmem x_carve(float4* smem, const Geometry& g, const AxisPlanDev& pl)
+{
+    XSmem s;
+    s.P = x_row_pitch(pl.L, g.xc);
+    s.A = smem;                                                   // engine tile first: 16-byte aligned
+    s.B = pl.generic ? (s.A + (size_t)pl.L * 8) : nullptr;
+    s.tw = reinterpret_cast<float2*>(s.A + (size_t)pl.L * 8 * (pl.generic ? 2 : 1));
+    s.rowt = s.tw + pl.L;
+    return s;
+}
+
 template <int LOADER>  // 0: dense real rows, 1: PSF gather
 __global__ void __launch_bounds__(kColThreads) x_fwd_kernel(XArgs a)
 {
     extern __shared__ float4 smem[];
     const Geometry g = a.g;
-    const int L = a.P.L;
-    const int tile_rows = g.odd ? L : (g.M + 1);
-    float4* A = smem;
-    float4* B = a.P.generic ? (A + (size_t)tile_rows * 8) : nullptr;
-    float2* tw_s = reinterpret_cast<float2*>(A + (size_t)tile_rows * 8 * (a.P.generic ? 2 : 1));
+    const int L = a.P.L;  // complex transform length: nx/2 (even nx) or nx (odd nx)
+    const XSmem sm = x_carve(smem, g, a.P);
+    const int P = sm.P;
+    float2* rowt = sm.rowt;
 
     const int t = threadIdx.x;
     const int cp = t & 7, w = t >> 3, W = blockDim.x >> 3;
     const int lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
-    const int pl = lane & 7, rr = (lane >> 3) & 1, ph = lane >> 4;
     const long long row0 = (long long)blockIdx.x * 16;
 
-    load_twiddles(tw_s, a.P.tw, L);
+    load_twiddles(sm.tw, a.P.tw, L);
 
-    // ---- transposing load: global rows -> tile[position][row]
-    {
-        float2* A2 = reinterpret_cast<float2*>(A);
-        const int npos = L;
-        const int nchunks = (npos + 15) >> 4;
-        for (int u = warp; u < 8 * nchunks; u += nwarps) {
-            const int rp = u / nchunks, c = u - rp * nchunks;
-            const int pos = c * 16 + ph * 8 + pl;
-            const int lrow = 2 * rp + rr;
-            const long long li = row0 + lrow;
-            const long long grow = (li < a.nrows) ? (a.rowList ? (long long)a.rowList[li] : li) : -1;
-            float2 v = make_float2(0.f, 0.f);
-            if (LOADER == 0 && !g.odd && pos < npos && grow >= 0) {
-                // asynchronous 8-byte copies: every thread keeps all its loads in flight, no registers
-                cp_async8(&A2[xslot(lrow, pos)], reinterpret_cast<const float2*>(a.in_real + grow * g.nx) + pos);
-                continue;
-            }
-            if (pos < npos && grow >= 0) {
-                if (LOADER == 0) {
-                    v.x = __ldg(a.in_real + grow * g.nx + pos);
-                } else {
-                    if (g.odd) v.x = psf_tap(a.psf, grow * g.nx + pos);
-                    else {
-                        v.x = psf_tap(a.psf, grow * g.nx + 2 * pos);
-                        v.y = psf_tap(a.psf, grow * g.nx + 2 * pos + 1);
-                    }
-                }
-            }
-            if (pos < npos) A2[xslot(lrow, pos)] = v;
+    // ---- global rows -> row tile (one warp per row at a time, lanes along x)
+    for (int lrow = warp; lrow < 16; lrow += nwarps) {
+        const long long li = row0 + lrow;
+        const long long grow = (li < a.nrows) ? (a.rowList ? (long long)a.rowList[li] : li) : -1;
+        float2* dst = rowt + lrow * P;
+        if (grow < 0) {
+            for (int pos = lane; pos < L; pos += 32) dst[pos] = make_float2(0.f, 0.f);
+        } else if (LOADER == 0 && !g.odd) {
+            const float2* src = reinterpret_cast<const float2*>(a.in_real + grow * g.nx);
+            for (int pos = lane; pos < L; pos += 32) cp_async8(dst + pos, src + pos);
+        } else if (LOADER == 0) {
+            const float* src = a.in_real + grow * g.nx;
+            for (int pos = lane; pos < L; pos += 32) dst[pos] = make_float2(__ldg(src + pos), 0.f);
+        } else if (!g.odd) {
+            const long long f0 = grow * g.nx;
+            for (int pos = lane; pos < L; pos += 32)
+                dst[pos] = make_float2(psf_tap(a.psf, f0 + 2 * pos), psf_tap(a.psf, f0 + 2 * pos + 1));
+        } else {
+            const long long f0 = grow * g.nx;
+            for (int pos = lane; pos < L; pos += 32) dst[pos] = make_float2(psf_tap(a.psf, f0 + pos), 0.f);
         }
     }
     cp_async_wait_all();
     __syncthreads();
 
-    float4* cur = engine_run<false, true>(a.P, A, B, tw_s, cp, w, W, 8, true);
-
-    // ---- split the packed transform into the spectrum of the real rows (even nx)
-    if (!g.odd) {
-        const int M = g.M;
-        for (int k = w; k <= M / 2; k += W) {
-            if (k == 0) {
-                const int p0 = __ldg(a.P.pos);
-                float4 v = cur[tile_idx<true>(p0, cp, 8)];
-                cur[tile_idx<true>(p0, cp, 8)] = make_float4(v.x + v.y, 0.f, v.z + v.w, 0.f);
-                cur[tile_idx<true>(M, cp, 8)] = make_float4(v.x - v.y, 0.f, v.z - v.w, 0.f);
-            } else {
-                const int k2 = M - k;
-                const int pk = __ldg(a.P.pos + k), pk2 = __ldg(a.P.pos + k2);
-                const float4 va = cur[tile_idx<true>(pk, cp, 8)];
-                const float4 vb = cur[tile_idx<true>(pk2, cp, 8)];
-                const float2 tk = __ldg(a.twx + k);  // exp(-2*pi*i*k/nx)
-                float4 o1, o2;
-                {
-                    float er = 0.5f * (va.x + vb.x), ei = 0.5f * (va.y - vb.y);
-                    float orr = 0.5f * (va.y + vb.y), oi = -0.5f * (va.x - vb.x);
-                    float wr = tk.x * orr - tk.y * oi, wi = tk.x * oi + tk.y * orr;
-                    o1.x = er + wr;
-                    o1.y = ei + wi;
-                    o2.x = er - wr;
-                    o2.y = -(ei - wi);
-                }
-                {
-                    float er = 0.5f * (va.z + vb.z), ei = 0.5f * (va.w - vb.w);
-                    float orr = 0.5f * (va.w + vb.w), oi = -0.5f * (va.z - vb.z);
-                    float wr = tk.x * orr - tk.y * oi, wi = tk.x * oi + tk.y * orr;
-                    o1.z = er + wr;
-                    o1.w = ei + wi;
-                    o2.z = er - wr;
-                    o2.w = -(ei - wi);
-                }
-                cur[tile_idx<true>(pk, cp, 8)] = o1;
-                cur[tile_idx<true>(pk2, cp, 8)] = o2;
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- transposing store: tile -> spectrum rows (pad columns are written as zeros)
+    // ---- row tile -> engine tile (lanes along rows: the transposition)
     {
-        const float2* C2 = reinterpret_cast<const float2*>(cur);
-        const int nchunks = (g.xcp + 15) >> 4;
-        for (int u = warp; u < 8 * nchunks; u += nwarps) {
-            const int rp = u / nchunks, c = u - rp * nchunks;
-            const int pos = c * 16 + ph * 8 + pl;
-            const int lrow = 2 * rp + rr;
-            const long long li = row0 + lrow;
-            const long long grow = (li < a.nrows) ? (a.rowList ? (long long)a.rowList[li] : li) : -1;
-            if (pos < g.xcp && grow >= 0) {
-                float2 v = make_float2(0.f, 0.f);
-                if (pos < g.xc) {
-                    const int p = g.odd ? __ldg(a.P.pos + pos) : pos;
-                    v = C2[xslot(lrow, p)];
+        float2* E = reinterpret_cast<float2*>(sm.A);
+        const int lrow = t & 15, q = t >> 4, Q = blockDim.x >> 4;
+        for (int pos = q; pos < L; pos += Q) E[eidx(pos, lrow)] = rowt[lrow * P + pos];
+    }
+    __syncthreads();
+
+    float4* cur = engine_run<false, false>(a.P, sm.A, sm.B, sm.tw, cp, w, W, 8, true);
+
+    // ---- engine tile -> row tile in natural kx order, splitting the packed transform (even nx)
+    {
+        const float2* E = reinterpret_cast<const float2*>(cur);
+        const int lrow = t & 15, q = t >> 4, Q = blockDim.x >> 4;
+        float2* out = rowt + lrow * P;
+        if (g.odd) {
+            for (int k = q; k < g.xc; k += Q) out[k] = E[eidx(__ldg(a.P.pos + k), lrow)];
+        } else {
+            const int M = g.M;
+            for (int k = q; k <= M / 2; k += Q) {
+                if (k == 0) {
+                    const float2 v = E[eidx(__ldg(a.P.pos), lrow)];
+                    out[0] = make_float2(v.x + v.y, 0.f);
+                    out[M] = make_float2(v.x - v.y, 0.f);
+                } else {
+                    const int k2 = M - k;
+                    const float2 va = E[eidx(__ldg(a.P.pos + k), lrow)];
+                    const float2 vb = E[eidx(__ldg(a.P.pos + k2), lrow)];
+                    const float2 tk = __ldg(a.twx + k);  // exp(-2*pi*i*k/nx)
+                    const float er = 0.5f * (va.x + vb.x), ei = 0.5f * (va.y - vb.y);
+                    const float orr = 0.5f * (va.y + vb.y), oi = -0.5f * (va.x - vb.x);
+                    const float wr = tk.x * orr - tk.y * oi, wi = tk.x * oi + tk.y * orr;
+                    out[k] = make_float2(er + wr, ei + wi);
+                    out[k2] = make_float2(er - wr, -(ei - wi));
                 }
-                a.spec[grow * g.xcp + pos] = v;
             }
         }
+    }
+    __syncthreads();
+
+    // ---- row tile -> spectrum rows (pad columns written as zeros)
+    for (int lrow = warp; lrow < 16; lrow += nwarps) {
+        const long long li = row0 + lrow;
+        const long long grow = (li < a.nrows) ? (a.rowList ? (long long)a.rowList[li] : li) : -1;
+        if (grow < 0) continue;
+        const float2* src = rowt + lrow * P;
+        float2* dst = a.spec + grow * g.xcp;
+        for (int k = lane; k < g.xcp; k += 32) dst[k] = (k < g.xc) ? src[k] : make_float2(0.f, 0.f);
     }
 }
 
@@ -208,103 +210,82 @@ __global__ void __launch_bounds__(kColThreads) x_inv_kernel(XArgs a)
     extern __shared__ float4 smem[];
     const Geometry g = a.g;
     const int L = a.P.L;
-    const int tile_rows = g.odd ? L : (g.M + 1);
-    float4* A = smem;
-    float4* B = a.P.generic ? (A + (size_t)tile_rows * 8) : nullptr;
-    float2* tw_s = reinterpret_cast<float2*>(A + (size_t)tile_rows * 8 * (a.P.generic ? 2 : 1));
+    const XSmem sm = x_carve(smem, g, a.P);
+    const int P = sm.P;
+    float2* rowt = sm.rowt;
 
     const int t = threadIdx.x;
     const int cp = t & 7, w = t >> 3, W = blockDim.x >> 3;
     const int lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
-    const int pl = lane & 7, rr = (lane >> 3) & 1, ph = lane >> 4;
     const long long row0 = (long long)blockIdx.x * 16;
 
-    load_twiddles(tw_s, a.P.tw, L);
+    load_twiddles(sm.tw, a.P.tw, L);
 
-    {
-        float2* A2 = reinterpret_cast<float2*>(A);
-        const int nchunks = (g.xc + 15) >> 4;
-        for (int u = warp; u < 8 * nchunks; u += nwarps) {
-            const int rp = u / nchunks, c = u - rp * nchunks;
-            const int pos = c * 16 + ph * 8 + pl;
-            const int lrow = 2 * rp + rr;
-            const long long grow = row0 + lrow;
-            if (pos < g.xc) {
-                if (!g.odd && grow < a.nrows) {
-                    cp_async8(&A2[xslot(lrow, pos)], a.spec + grow * g.xcp + pos);
-                    continue;
-                }
-                float2 v = make_float2(0.f, 0.f);
-                if (grow < a.nrows) v = __ldg(a.spec + grow * g.xcp + pos);
-                if (!g.odd) {
-                    A2[xslot(lrow, pos)] = v;
-                } else {
-                    A2[xslot(lrow, __ldg(a.P.pos + pos))] = v;
-                    if (pos > 0) A2[xslot(lrow, __ldg(a.P.pos + (g.nx - pos)))] = make_float2(v.x, -v.y);
-                }
-            }
+    // ---- spectrum rows -> row tile
+    for (int lrow = warp; lrow < 16; lrow += nwarps) {
+        const long long grow = row0 + lrow;
+        float2* dst = rowt + lrow * P;
+        if (grow < a.nrows) {
+            const float2* src = a.spec + grow * g.xcp;
+            for (int k = lane; k < g.xc; k += 32) cp_async8(dst + k, src + k);
+        } else {
+            for (int k = lane; k < g.xc; k += 32) dst[k] = make_float2(0.f, 0.f);
         }
     }
     cp_async_wait_all();
     __syncthreads();
 
-    if (!g.odd) {
-        const int M = g.M;
-        for (int k = w; k <= M / 2; k += W) {
-            if (k == 0) {
-                const int p0 = __ldg(a.P.pos);
-                const float4 x0 = A[tile_idx<true>(p0, cp, 8)];
-                const float4 xm = A[tile_idx<true>(M, cp, 8)];
-                A[tile_idx<true>(p0, cp, 8)] = make_float4(x0.x + xm.x, x0.x - xm.x, x0.z + xm.z, x0.z - xm.z);
-            } else {
-                const int k2 = M - k;
-                const int pk = __ldg(a.P.pos + k), pk2 = __ldg(a.P.pos + k2);
-                const float4 va = A[tile_idx<true>(pk, cp, 8)];
-                const float4 vb = A[tile_idx<true>(pk2, cp, 8)];
-                const float2 tk = __ldg(a.twx + k);
-                float4 o1, o2;
-                {
-                    float sr = va.x + vb.x, si = va.y - vb.y;
-                    float Dr = va.x - vb.x, Di = va.y + vb.y;
-                    // d = D * conj(w)
-                    float dr = Dr * tk.x + Di * tk.y, di = Di * tk.x - Dr * tk.y;
-                    o1.x = sr - di;
-                    o1.y = si + dr;
-                    o2.x = sr + di;
-                    o2.y = dr - si;
+    // ---- row tile -> engine tile (positions), merging the half spectrum into the packed transform
+    {
+        float2* E = reinterpret_cast<float2*>(sm.A);
+        const int lrow = t & 15, q = t >> 4, Q = blockDim.x >> 4;
+        const float2* in = rowt + lrow * P;
+        if (g.odd) {
+            for (int k = q; k < g.xc; k += Q) {
+                const float2 v = in[k];
+                E[eidx(__ldg(a.P.pos + k), lrow)] = v;
+                if (k > 0) E[eidx(__ldg(a.P.pos + (g.nx - k)), lrow)] = make_float2(v.x, -v.y);
+            }
+        } else {
+            const int M = g.M;
+            for (int k = q; k <= M / 2; k += Q) {
+                if (k == 0) {
+                    const float2 x0 = in[0], xm = in[M];
+                    E[eidx(__ldg(a.P.pos), lrow)] = make_float2(x0.x + xm.x, x0.x - xm.x);
+                } else {
+                    const int k2 = M - k;
+                    const float2 va = in[k], vb = in[k2];
+                    const float2 tk = __ldg(a.twx + k);
+                    const float sr = va.x + vb.x, si = va.y - vb.y;
+                    const float Dr = va.x - vb.x, Di = va.y + vb.y;
+                    const float dr = Dr * tk.x + Di * tk.y, di = Di * tk.x - Dr * tk.y;  // D * conj(w)
+                    E[eidx(__ldg(a.P.pos + k), lrow)] = make_float2(sr - di, si + dr);
+                    if (k2 != k) E[eidx(__ldg(a.P.pos + k2), lrow)] = make_float2(sr + di, dr - si);
                 }
-                {
-                    float sr = va.z + vb.z, si = va.w - vb.w;
-                    float Dr = va.z - vb.z, Di = va.w + vb.w;
-                    float dr = Dr * tk.x + Di * tk.y, di = Di * tk.x - Dr * tk.y;
-                    o1.z = sr - di;
-                    o1.w = si + dr;
-                    o2.z = sr + di;
-                    o2.w = dr - si;
-                }
-                A[tile_idx<true>(pk, cp, 8)] = o1;
-                if (k2 != k) A[tile_idx<true>(pk2, cp, 8)] = o2;
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
-    float4* cur = engine_run<true, true>(a.P, A, B, tw_s, cp, w, W, 8, true);
+    float4* cur = engine_run<true, false>(a.P, sm.A, sm.B, sm.tw, cp, w, W, 8, true);
 
+    // ---- engine tile -> row tile (natural order), then row tile -> real rows
     {
-        const float2* C2 = reinterpret_cast<const float2*>(cur);
-        const int npos = L;
-        const int nchunks = (npos + 15) >> 4;
-        for (int u = warp; u < 8 * nchunks; u += nwarps) {
-            const int rp = u / nchunks, c = u - rp * nchunks;
-            const int pos = c * 16 + ph * 8 + pl;
-            const int lrow = 2 * rp + rr;
-            const long long grow = row0 + lrow;
-            if (pos < npos && grow < a.nrows) {
-                const float2 v = C2[xslot(lrow, pos)];
-                if (g.odd) a.out_real[grow * g.nx + pos] = v.x;
-                else reinterpret_cast<float2*>(a.out_real + grow * g.nx)[pos] = v;
-            }
+        const float2* E = reinterpret_cast<const float2*>(cur);
+        const int lrow = t & 15, q = t >> 4, Q = blockDim.x >> 4;
+        for (int pos = q; pos < L; pos += Q) rowt[lrow * P + pos] = E[eidx(pos, lrow)];
+    }
+    __syncthreads();
+    for (int lrow = warp; lrow < 16; lrow += nwarps) {
+        const long long grow = row0 + lrow;
+        if (grow >= a.nrows) continue;
+        const float2* src = rowt + lrow * P;
+        if (g.odd) {
+            float* dst = a.out_real + grow * g.nx;
+            for (int pos = lane; pos < L; pos += 32) dst[pos] = src[pos].x;
+        } else {
+            float2* dst = reinterpret_cast<float2*>(a.out_real + grow * g.nx);
+            for (int pos = lane; pos < L; pos += 32) dst[pos] = src[pos];
         }
     }
 }
@@ -387,8 +368,8 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
 // ------------------------------------------------------------------------------------------------
 static size_t x_smem_bytes(const Geometry& g, const AxisPlanDev& P)
 {
-    const size_t tile_rows = g.odd ? (size_t)P.L : (size_t)g.M + 1;
-    return tile_rows * 8 * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)P.L * sizeof(float2);
+    const size_t rowt = 16 * (size_t)x_row_pitch(P.L, g.xc) * sizeof(float2);
+    return (size_t)P.L * 8 * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)P.L * sizeof(float2) + rowt;
 }
 
 bool x_pass_supported(const Geometry& g, const AxisPlanDev& P) { return x_smem_bytes(g, P) <= (size_t)kMaxDynSmem; }
@@ -409,6 +390,16 @@ static void set_smem(K kernel, size_t bytes)
         FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
+static int x_threads()
+{
+    static const int t = [] {
+        const char* e = std::getenv("FCB200_X_THREADS");
+        int v = e ? std::atoi(e) : kColThreads;
+        return std::max(64, std::min(v, kColThreads)) & ~31;
+    }();
+    return t;
+}
+
 void launch_x_fwd(const XArgs& a, bool psf, cudaStream_t st)
 {
     const size_t smem = x_smem_bytes(a.g, a.P);
@@ -416,10 +407,10 @@ void launch_x_fwd(const XArgs& a, bool psf, cudaStream_t st)
     if (tiles == 0) return;
     if (psf) {
         set_smem(x_fwd_kernel<1>, smem);
-        x_fwd_kernel<1><<<(unsigned)tiles, kColThreads, smem, st>>>(a);
+        x_fwd_kernel<1><<<(unsigned)tiles, x_threads(), smem, st>>>(a);
     } else {
         set_smem(x_fwd_kernel<0>, smem);
-        x_fwd_kernel<0><<<(unsigned)tiles, kColThreads, smem, st>>>(a);
+        x_fwd_kernel<0><<<(unsigned)tiles, x_threads(), smem, st>>>(a);
     }
     FC_CUDA_KERNEL();
 }
@@ -430,7 +421,7 @@ void launch_x_inv(const XArgs& a, cudaStream_t st)
     const long long tiles = (a.nrows + 15) / 16;
     if (tiles == 0) return;
     set_smem(x_inv_kernel, smem);
-    x_inv_kernel<<<(unsigned)tiles, kColThreads, smem, st>>>(a);
+    x_inv_kernel<<<(unsigned)tiles, x_threads(), smem, st>>>(a);
     FC_CUDA_KERNEL();
 }
 
