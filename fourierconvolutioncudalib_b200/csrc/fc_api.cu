@@ -116,9 +116,14 @@ void download_spectrum(ConvPlan& p, const float2* d_spec, float* out, cudaStream
     std::vector<float2> h((size_t)g.nz * g.ny * g.xcp);
     FC_CUDA(cudaMemcpyAsync(h.data(), d_spec, h.size() * sizeof(float2), cudaMemcpyDeviceToHost, st));
     FC_CUDA(cudaStreamSynchronize(st));
+    // device rows are pair-planar: floats (re_2c, re_2c+1, im_2c, im_2c+1) per column pair
     float2* o = reinterpret_cast<float2*>(out);
+    const float* hf = reinterpret_cast<const float*>(h.data());
     for (size_t r = 0; r < (size_t)g.nz * g.ny; ++r)
-        for (int k = 0; k < g.xc; ++k) o[r * g.xc + k] = h[r * g.xcp + k];
+        for (int k = 0; k < g.xc; ++k) {
+            const size_t f = r * g.xcp * 2 + (size_t)((k >> 1) << 2) + (k & 1);
+            o[r * g.xc + k] = make_float2(hf[f], hf[f + 2]);
+        }
 }
 
 }  // namespace
@@ -351,8 +356,13 @@ void fcb200_debug_irfft3(const float* spec, const int* imDim, imageType* out, in
         const Geometry& g = p.g;
         std::vector<float2> h((size_t)g.nz * g.ny * g.xcp, make_float2(0.f, 0.f));
         const float2* s = reinterpret_cast<const float2*>(spec);
+        float* hf = reinterpret_cast<float*>(h.data());
         for (size_t r = 0; r < (size_t)g.nz * g.ny; ++r)
-            for (int k = 0; k < g.xc; ++k) h[r * g.xcp + k] = s[r * g.xc + k];
+            for (int k = 0; k < g.xc; ++k) {
+                const size_t f = r * g.xcp * 2 + (size_t)((k >> 1) << 2) + (k & 1);
+                hf[f] = s[r * g.xc + k].x;
+                hf[f + 2] = s[r * g.xc + k].y;
+            }
         if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
         FC_CUDA(cudaMemcpyAsync(p.d_spec, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice, p.stream));
         run_inverse(p, p.d_spec, p.d_real, p.stream);

@@ -29,7 +29,9 @@ struct AxisPlanDev {
 //                  /root/reference/src/convolution3Dfft.cu:417-421)
 //   spectrum     : [nz][ny][xcp] float2, xc = nx/2+1 valid bins per row, xcp = xc rounded up to 4
 //                  (32-byte sector alignment of every row); kx, ky and kz are all in natural order,
-//                  i.e. the buffer is numpy.fft.rfftn of the volume with padded rows.
+//                  i.e. the buffer is numpy.fft.rfftn of the volume with padded rows -- except that
+//                  each 16 bytes hold two adjacent kx bins in PAIR-PLANAR form (re0, re1, im0, im1)
+//                  so the strided passes can use packed fp32 arithmetic without any shuffles.
 struct Geometry {
     int nx, ny, nz;
     int xc, xcp;

@@ -1,8 +1,13 @@
-// Radix butterflies for the sm_100a FFT engine.
+// Radix butterflies for the sm_100a FFT engine, on PACKED pairs of pencils.
 //
-// All butterflies are forward DFTs (kernel exp(-2*pi*i*k*m/R)) on split real/imag register arrays.
-// The inverse transform is obtained for free by swapping the two array arguments:
-//   IDFT(x) = swap(DFT(swap(x)))   ->   Dft<R>::run(im, re)
+// Every value is a float2 holding the same quantity of two adjacent pencils (lo = pencil 0,
+// hi = pencil 1); real and imaginary parts live in separate arrays.  All arithmetic uses Blackwell's
+// packed fp32 instructions (FADD2 / FMUL2 / FFMA2, PTX add/mul/fma.f32x2, sm_100+), so one issued
+// instruction advances two pencils.  The spectrum is therefore stored "pair-planar": 16 bytes =
+// (re0, re1, im0, im1) -- see fc_common.h.
+//
+// All butterflies are forward DFTs (kernel exp(-2*pi*i*k*m/R)).  The inverse transform is obtained
+// for free by swapping the two array arguments:  IDFT(x) = swap(DFT(swap(x)))  ->  Dft<R>::run(im, re).
 // Part of the replacement for the cuFFT calls of the reference hot path
 // (/root/reference/src/convolution3Dfft.cu:519-525, :544-547).
 #pragma once
@@ -10,92 +15,102 @@
 
 namespace fcb200 {
 
+typedef float2 p2;
+
+__device__ __forceinline__ p2 padd(p2 a, p2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ p2 pneg(p2 a) { return make_float2(-a.x, -a.y); }      // folds into operand modifiers
+__device__ __forceinline__ p2 psub(p2 a, p2 b) { return __fadd2_rn(a, pneg(b)); }
+__device__ __forceinline__ p2 pmul(p2 a, p2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ p2 pmuls(p2 a, float c) { return __fmul2_rn(a, make_float2(c, c)); }
+__device__ __forceinline__ p2 pfma(p2 a, p2 b, p2 c) { return __ffma2_rn(a, b, c); }           // a*b + c
+__device__ __forceinline__ p2 pfmas(p2 a, float s, p2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
+
 template <int R>
 struct Dft;
 
 template <>
 struct Dft<2> {
-    static __device__ __forceinline__ void run(float* r, float* i)
+    static __device__ __forceinline__ void run(p2* r, p2* i)
     {
-        float t = r[0] - r[1];
-        r[0] = r[0] + r[1];
+        p2 t = psub(r[0], r[1]);
+        r[0] = padd(r[0], r[1]);
         r[1] = t;
-        t = i[0] - i[1];
-        i[0] = i[0] + i[1];
+        t = psub(i[0], i[1]);
+        i[0] = padd(i[0], i[1]);
         i[1] = t;
     }
 };
 
 template <>
 struct Dft<3> {
-    static __device__ __forceinline__ void run(float* r, float* i)
+    static __device__ __forceinline__ void run(p2* r, p2* i)
     {
         const float S3 = 0.86602540378443864676f;  // sin(2*pi/3)
-        float tr = r[1] + r[2], ti = i[1] + i[2];
-        float ur = (r[1] - r[2]) * S3, ui = (i[1] - i[2]) * S3;
-        float mr = fmaf(-0.5f, tr, r[0]), mi = fmaf(-0.5f, ti, i[0]);
-        r[0] += tr;
-        i[0] += ti;
+        p2 tr = padd(r[1], r[2]), ti = padd(i[1], i[2]);
+        p2 ur = pmuls(psub(r[1], r[2]), S3), ui = pmuls(psub(i[1], i[2]), S3);
+        p2 mr = pfmas(tr, -0.5f, r[0]), mi = pfmas(ti, -0.5f, i[0]);
+        r[0] = padd(r[0], tr);
+        i[0] = padd(i[0], ti);
         // y1 = m - i*u ; y2 = m + i*u
-        r[1] = mr + ui;
-        i[1] = mi - ur;
-        r[2] = mr - ui;
-        i[2] = mi + ur;
+        r[1] = padd(mr, ui);
+        i[1] = psub(mi, ur);
+        r[2] = psub(mr, ui);
+        i[2] = padd(mi, ur);
     }
 };
 
 template <>
 struct Dft<4> {
-    static __device__ __forceinline__ void run(float* r, float* i)
+    static __device__ __forceinline__ void run(p2* r, p2* i)
     {
-        float t0r = r[0] + r[2], t0i = i[0] + i[2];
-        float t1r = r[0] - r[2], t1i = i[0] - i[2];
-        float t2r = r[1] + r[3], t2i = i[1] + i[3];
-        float t3r = r[1] - r[3], t3i = i[1] - i[3];
-        r[0] = t0r + t2r;
-        i[0] = t0i + t2i;
-        r[2] = t0r - t2r;
-        i[2] = t0i - t2i;
-        r[1] = t1r + t3i;  // t1 - i*t3
-        i[1] = t1i - t3r;
-        r[3] = t1r - t3i;  // t1 + i*t3
-        i[3] = t1i + t3r;
+        p2 t0r = padd(r[0], r[2]), t0i = padd(i[0], i[2]);
+        p2 t1r = psub(r[0], r[2]), t1i = psub(i[0], i[2]);
+        p2 t2r = padd(r[1], r[3]), t2i = padd(i[1], i[3]);
+        p2 t3r = psub(r[1], r[3]), t3i = psub(i[1], i[3]);
+        r[0] = padd(t0r, t2r);
+        i[0] = padd(t0i, t2i);
+        r[2] = psub(t0r, t2r);
+        i[2] = psub(t0i, t2i);
+        r[1] = padd(t1r, t3i);  // t1 - i*t3
+        i[1] = psub(t1i, t3r);
+        r[3] = psub(t1r, t3i);  // t1 + i*t3
+        i[3] = padd(t1i, t3r);
     }
 };
 
 template <>
 struct Dft<5> {
-    static __device__ __forceinline__ void run(float* r, float* i)
+    static __device__ __forceinline__ void run(p2* r, p2* i)
     {
         const float C1 = 0.30901699437494742410f;   // cos(2*pi/5)
         const float C2 = -0.80901699437494742410f;  // cos(4*pi/5)
         const float S1 = 0.95105651629515357212f;   // sin(2*pi/5)
         const float S2 = 0.58778525229247312917f;   // sin(4*pi/5)
-        float t1r = r[1] + r[4], t1i = i[1] + i[4];
-        float t2r = r[2] + r[3], t2i = i[2] + i[3];
-        float t3r = r[1] - r[4], t3i = i[1] - i[4];
-        float t4r = r[2] - r[3], t4i = i[2] - i[3];
-        float a1r = fmaf(C2, t2r, fmaf(C1, t1r, r[0])), a1i = fmaf(C2, t2i, fmaf(C1, t1i, i[0]));
-        float a2r = fmaf(C1, t2r, fmaf(C2, t1r, r[0])), a2i = fmaf(C1, t2i, fmaf(C2, t1i, i[0]));
-        float b1r = fmaf(S2, t4r, S1 * t3r), b1i = fmaf(S2, t4i, S1 * t3i);
-        float b2r = fmaf(-S1, t4r, S2 * t3r), b2i = fmaf(-S1, t4i, S2 * t3i);
-        r[0] = r[0] + t1r + t2r;
-        i[0] = i[0] + t1i + t2i;
+        p2 t1r = padd(r[1], r[4]), t1i = padd(i[1], i[4]);
+        p2 t2r = padd(r[2], r[3]), t2i = padd(i[2], i[3]);
+        p2 t3r = psub(r[1], r[4]), t3i = psub(i[1], i[4]);
+        p2 t4r = psub(r[2], r[3]), t4i = psub(i[2], i[3]);
+        p2 a1r = pfmas(t2r, C2, pfmas(t1r, C1, r[0])), a1i = pfmas(t2i, C2, pfmas(t1i, C1, i[0]));
+        p2 a2r = pfmas(t2r, C1, pfmas(t1r, C2, r[0])), a2i = pfmas(t2i, C1, pfmas(t1i, C2, i[0]));
+        p2 b1r = pfmas(t4r, S2, pmuls(t3r, S1)), b1i = pfmas(t4i, S2, pmuls(t3i, S1));
+        p2 b2r = pfmas(t4r, -S1, pmuls(t3r, S2)), b2i = pfmas(t4i, -S1, pmuls(t3i, S2));
+        r[0] = padd(padd(r[0], t1r), t2r);
+        i[0] = padd(padd(i[0], t1i), t2i);
         // y1 = a1 - i*b1 ; y4 = a1 + i*b1 ; y2 = a2 - i*b2 ; y3 = a2 + i*b2
-        r[1] = a1r + b1i;
-        i[1] = a1i - b1r;
-        r[4] = a1r - b1i;
-        i[4] = a1i + b1r;
-        r[2] = a2r + b2i;
-        i[2] = a2i - b2r;
-        r[3] = a2r - b2i;
-        i[3] = a2i + b2r;
+        r[1] = padd(a1r, b1i);
+        i[1] = psub(a1i, b1r);
+        r[4] = psub(a1r, b1i);
+        i[4] = padd(a1i, b1r);
+        r[2] = padd(a2r, b2i);
+        i[2] = psub(a2i, b2r);
+        r[3] = psub(a2r, b2i);
+        i[3] = padd(a2i, b2r);
     }
 };
 
 template <>
 struct Dft<7> {
-    static __device__ __forceinline__ void run(float* r, float* i)
+    static __device__ __forceinline__ void run(p2* r, p2* i)
     {
         const float C1 = 0.62348980185873353053f;   // cos(2*pi/7)
         const float C2 = -0.22252093395631440429f;  // cos(4*pi/7)
@@ -103,81 +118,85 @@ struct Dft<7> {
         const float S1 = 0.78183148246802980871f;   // sin(2*pi/7)
         const float S2 = 0.97492791218182360702f;   // sin(4*pi/7)
         const float S3 = 0.43388373911755812048f;   // sin(6*pi/7)
-        float t1r = r[1] + r[6], t1i = i[1] + i[6], u1r = r[1] - r[6], u1i = i[1] - i[6];
-        float t2r = r[2] + r[5], t2i = i[2] + i[5], u2r = r[2] - r[5], u2i = i[2] - i[5];
-        float t3r = r[3] + r[4], t3i = i[3] + i[4], u3r = r[3] - r[4], u3i = i[3] - i[4];
-        // m=1: cos idx (1,2,3) sin idx (1,2,3); m=2: (2,4->3,6->1) sin(2, 4->-3, 6->-1); m=3: (3,6->1,9->2) sin(3,-1,2)
-        float a1r = fmaf(C3, t3r, fmaf(C2, t2r, fmaf(C1, t1r, r[0])));
-        float a1i = fmaf(C3, t3i, fmaf(C2, t2i, fmaf(C1, t1i, i[0])));
-        float a2r = fmaf(C1, t3r, fmaf(C3, t2r, fmaf(C2, t1r, r[0])));
-        float a2i = fmaf(C1, t3i, fmaf(C3, t2i, fmaf(C2, t1i, i[0])));
-        float a3r = fmaf(C2, t3r, fmaf(C1, t2r, fmaf(C3, t1r, r[0])));
-        float a3i = fmaf(C2, t3i, fmaf(C1, t2i, fmaf(C3, t1i, i[0])));
-        float b1r = fmaf(S3, u3r, fmaf(S2, u2r, S1 * u1r)), b1i = fmaf(S3, u3i, fmaf(S2, u2i, S1 * u1i));
-        float b2r = fmaf(-S1, u3r, fmaf(-S3, u2r, S2 * u1r)), b2i = fmaf(-S1, u3i, fmaf(-S3, u2i, S2 * u1i));
-        float b3r = fmaf(S2, u3r, fmaf(-S1, u2r, S3 * u1r)), b3i = fmaf(S2, u3i, fmaf(-S1, u2i, S3 * u1i));
-        r[0] = r[0] + t1r + t2r + t3r;
-        i[0] = i[0] + t1i + t2i + t3i;
-        r[1] = a1r + b1i;
-        i[1] = a1i - b1r;
-        r[6] = a1r - b1i;
-        i[6] = a1i + b1r;
-        r[2] = a2r + b2i;
-        i[2] = a2i - b2r;
-        r[5] = a2r - b2i;
-        i[5] = a2i + b2r;
-        r[3] = a3r + b3i;
-        i[3] = a3i - b3r;
-        r[4] = a3r - b3i;
-        i[4] = a3i + b3r;
+        p2 t1r = padd(r[1], r[6]), t1i = padd(i[1], i[6]), u1r = psub(r[1], r[6]), u1i = psub(i[1], i[6]);
+        p2 t2r = padd(r[2], r[5]), t2i = padd(i[2], i[5]), u2r = psub(r[2], r[5]), u2i = psub(i[2], i[5]);
+        p2 t3r = padd(r[3], r[4]), t3i = padd(i[3], i[4]), u3r = psub(r[3], r[4]), u3i = psub(i[3], i[4]);
+        // cos index (m*k mod 7 folded to 1..3), sin index with sign: m=1: (1,2,3); m=2: (2,-3,-1); m=3: (3,-1,2)
+        p2 a1r = pfmas(t3r, C3, pfmas(t2r, C2, pfmas(t1r, C1, r[0])));
+        p2 a1i = pfmas(t3i, C3, pfmas(t2i, C2, pfmas(t1i, C1, i[0])));
+        p2 a2r = pfmas(t3r, C1, pfmas(t2r, C3, pfmas(t1r, C2, r[0])));
+        p2 a2i = pfmas(t3i, C1, pfmas(t2i, C3, pfmas(t1i, C2, i[0])));
+        p2 a3r = pfmas(t3r, C2, pfmas(t2r, C1, pfmas(t1r, C3, r[0])));
+        p2 a3i = pfmas(t3i, C2, pfmas(t2i, C1, pfmas(t1i, C3, i[0])));
+        p2 b1r = pfmas(u3r, S3, pfmas(u2r, S2, pmuls(u1r, S1))), b1i = pfmas(u3i, S3, pfmas(u2i, S2, pmuls(u1i, S1)));
+        p2 b2r = pfmas(u3r, -S1, pfmas(u2r, -S3, pmuls(u1r, S2))), b2i = pfmas(u3i, -S1, pfmas(u2i, -S3, pmuls(u1i, S2)));
+        p2 b3r = pfmas(u3r, S2, pfmas(u2r, -S1, pmuls(u1r, S3))), b3i = pfmas(u3i, S2, pfmas(u2i, -S1, pmuls(u1i, S3)));
+        r[0] = padd(padd(r[0], t1r), padd(t2r, t3r));
+        i[0] = padd(padd(i[0], t1i), padd(t2i, t3i));
+        r[1] = padd(a1r, b1i);
+        i[1] = psub(a1i, b1r);
+        r[6] = psub(a1r, b1i);
+        i[6] = padd(a1i, b1r);
+        r[2] = padd(a2r, b2i);
+        i[2] = psub(a2i, b2r);
+        r[5] = psub(a2r, b2i);
+        i[5] = padd(a2i, b2r);
+        r[3] = padd(a3r, b3i);
+        i[3] = psub(a3i, b3r);
+        r[4] = psub(a3r, b3i);
+        i[4] = padd(a3i, b3r);
     }
 };
 
 template <>
 struct Dft<8> {
-    static __device__ __forceinline__ void run(float* r, float* i)
+    static __device__ __forceinline__ void run(p2* r, p2* i)
     {
         const float C = 0.70710678118654752440f;
-        float er[4] = {r[0], r[2], r[4], r[6]}, ei[4] = {i[0], i[2], i[4], i[6]};
-        float qr[4] = {r[1], r[3], r[5], r[7]}, qi[4] = {i[1], i[3], i[5], i[7]};
+        p2 er[4] = {r[0], r[2], r[4], r[6]}, ei[4] = {i[0], i[2], i[4], i[6]};
+        p2 qr[4] = {r[1], r[3], r[5], r[7]}, qi[4] = {i[1], i[3], i[5], i[7]};
         Dft<4>::run(er, ei);
         Dft<4>::run(qr, qi);
         // odd outputs times w8^k
-        float o1r = C * (qr[1] + qi[1]), o1i = C * (qi[1] - qr[1]);
-        float o2r = qi[2], o2i = -qr[2];
-        float o3r = C * (qi[3] - qr[3]), o3i = -C * (qr[3] + qi[3]);
-        r[0] = er[0] + qr[0];
-        i[0] = ei[0] + qi[0];
-        r[4] = er[0] - qr[0];
-        i[4] = ei[0] - qi[0];
-        r[1] = er[1] + o1r;
-        i[1] = ei[1] + o1i;
-        r[5] = er[1] - o1r;
-        i[5] = ei[1] - o1i;
-        r[2] = er[2] + o2r;
-        i[2] = ei[2] + o2i;
-        r[6] = er[2] - o2r;
-        i[6] = ei[2] - o2i;
-        r[3] = er[3] + o3r;
-        i[3] = ei[3] + o3i;
-        r[7] = er[3] - o3r;
-        i[7] = ei[3] - o3i;
+        p2 o1r = pmuls(padd(qr[1], qi[1]), C), o1i = pmuls(psub(qi[1], qr[1]), C);
+        p2 o2r = qi[2], o2i = pneg(qr[2]);
+        p2 o3r = pmuls(psub(qi[3], qr[3]), C), o3i = pmuls(padd(qr[3], qi[3]), -C);
+        r[0] = padd(er[0], qr[0]);
+        i[0] = padd(ei[0], qi[0]);
+        r[4] = psub(er[0], qr[0]);
+        i[4] = psub(ei[0], qi[0]);
+        r[1] = padd(er[1], o1r);
+        i[1] = padd(ei[1], o1i);
+        r[5] = psub(er[1], o1r);
+        i[5] = psub(ei[1], o1i);
+        r[2] = padd(er[2], o2r);
+        i[2] = padd(ei[2], o2i);
+        r[6] = psub(er[2], o2r);
+        i[6] = psub(ei[2], o2i);
+        r[3] = padd(er[3], o3r);
+        i[3] = padd(ei[3], o3i);
+        r[7] = psub(er[3], o3r);
+        i[7] = psub(ei[3], o3i);
     }
 };
 
+// Twiddles are kept in shared memory as float4 (c, c, s, s): both packed operands come out of one
+// 128-bit load as aligned register pairs.
 // (xr + i*xi) *= (c + i*s)
-__device__ __forceinline__ void cmul(float& xr, float& xi, float c, float s)
+__device__ __forceinline__ void cmul(p2& xr, p2& xi, const float4& t)
 {
-    float t = xr * c - xi * s;
-    xi = fmaf(xr, s, xi * c);
-    xr = t;
+    const p2 C = make_float2(t.x, t.y), S = make_float2(t.z, t.w);
+    const p2 nr = pfma(xr, C, pneg(pmul(xi, S)));
+    xi = pfma(xr, S, pmul(xi, C));
+    xr = nr;
 }
 // (xr + i*xi) *= conj(c + i*s)
-__device__ __forceinline__ void cmulc(float& xr, float& xi, float c, float s)
+__device__ __forceinline__ void cmulc(p2& xr, p2& xi, const float4& t)
 {
-    float t = fmaf(xi, s, xr * c);
-    xi = xi * c - xr * s;
-    xr = t;
+    const p2 C = make_float2(t.x, t.y), S = make_float2(t.z, t.w);
+    const p2 nr = pfma(xi, S, pmul(xr, C));
+    xi = pfma(xi, C, pneg(pmul(xr, S)));
+    xr = nr;
 }
 
 }  // namespace fcb200

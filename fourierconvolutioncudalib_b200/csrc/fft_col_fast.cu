@@ -35,21 +35,21 @@ __device__ __forceinline__ float4 ldg_stream(const float2* p)
 }
 
 template <int R>
-__device__ __forceinline__ void split(const float4* v, float* ar, float* ai, float* br, float* bi)
+__device__ __forceinline__ void split(const float4* v, p2* r, p2* i)
 {
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-        ar[k] = v[k].x;
-        ai[k] = v[k].y;
-        br[k] = v[k].z;
-        bi[k] = v[k].w;
+        r[k] = make_float2(v[k].x, v[k].y);   // pair-planar: real parts of the two pencils
+        i[k] = make_float2(v[k].z, v[k].w);
     }
 }
+
+__device__ __forceinline__ float4 join(p2 r, p2 i) { return make_float4(r.x, r.y, i.x, i.y); }
 
 // ---- first forward stage: global (natural rows) -> registers -> smem -----------------------------
 template <int R, int LOADS>
 __device__ __forceinline__ void first_fwd(const float2* __restrict__ base, long long stride, float4* __restrict__ sm,
-                                          const float2* __restrict__ tw, int L, int cp, int w, int W,
+                                          const float4* __restrict__ tw, int L, int cp, int w, int W,
                                           const unsigned char* __restrict__ rowMask)
 {
     constexpr int U = Batch<R, LOADS>::U;
@@ -70,18 +70,13 @@ __device__ __forceinline__ void first_fwd(const float2* __restrict__ base, long 
         for (int u = 0; u < U; ++u) {
             const int j = b0 + u * W;
             if (j < S) {
-                float ar[R], ai[R], br[R], bi[R];
-                split<R>(v[u], ar, ai, br, bi);
-                Dft<R>::run(ar, ai);
-                Dft<R>::run(br, bi);
+                p2 r[R], i[R];
+                split<R>(v[u], r, i);
+                Dft<R>::run(r, i);
 #pragma unroll
-                for (int m = 1; m < R; ++m) {
-                    const float2 t = tw[j * m];
-                    cmul(ar[m], ai[m], t.x, t.y);
-                    cmul(br[m], bi[m], t.x, t.y);
-                }
+                for (int m = 1; m < R; ++m) cmul(r[m], i[m], tw[j * m]);
 #pragma unroll
-                for (int m = 0; m < R; ++m) sm[(j + m * S) * 8 + cp] = make_float4(ar[m], ai[m], br[m], bi[m]);
+                for (int m = 0; m < R; ++m) sm[(j + m * S) * 8 + cp] = join(r[m], i[m]);
             }
         }
     }
@@ -110,12 +105,11 @@ __device__ __forceinline__ void first_inv(const float2* __restrict__ base, long 
         for (int u = 0; u < U; ++u) {
             const int b = b0 + u * W;
             if (b < nb) {
-                float ar[R], ai[R], br[R], bi[R];
-                split<R>(v[u], ar, ai, br, bi);
-                Dft<R>::run(ai, ar);
-                Dft<R>::run(bi, br);
+                p2 r[R], i[R];
+                split<R>(v[u], r, i);
+                Dft<R>::run(i, r);
 #pragma unroll
-                for (int m = 0; m < R; ++m) sm[(b * R + m) * 8 + cp] = make_float4(ar[m], ai[m], br[m], bi[m]);
+                for (int m = 0; m < R; ++m) sm[(b * R + m) * 8 + cp] = join(r[m], i[m]);
             }
         }
     }
@@ -129,51 +123,31 @@ __device__ __forceinline__ void last_fwd(float2* __restrict__ base, long long st
     const int nb = L / R;
     const int fs = L / R;
     for (int b = w; b < nb; b += W) {
-        float ar[R], ai[R], br[R], bi[R];
+        p2 r[R], i[R];
         const int k0 = __ldg(rev + b * R);
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const float4 v = sm[(b * R + k) * 8 + cp];
-            ar[k] = v.x;
-            ai[k] = v.y;
-            br[k] = v.z;
-            bi[k] = v.w;
-        }
-        Dft<R>::run(ar, ai);
-        Dft<R>::run(br, bi);
+        load_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
+        Dft<R>::run(r, i);
 #pragma unroll
         for (int m = 0; m < R; ++m)
-            *reinterpret_cast<float4*>(base + (size_t)(k0 + m * fs) * stride) = make_float4(ar[m], ai[m], br[m], bi[m]);
+            *reinterpret_cast<float4*>(base + (size_t)(k0 + m * fs) * stride) = join(r[m], i[m]);
     }
 }
 
 // ---- last inverse stage: smem -> registers -> global (natural rows) -----------------------------
 template <int R>
 __device__ __forceinline__ void last_inv(float2* __restrict__ base, long long stride, const float4* __restrict__ sm,
-                                         const float2* __restrict__ tw, int L, int cp, int w, int W)
+                                         const float4* __restrict__ tw, int L, int cp, int w, int W)
 {
     const int S = L / R;  // Li == L, j == b
     for (int j = w; j < S; j += W) {
-        float ar[R], ai[R], br[R], bi[R];
+        p2 r[R], i[R];
+        load_pairs<R>(sm, j * 8 + cp, S * 8, r, i);
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const float4 v = sm[(j + k * S) * 8 + cp];
-            ar[k] = v.x;
-            ai[k] = v.y;
-            br[k] = v.z;
-            bi[k] = v.w;
-        }
-#pragma unroll
-        for (int k = 1; k < R; ++k) {
-            const float2 t = tw[j * k];
-            cmulc(ar[k], ai[k], t.x, t.y);
-            cmulc(br[k], bi[k], t.x, t.y);
-        }
-        Dft<R>::run(ai, ar);
-        Dft<R>::run(bi, br);
+        for (int k = 1; k < R; ++k) cmulc(r[k], i[k], tw[j * k]);
+        Dft<R>::run(i, r);
 #pragma unroll
         for (int m = 0; m < R; ++m)
-            *reinterpret_cast<float4*>(base + (size_t)(j + m * S) * stride) = make_float4(ar[m], ai[m], br[m], bi[m]);
+            *reinterpret_cast<float4*>(base + (size_t)(j + m * S) * stride) = join(r[m], i[m]);
     }
 }
 
@@ -200,34 +174,20 @@ __device__ __forceinline__ void mid_fused(const float2* __restrict__ hbase, long
         for (int u = 0; u < U; ++u) {
             const int b = b0 + u * W;
             if (b < nb) {
-                float ar[R], ai[R], br[R], bi[R];
-#pragma unroll
-                for (int k = 0; k < R; ++k) {
-                    const float4 v = sm[(b * R + k) * 8 + cp];
-                    ar[k] = v.x;
-                    ai[k] = v.y;
-                    br[k] = v.z;
-                    bi[k] = v.w;
-                }
-                Dft<R>::run(ar, ai);
-                Dft<R>::run(br, bi);
+                p2 r[R], i[R];
+                load_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
+                Dft<R>::run(r, i);
                 // Dst = c * (Src * Dst), Src = PSF spectrum (reference mulAndScale, :41-45)
 #pragma unroll
                 for (int m = 0; m < R; ++m) {
-                    const float4 hh = h[u][m];
-                    const float xr = c * (hh.x * ar[m] - hh.y * ai[m]);
-                    const float xi = c * (hh.y * ar[m] + hh.x * ai[m]);
-                    const float yr = c * (hh.z * br[m] - hh.w * bi[m]);
-                    const float yi = c * (hh.w * br[m] + hh.z * bi[m]);
-                    ar[m] = xr;
-                    ai[m] = xi;
-                    br[m] = yr;
-                    bi[m] = yi;
+                    const p2 hr = make_float2(h[u][m].x, h[u][m].y), hi = make_float2(h[u][m].z, h[u][m].w);
+                    const p2 xr = pmuls(pfma(hr, r[m], pneg(pmul(hi, i[m]))), c);
+                    const p2 xi = pmuls(pfma(hi, r[m], pmul(hr, i[m])), c);
+                    r[m] = xr;
+                    i[m] = xi;
                 }
-                Dft<R>::run(ai, ar);
-                Dft<R>::run(bi, br);
-#pragma unroll
-                for (int m = 0; m < R; ++m) sm[(b * R + m) * 8 + cp] = make_float4(ar[m], ai[m], br[m], bi[m]);
+                Dft<R>::run(i, r);
+                store_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
             }
         }
     }
@@ -244,9 +204,9 @@ __device__ __forceinline__ void mid_fused(const float2* __restrict__ hbase, long
     }
 
 template <bool INV>
-__device__ __forceinline__ void mid_stage(int R, float4* sm, const float2* tw, int L, int Li, int cp, int w, int W)
+__device__ __forceinline__ void mid_stage(int R, float4* sm, const float4* tw, int L, int Li, int cp, int w, int W)
 {
-    FC_RADIX_SWITCH(R, (stage_smem<RR, INV, false>(sm, tw, L, Li, cp, w, W, 8)));
+    FC_RADIX_SWITCH(R, (stage_smem<RR, INV>(sm, tw, L, Li, cp, w, W, 8)));
 }
 
 }  // namespace
@@ -260,7 +220,7 @@ __global__ void __launch_bounds__(MAXT, MINB) col_fast_kernel(ColArgs a)
     const int L = a.P.L;
     const int ns = a.P.ns;
     float4* sm = smem;
-    float2* tw_s = reinterpret_cast<float2*>(sm + (size_t)L * 8);
+    float4* tw_s = sm + (size_t)L * 8;
 
     const int t = threadIdx.x;
     const int cp = t & 7, w = t >> 3, W = blockDim.x >> 3;
@@ -273,7 +233,7 @@ __global__ void __launch_bounds__(MAXT, MINB) col_fast_kernel(ColArgs a)
     const size_t off = (size_t)group * a.groupStride + col0 + 2 * cp;
     float2* base = a.data + off;
 
-    for (int i = t; i < L; i += blockDim.x) tw_s[i] = __ldg(a.P.tw + i);
+    load_twiddles(tw_s, a.P.tw, L);
     __syncthreads();
 
     const int Rf = a.P.radix[0];
@@ -313,7 +273,7 @@ __global__ void __launch_bounds__(MAXT, MINB) col_fast_kernel(ColArgs a)
 bool col_fast_supported(const AxisPlanDev& P)
 {
     if (P.generic || P.ns < 2) return false;
-    const size_t need = (size_t)P.L * 8 * sizeof(float4) + (size_t)P.L * sizeof(float2);
+    const size_t need = (size_t)P.L * 8 * sizeof(float4) + (size_t)P.L * sizeof(float4);
     return need <= (size_t)kMaxDynSmem;
 }
 
@@ -330,7 +290,7 @@ void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t
 {
     static const int variant = env_int("FCB200_COL_VARIANT", 0);
     static const int threads_env = env_int("FCB200_COL_THREADS", 0);
-    const size_t smem = (size_t)a.P.L * 8 * sizeof(float4) + (size_t)a.P.L * sizeof(float2);
+    const size_t smem = (size_t)a.P.L * 8 * sizeof(float4) + (size_t)a.P.L * sizeof(float4);
     const long long grid = ngroups * a.tilesPerGroup;
     if (grid == 0) return;
     if (grid > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");

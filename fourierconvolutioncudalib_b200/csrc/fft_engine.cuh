@@ -2,8 +2,10 @@
 // mirrored decimation-in-time inverse, on a tile of pencils held as sm[position][column-pair].
 //
 // Tile layout: one tile row per transform position, TXP float4 per row; a float4 holds the same
-// position of two adjacent pencils (re0, im0, re1, im1).  With TXP = 8 a row is 128 bytes = all 32
-// banks, and the 8 lanes that share a worker index read one full row: every shared-memory access
+// position of two adjacent pencils in PAIR-PLANAR form (re0, re1, im0, im1), so the real parts and
+// the imaginary parts of the two pencils are aligned register pairs and every butterfly runs on
+// Blackwell's packed fp32 instructions (fft_butterflies.cuh).  With TXP = 8 a row is 128 bytes = all
+// 32 banks, and the 8 lanes that share a worker index read one full row: every shared-memory access
 // of the engine is conflict-free without padding.  Thread t works on column pair cp = t % TXP as
 // worker w = t / TXP; workers split the butterflies of a stage.
 //
@@ -22,21 +24,37 @@
 
 namespace fcb200 {
 
-// XOR swizzle of the column-pair slot, used by the X pass whose tile is filled by a transposing
-// load (lanes run along positions there).  Bijective over 8 consecutive positions, over the 8 even
-// and over the 8 odd positions of a 16-aligned group (tests/engine_model.py: swz).
-__device__ __forceinline__ int swz8(int pos) { return (pos ^ (pos >> 3)) & 7; }
-
-template <bool SWZ>
-__device__ __forceinline__ int tile_idx(int pos, int cp, int txp)
+// twiddle table in shared memory: float4 (c, c, s, s) per root, from the global float2 (c, s) table
+__device__ __forceinline__ void load_twiddles(float4* tw_s, const float2* tw_g, int L)
 {
-    return SWZ ? (pos * 8 + (cp ^ swz8(pos))) : (pos * txp + cp);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const float2 t = __ldg(tw_g + i);
+        tw_s[i] = make_float4(t.x, t.x, t.y, t.y);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void load_pairs(const float4* __restrict__ buf, int idx0, int step, p2* r, p2* i)
+{
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const float4 v = buf[idx0 + k * step];
+        r[k] = make_float2(v.x, v.y);
+        i[k] = make_float2(v.z, v.w);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void store_pairs(float4* __restrict__ buf, int idx0, int step, const p2* r, const p2* i)
+{
+#pragma unroll
+    for (int m = 0; m < R; ++m) buf[idx0 + m * step] = make_float4(r[m].x, r[m].y, i[m].x, i[m].y);
 }
 
 // One in-register radix-R stage, shared memory -> shared memory, in place.
 //   L   transform length, Li current block length (forward: before the stage; inverse: after it)
-template <int R, bool INV, bool SWZ>
-__device__ __forceinline__ void stage_smem(float4* __restrict__ buf, const float2* __restrict__ tw, int L, int Li,
+template <int R, bool INV>
+__device__ __forceinline__ void stage_smem(float4* __restrict__ buf, const float4* __restrict__ tw, int L, int Li,
                                            int cp, int w, int W, int txp)
 {
     const int S = Li / R;
@@ -47,49 +65,30 @@ __device__ __forceinline__ void stage_smem(float4* __restrict__ buf, const float
         // b / S without an integer division: exact for b < 2^16 (checked exhaustively on the host)
         const int beta = __float2int_rz(((float)b + 0.5f) * invS);
         const int j = b - beta * S;
-        const int base = beta * Li + j;
-        float ar[R], ai[R], br[R], bi[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            float4 v = buf[tile_idx<SWZ>(base + k * S, cp, txp)];
-            ar[k] = v.x;
-            ai[k] = v.y;
-            br[k] = v.z;
-            bi[k] = v.w;
-        }
+        const int idx0 = (beta * Li + j) * txp + cp;
+        p2 r[R], i[R];
+        load_pairs<R>(buf, idx0, S * txp, r, i);
         if (INV) {
             if (S > 1) {
 #pragma unroll
-                for (int k = 1; k < R; ++k) {
-                    float2 t = tw[j * k * tstep];
-                    cmulc(ar[k], ai[k], t.x, t.y);
-                    cmulc(br[k], bi[k], t.x, t.y);
-                }
+                for (int k = 1; k < R; ++k) cmulc(r[k], i[k], tw[j * k * tstep]);
             }
-            Dft<R>::run(ai, ar);
-            Dft<R>::run(bi, br);
+            Dft<R>::run(i, r);
         } else {
-            Dft<R>::run(ar, ai);
-            Dft<R>::run(br, bi);
+            Dft<R>::run(r, i);
             if (S > 1) {
 #pragma unroll
-                for (int m = 1; m < R; ++m) {
-                    float2 t = tw[j * m * tstep];
-                    cmul(ar[m], ai[m], t.x, t.y);
-                    cmul(br[m], bi[m], t.x, t.y);
-                }
+                for (int m = 1; m < R; ++m) cmul(r[m], i[m], tw[j * m * tstep]);
             }
         }
-#pragma unroll
-        for (int m = 0; m < R; ++m)
-            buf[tile_idx<SWZ>(base + m * S, cp, txp)] = make_float4(ar[m], ai[m], br[m], bi[m]);
+        store_pairs<R>(buf, idx0, S * txp, r, i);
     }
 }
 
 // Generic prime radix p (run-time), src -> dst (distinct tile buffers).
-template <bool INV, bool SWZ>
+template <bool INV>
 __device__ __forceinline__ void stage_generic(const float4* __restrict__ src, float4* __restrict__ dst,
-                                              const float2* __restrict__ tw, int L, int Li, int p, int cp, int w,
+                                              const float4* __restrict__ tw, int L, int Li, int p, int cp, int w,
                                               int W, int txp)
 {
     const int S = Li / p;
@@ -98,60 +97,57 @@ __device__ __forceinline__ void stage_generic(const float4* __restrict__ src, fl
     const float invS = 1.0f / (float)S, invLi = 1.0f / (float)Li;
     for (int o = w; o < L; o += W) {
         const int beta = __float2int_rz(((float)o + 0.5f) * invLi);
-        const int r = o - beta * Li;
-        const int m = __float2int_rz(((float)r + 0.5f) * invS);
-        const int j = r - m * S;
+        const int rr = o - beta * Li;
+        const int m = __float2int_rz(((float)rr + 0.5f) * invS);
+        const int j = rr - m * S;
         const int base = beta * Li + j;
         // forward: y_m = w_Li^{j m} * sum_k x_k w_p^{k m}
         // inverse: y_m = sum_k x_k conj(w_Li^{j k} w_p^{k m})      (both roots come from the one table)
         const int inc = INV ? (j * tstep + m * rstep) : (m * rstep);
         int idx = 0;
-        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        p2 ar = make_float2(0.f, 0.f), ai = make_float2(0.f, 0.f);
         for (int k = 0; k < p; ++k) {
-            float2 t = tw[idx];
-            float4 v = src[tile_idx<SWZ>(base + k * S, cp, txp)];
+            const float4 t = tw[idx];
+            const float4 v = src[(base + k * S) * txp + cp];
+            const p2 C = make_float2(t.x, t.y), Sn = make_float2(t.z, t.w);
+            const p2 xr = make_float2(v.x, v.y), xi = make_float2(v.z, v.w);
             if (INV) {
-                a0 = fmaf(v.x, t.x, fmaf(v.y, t.y, a0));
-                a1 = fmaf(v.y, t.x, fmaf(-v.x, t.y, a1));
-                b0 = fmaf(v.z, t.x, fmaf(v.w, t.y, b0));
-                b1 = fmaf(v.w, t.x, fmaf(-v.z, t.y, b1));
+                ar = pfma(xr, C, pfma(xi, Sn, ar));
+                ai = pfma(xi, C, pfma(xr, pneg(Sn), ai));
             } else {
-                a0 = fmaf(v.x, t.x, fmaf(-v.y, t.y, a0));
-                a1 = fmaf(v.y, t.x, fmaf(v.x, t.y, a1));
-                b0 = fmaf(v.z, t.x, fmaf(-v.w, t.y, b0));
-                b1 = fmaf(v.w, t.x, fmaf(v.z, t.y, b1));
+                ar = pfma(xr, C, pfma(xi, pneg(Sn), ar));
+                ai = pfma(xi, C, pfma(xr, Sn, ai));
             }
             idx += inc;
             if (idx >= L) idx -= L;
         }
-        if (!INV && S > 1) {
-            float2 t = tw[j * m * tstep];
-            cmul(a0, a1, t.x, t.y);
-            cmul(b0, b1, t.x, t.y);
-        }
-        dst[tile_idx<SWZ>(o, cp, txp)] = make_float4(a0, a1, b0, b1);
+        if (!INV && S > 1) cmul(ar, ai, tw[j * m * tstep]);
+        dst[o * txp + cp] = make_float4(ar.x, ar.y, ai.x, ai.y);
     }
 }
 
-template <bool INV, bool SWZ>
-__device__ __forceinline__ void stage_dispatch(int R, float4*& cur, float4*& oth, const float2* tw, int L, int Li,
+__device__ __forceinline__ bool is_fast_radix(int R)
+{
+    return R == 1 || R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8;
+}
+
+template <bool INV>
+__device__ __forceinline__ void stage_dispatch(int R, float4*& cur, float4*& oth, const float4* tw, int L, int Li,
                                                int cp, int w, int W, int txp, bool active)
 {
-    bool swap = false;
     if (active) {
         switch (R) {
             case 1: break;
-            case 2: stage_smem<2, INV, SWZ>(cur, tw, L, Li, cp, w, W, txp); break;
-            case 3: stage_smem<3, INV, SWZ>(cur, tw, L, Li, cp, w, W, txp); break;
-            case 4: stage_smem<4, INV, SWZ>(cur, tw, L, Li, cp, w, W, txp); break;
-            case 5: stage_smem<5, INV, SWZ>(cur, tw, L, Li, cp, w, W, txp); break;
-            case 7: stage_smem<7, INV, SWZ>(cur, tw, L, Li, cp, w, W, txp); break;
-            case 8: stage_smem<8, INV, SWZ>(cur, tw, L, Li, cp, w, W, txp); break;
-            default: stage_generic<INV, SWZ>(cur, oth, tw, L, Li, R, cp, w, W, txp); break;
+            case 2: stage_smem<2, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 3: stage_smem<3, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 4: stage_smem<4, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 5: stage_smem<5, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 7: stage_smem<7, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 8: stage_smem<8, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            default: stage_generic<INV>(cur, oth, tw, L, Li, R, cp, w, W, txp); break;
         }
     }
-    swap = !(R == 1 || R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8);
-    if (swap) {
+    if (!is_fast_radix(R)) {
         float4* t = cur;
         cur = oth;
         oth = t;
@@ -162,8 +158,8 @@ __device__ __forceinline__ void stage_dispatch(int R, float4*& cur, float4*& oth
 // Ends with a __syncthreads(); returns the buffer that holds the result.
 //   forward: natural order in, position p holds frequency P.rev[p] out
 //   inverse: the mirror image (scaled by L, like cuFFT's unnormalised inverse)
-template <bool INV, bool SWZ>
-__device__ __forceinline__ float4* engine_run(const AxisPlanDev& P, float4* A, float4* B, const float2* tw, int cp,
+template <bool INV>
+__device__ __forceinline__ float4* engine_run(const AxisPlanDev& P, float4* A, float4* B, const float4* tw, int cp,
                                               int w, int W, int txp, bool active)
 {
     float4* cur = A;
@@ -172,7 +168,7 @@ __device__ __forceinline__ float4* engine_run(const AxisPlanDev& P, float4* A, f
         int Li = P.L;
         for (int s = 0; s < P.ns; ++s) {
             const int R = P.radix[s];
-            stage_dispatch<false, SWZ>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active);
+            stage_dispatch<false>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active);
             Li /= R;
             __syncthreads();
         }
@@ -181,7 +177,7 @@ __device__ __forceinline__ float4* engine_run(const AxisPlanDev& P, float4* A, f
         for (int s = P.ns - 1; s >= 0; --s) {
             const int R = P.radix[s];
             Li *= R;
-            stage_dispatch<true, SWZ>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active);
+            stage_dispatch<true>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active);
             __syncthreads();
         }
     }

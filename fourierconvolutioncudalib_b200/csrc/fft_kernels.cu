@@ -72,40 +72,36 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-__device__ __forceinline__ void load_twiddles(float2* tw_s, const float2* tw_g, int L)
-{
-    for (int i = threadIdx.x; i < L; i += blockDim.x) tw_s[i] = __ldg(tw_g + i);
-}
-
 // ------------------------------------------------------------------------------------------------
 // X passes.  16 rows per CTA, two shared-memory tiles:
-//   row tile    [16 rows][P float2], P odd: filled / drained with lanes running along x (coalesced,
-//               conflict-free), read / written column-wise with lanes running along rows
-//               (conflict-free because P is odd);
-//   engine tile [L positions][16 rows] float2 = [L][8] float4: the layout of fft_engine.cuh.
+//   row tile    [16 rows][P float2], P odd: holds global rows verbatim (real rows as float2 = two
+//               consecutive samples; spectrum rows in pair-planar form).  Filled / drained with lanes
+//               running along x (coalesced, conflict-free); read / written column-wise with lanes
+//               running along row pairs (conflict-free because P is odd);
+//   engine tile [L positions][8 row pairs] float4, pair-planar: the layout of fft_engine.cuh.
 // Moving data between the two tiles is the transposition; kx comes out in natural order.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ int x_row_pitch(int L, int xc) { return (L > xc ? L : xc) | 1; }
+__host__ __device__ __forceinline__ int x_row_pitch(int L, int xcp) { return (L > xcp ? L : xcp) | 1; }
 
-// engine tile viewed as float2: (position, local row)
-__device__ __forceinline__ int eidx(int pos, int lrow) { return pos * 16 + lrow; }
+// float index of the real part of column k inside a pair-planar row (imaginary part at +2)
+__device__ __forceinline__ int pp(int k) { return ((k >> 1) << 2) | (k & 1); }
 
 struct XSmem {
-    float2* rowt;
     float4* A;
     float4* B;
-    float2* tw;
+    float4* tw;
+    float2* rowt;
     int P;
 };
 
 __device__ __forceinline__ XSmem x_carve(float4* smem, const Geometry& g, const AxisPlanDev& pl)
 {
     XSmem s;
-    s.P = x_row_pitch(pl.L, g.xc);
-    s.A = smem;                                                   // engine tile first: 16-byte aligned
+    s.P = x_row_pitch(pl.L, g.xcp);
+    s.A = smem;
     s.B = pl.generic ? (s.A + (size_t)pl.L * 8) : nullptr;
-    s.tw = reinterpret_cast<float2*>(s.A + (size_t)pl.L * 8 * (pl.generic ? 2 : 1));
-    s.rowt = s.tw + pl.L;
+    s.tw = s.A + (size_t)pl.L * 8 * (pl.generic ? 2 : 1);
+    s.rowt = reinterpret_cast<float2*>(s.tw + pl.L);
     return s;
 }
 
@@ -151,54 +147,69 @@ __global__ void __launch_bounds__(kColThreads) x_fwd_kernel(XArgs a)
     cp_async_wait_all();
     __syncthreads();
 
-    // ---- row tile -> engine tile (lanes along rows: the transposition)
-    {
-        float2* E = reinterpret_cast<float2*>(sm.A);
-        const int lrow = t & 15, q = t >> 4, Q = blockDim.x >> 4;
-        for (int pos = q; pos < L; pos += Q) E[eidx(pos, lrow)] = rowt[lrow * P + pos];
+    // ---- row tile -> engine tile (lanes along row pairs: the transposition)
+    for (int pos = w; pos < L; pos += W) {
+        const float2 u = rowt[(2 * cp) * P + pos], v = rowt[(2 * cp + 1) * P + pos];
+        sm.A[pos * 8 + cp] = make_float4(u.x, v.x, u.y, v.y);
     }
     __syncthreads();
 
-    float4* cur = engine_run<false, false>(a.P, sm.A, sm.B, sm.tw, cp, w, W, 8, true);
+    float4* cur = engine_run<false>(a.P, sm.A, sm.B, sm.tw, cp, w, W, 8, true);
 
-    // ---- engine tile -> row tile in natural kx order, splitting the packed transform (even nx)
+    // ---- engine tile -> row tile (pair-planar spectrum rows, natural kx); even nx: split the
+    //      packed half-length transform into the spectrum of the real rows
     {
-        const float2* E = reinterpret_cast<const float2*>(cur);
-        const int lrow = t & 15, q = t >> 4, Q = blockDim.x >> 4;
-        float2* out = rowt + lrow * P;
+        float* ra = reinterpret_cast<float*>(rowt + (2 * cp) * P);
+        float* rb = reinterpret_cast<float*>(rowt + (2 * cp + 1) * P);
+        auto put = [&](int k, p2 re, p2 im) {
+            const int f = pp(k);
+            ra[f] = re.x;
+            ra[f + 2] = im.x;
+            rb[f] = re.y;
+            rb[f + 2] = im.y;
+        };
         if (g.odd) {
-            for (int k = q; k < g.xc; k += Q) out[k] = E[eidx(__ldg(a.P.pos + k), lrow)];
+            for (int k = w; k < g.xc; k += W) {
+                const float4 v = cur[__ldg(a.P.pos + k) * 8 + cp];
+                put(k, make_float2(v.x, v.y), make_float2(v.z, v.w));
+            }
         } else {
             const int M = g.M;
-            for (int k = q; k <= M / 2; k += Q) {
+            for (int k = w; k <= M / 2; k += W) {
                 if (k == 0) {
-                    const float2 v = E[eidx(__ldg(a.P.pos), lrow)];
-                    out[0] = make_float2(v.x + v.y, 0.f);
-                    out[M] = make_float2(v.x - v.y, 0.f);
+                    const float4 v = cur[__ldg(a.P.pos) * 8 + cp];
+                    const p2 r = make_float2(v.x, v.y), i = make_float2(v.z, v.w), z = make_float2(0.f, 0.f);
+                    put(0, padd(r, i), z);
+                    put(M, psub(r, i), z);
                 } else {
                     const int k2 = M - k;
-                    const float2 va = E[eidx(__ldg(a.P.pos + k), lrow)];
-                    const float2 vb = E[eidx(__ldg(a.P.pos + k2), lrow)];
+                    const float4 va = cur[__ldg(a.P.pos + k) * 8 + cp];
+                    const float4 vb = cur[__ldg(a.P.pos + k2) * 8 + cp];
                     const float2 tk = __ldg(a.twx + k);  // exp(-2*pi*i*k/nx)
-                    const float er = 0.5f * (va.x + vb.x), ei = 0.5f * (va.y - vb.y);
-                    const float orr = 0.5f * (va.y + vb.y), oi = -0.5f * (va.x - vb.x);
-                    const float wr = tk.x * orr - tk.y * oi, wi = tk.x * oi + tk.y * orr;
-                    out[k] = make_float2(er + wr, ei + wi);
-                    out[k2] = make_float2(er - wr, -(ei - wi));
+                    const p2 ar = make_float2(va.x, va.y), ai = make_float2(va.z, va.w);
+                    const p2 br = make_float2(vb.x, vb.y), bi = make_float2(vb.z, vb.w);
+                    const p2 er = pmuls(padd(ar, br), 0.5f), ei = pmuls(psub(ai, bi), 0.5f);
+                    const p2 orr = pmuls(padd(ai, bi), 0.5f), oi = pmuls(psub(ar, br), -0.5f);
+                    const p2 wr = pfmas(orr, tk.x, pmuls(oi, -tk.y));   // c*or - s*oi
+                    const p2 wi = pfmas(oi, tk.x, pmuls(orr, tk.y));    // c*oi + s*or
+                    put(k, padd(er, wr), padd(ei, wi));
+                    put(k2, psub(er, wr), psub(wi, ei));
                 }
             }
         }
+        // pad columns [xc, xcp) are kept at zero so that the strided passes never see garbage
+        for (int k = g.xc + w; k < g.xcp; k += W) put(k, make_float2(0.f, 0.f), make_float2(0.f, 0.f));
     }
     __syncthreads();
 
-    // ---- row tile -> spectrum rows (pad columns written as zeros)
+    // ---- row tile -> spectrum rows (verbatim)
     for (int lrow = warp; lrow < 16; lrow += nwarps) {
         const long long li = row0 + lrow;
         const long long grow = (li < a.nrows) ? (a.rowList ? (long long)a.rowList[li] : li) : -1;
         if (grow < 0) continue;
         const float2* src = rowt + lrow * P;
         float2* dst = a.spec + grow * g.xcp;
-        for (int k = lane; k < g.xcp; k += 32) dst[k] = (k < g.xc) ? src[k] : make_float2(0.f, 0.f);
+        for (int k = lane; k < g.xcp; k += 32) dst[k] = src[k];
     }
 }
 
@@ -221,15 +232,15 @@ __global__ void __launch_bounds__(kColThreads) x_inv_kernel(XArgs a)
 
     load_twiddles(sm.tw, a.P.tw, L);
 
-    // ---- spectrum rows -> row tile
+    // ---- spectrum rows -> row tile (verbatim, asynchronous)
     for (int lrow = warp; lrow < 16; lrow += nwarps) {
         const long long grow = row0 + lrow;
         float2* dst = rowt + lrow * P;
         if (grow < a.nrows) {
             const float2* src = a.spec + grow * g.xcp;
-            for (int k = lane; k < g.xc; k += 32) cp_async8(dst + k, src + k);
+            for (int k = lane; k < g.xcp; k += 32) cp_async8(dst + k, src + k);
         } else {
-            for (int k = lane; k < g.xc; k += 32) dst[k] = make_float2(0.f, 0.f);
+            for (int k = lane; k < g.xcp; k += 32) dst[k] = make_float2(0.f, 0.f);
         }
     }
     cp_async_wait_all();
@@ -237,43 +248,56 @@ __global__ void __launch_bounds__(kColThreads) x_inv_kernel(XArgs a)
 
     // ---- row tile -> engine tile (positions), merging the half spectrum into the packed transform
     {
-        float2* E = reinterpret_cast<float2*>(sm.A);
-        const int lrow = t & 15, q = t >> 4, Q = blockDim.x >> 4;
-        const float2* in = rowt + lrow * P;
+        const float* ra = reinterpret_cast<const float*>(rowt + (2 * cp) * P);
+        const float* rb = reinterpret_cast<const float*>(rowt + (2 * cp + 1) * P);
+        auto get = [&](int k, p2& re, p2& im) {
+            const int f = pp(k);
+            re = make_float2(ra[f], rb[f]);
+            im = make_float2(ra[f + 2], rb[f + 2]);
+        };
         if (g.odd) {
-            for (int k = q; k < g.xc; k += Q) {
-                const float2 v = in[k];
-                E[eidx(__ldg(a.P.pos + k), lrow)] = v;
-                if (k > 0) E[eidx(__ldg(a.P.pos + (g.nx - k)), lrow)] = make_float2(v.x, -v.y);
+            for (int k = w; k < g.xc; k += W) {
+                p2 re, im;
+                get(k, re, im);
+                sm.A[__ldg(a.P.pos + k) * 8 + cp] = make_float4(re.x, re.y, im.x, im.y);
+                if (k > 0) sm.A[__ldg(a.P.pos + (g.nx - k)) * 8 + cp] = make_float4(re.x, re.y, -im.x, -im.y);
             }
         } else {
             const int M = g.M;
-            for (int k = q; k <= M / 2; k += Q) {
+            for (int k = w; k <= M / 2; k += W) {
                 if (k == 0) {
-                    const float2 x0 = in[0], xm = in[M];
-                    E[eidx(__ldg(a.P.pos), lrow)] = make_float2(x0.x + xm.x, x0.x - xm.x);
+                    p2 x0r, x0i, xmr, xmi;
+                    get(0, x0r, x0i);
+                    get(M, xmr, xmi);
+                    const p2 zr = padd(x0r, xmr), zi = psub(x0r, xmr);
+                    sm.A[__ldg(a.P.pos) * 8 + cp] = make_float4(zr.x, zr.y, zi.x, zi.y);
                 } else {
                     const int k2 = M - k;
-                    const float2 va = in[k], vb = in[k2];
+                    p2 ar, ai, br, bi;
+                    get(k, ar, ai);
+                    get(k2, br, bi);
                     const float2 tk = __ldg(a.twx + k);
-                    const float sr = va.x + vb.x, si = va.y - vb.y;
-                    const float Dr = va.x - vb.x, Di = va.y + vb.y;
-                    const float dr = Dr * tk.x + Di * tk.y, di = Di * tk.x - Dr * tk.y;  // D * conj(w)
-                    E[eidx(__ldg(a.P.pos + k), lrow)] = make_float2(sr - di, si + dr);
-                    if (k2 != k) E[eidx(__ldg(a.P.pos + k2), lrow)] = make_float2(sr + di, dr - si);
+                    const p2 sr = padd(ar, br), si = psub(ai, bi);
+                    const p2 Dr = psub(ar, br), Di = padd(ai, bi);
+                    const p2 dr = pfmas(Dr, tk.x, pmuls(Di, tk.y));    // D * conj(w)
+                    const p2 di = pfmas(Di, tk.x, pmuls(Dr, -tk.y));
+                    const p2 z1r = psub(sr, di), z1i = padd(si, dr);
+                    const p2 z2r = padd(sr, di), z2i = psub(dr, si);
+                    sm.A[__ldg(a.P.pos + k) * 8 + cp] = make_float4(z1r.x, z1r.y, z1i.x, z1i.y);
+                    if (k2 != k) sm.A[__ldg(a.P.pos + k2) * 8 + cp] = make_float4(z2r.x, z2r.y, z2i.x, z2i.y);
                 }
             }
         }
     }
     __syncthreads();
 
-    float4* cur = engine_run<true, false>(a.P, sm.A, sm.B, sm.tw, cp, w, W, 8, true);
+    float4* cur = engine_run<true>(a.P, sm.A, sm.B, sm.tw, cp, w, W, 8, true);
 
-    // ---- engine tile -> row tile (natural order), then row tile -> real rows
-    {
-        const float2* E = reinterpret_cast<const float2*>(cur);
-        const int lrow = t & 15, q = t >> 4, Q = blockDim.x >> 4;
-        for (int pos = q; pos < L; pos += Q) rowt[lrow * P + pos] = E[eidx(pos, lrow)];
+    // ---- engine tile -> row tile (real rows, natural order), then row tile -> global
+    for (int pos = w; pos < L; pos += W) {
+        const float4 v = cur[pos * 8 + cp];
+        rowt[(2 * cp) * P + pos] = make_float2(v.x, v.z);
+        rowt[(2 * cp + 1) * P + pos] = make_float2(v.y, v.w);
     }
     __syncthreads();
     for (int lrow = warp; lrow < 16; lrow += nwarps) {
@@ -301,7 +325,7 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
     const int txp = a.txp;
     float4* A = smem;
     float4* B = a.P.generic ? (A + (size_t)L * txp) : nullptr;
-    float2* tw_s = reinterpret_cast<float2*>(A + (size_t)L * txp * (a.P.generic ? 2 : 1));
+    float4* tw_s = A + (size_t)L * txp * (a.P.generic ? 2 : 1);
 
     const int t = threadIdx.x;
     const int cp = t % txp, w = t / txp, W = blockDim.x / txp;
@@ -328,9 +352,9 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
 
     float4* cur;
     if (MODE == 1) {
-        cur = engine_run<true, false>(a.P, A, B, tw_s, cp, w, W, txp, active);
+        cur = engine_run<true>(a.P, A, B, tw_s, cp, w, W, txp, active);
     } else {
-        cur = engine_run<false, false>(a.P, A, B, tw_s, cp, w, W, txp, active);
+        cur = engine_run<false>(a.P, A, B, tw_s, cp, w, W, txp, active);
     }
 
     if (MODE == 2) {
@@ -342,17 +366,18 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
                 const int k = __ldg(a.P.rev + p);
                 const float4 h = __ldg(reinterpret_cast<const float4*>(hb + (size_t)k * a.stride));
                 const float4 v = cur[p * txp + cp];
+                // pair-planar: (x, y) = real parts, (z, w) = imaginary parts of the two pencils
                 float4 o;
-                o.x = c * (h.x * v.x - h.y * v.y);
-                o.y = c * (h.y * v.x + h.x * v.y);
-                o.z = c * (h.z * v.z - h.w * v.w);
-                o.w = c * (h.w * v.z + h.z * v.w);
+                o.x = c * (h.x * v.x - h.z * v.z);
+                o.y = c * (h.y * v.y - h.w * v.w);
+                o.z = c * (h.z * v.x + h.x * v.z);
+                o.w = c * (h.w * v.y + h.y * v.w);
                 cur[p * txp + cp] = o;
             }
         }
         __syncthreads();
         float4* oth = (cur == A) ? B : A;
-        cur = engine_run<true, false>(a.P, cur, oth, tw_s, cp, w, W, txp, active);
+        cur = engine_run<true>(a.P, cur, oth, tw_s, cp, w, W, txp, active);
     }
 
     if (active) {
@@ -368,8 +393,8 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
 // ------------------------------------------------------------------------------------------------
 static size_t x_smem_bytes(const Geometry& g, const AxisPlanDev& P)
 {
-    const size_t rowt = 16 * (size_t)x_row_pitch(P.L, g.xc) * sizeof(float2);
-    return (size_t)P.L * 8 * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)P.L * sizeof(float2) + rowt;
+    const size_t rowt = 16 * (size_t)x_row_pitch(P.L, g.xcp) * sizeof(float2);
+    return (size_t)P.L * 8 * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)P.L * sizeof(float4) + rowt;
 }
 
 bool x_pass_supported(const Geometry& g, const AxisPlanDev& P) { return x_smem_bytes(g, P) <= (size_t)kMaxDynSmem; }
@@ -377,7 +402,7 @@ bool x_pass_supported(const Geometry& g, const AxisPlanDev& P) { return x_smem_b
 int col_pick_txp(const AxisPlanDev& P)
 {
     for (int txp = 8; txp >= 1; txp >>= 1) {
-        size_t need = (size_t)P.L * txp * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)P.L * sizeof(float2);
+        size_t need = (size_t)P.L * txp * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)P.L * sizeof(float4);
         if (need <= (size_t)kMaxDynSmem) return txp;
     }
     return 0;
@@ -427,7 +452,7 @@ void launch_x_inv(const XArgs& a, cudaStream_t st)
 
 void launch_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
-    const size_t smem = (size_t)a.P.L * a.txp * sizeof(float4) * (a.P.generic ? 2 : 1) + (size_t)a.P.L * sizeof(float2);
+    const size_t smem = (size_t)a.P.L * a.txp * sizeof(float4) * (a.P.generic ? 2 : 1) + (size_t)a.P.L * sizeof(float4);
     const long long grid = ngroups * a.tilesPerGroup;
     if (grid == 0) return;
     if (grid > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
