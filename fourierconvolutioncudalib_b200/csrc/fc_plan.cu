@@ -343,6 +343,7 @@ static ColArgs y_args(ConvPlan& p, float2* data)
 
 static void col_pass(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
+    if (launch_col_static(a, mode, ngroups, st)) return;
     if (a.txp == 8 && col_fast_supported(a.P)) launch_col_fast(a, mode, ngroups, st);
     else launch_col(a, mode, ngroups, st);
 }

@@ -31,6 +31,7 @@ struct ColArgs {
 };
 
 bool x_pass_supported(const Geometry& g, const AxisPlanDev& P);
+size_t x_smem_bytes(const Geometry& g, const AxisPlanDev& P);
 int col_pick_txp(const AxisPlanDev& P);
 void launch_x_fwd(const XArgs& a, bool psf, cudaStream_t st);
 void launch_x_inv(const XArgs& a, cudaStream_t st);
@@ -38,5 +39,9 @@ void launch_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
 // fast path (fft_col_fast.cu): first/last stage fused with the global loads/stores
 bool col_fast_supported(const AxisPlanDev& P);
 void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
+// compile-time specialised kernels (fft_static.cu); return false when none matches the plan
+bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
+bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st);
+bool launch_x_inv_static(const XArgs& a, cudaStream_t st);
 
 }  // namespace fcb200
