@@ -40,7 +40,7 @@ __host__ __device__ constexpr int srev(int p)
 }
 
 // ---- shared -> shared stage ---------------------------------------------------------------------
-template <int R, int L, int Li, int NW, bool INV>
+template <int R, int L, int Li, int NW, bool INV, int TXP = 8>
 __device__ __forceinline__ void sstage(float4* __restrict__ buf, const float4* __restrict__ tw, int cp, int w)
 {
     constexpr int S = Li / R, nb = L / R, tstep = L / Li;
@@ -50,9 +50,9 @@ __device__ __forceinline__ void sstage(float4* __restrict__ buf, const float4* _
         const int b = w + it * NW;
         if ((nb % NW) != 0 && b >= nb) break;
         const int beta = b / S, j = b % S;     // S is a constant: shifts / multiply-high
-        const int idx0 = (beta * Li + j) * 8 + cp;
+        const int idx0 = (beta * Li + j) * TXP + cp;
         p2 r[R], i[R];
-        load_pairs<R>(buf, idx0, S * 8, r, i);
+        load_pairs<R>(buf, idx0, S * TXP, r, i);
         if (INV) {
             if (S > 1) {
 #pragma unroll
@@ -66,7 +66,7 @@ __device__ __forceinline__ void sstage(float4* __restrict__ buf, const float4* _
                 for (int m = 1; m < R; ++m) cmul(r[m], i[m], tw[j * (m * tstep)]);
             }
         }
-        store_pairs<R>(buf, idx0, S * 8, r, i);
+        store_pairs<R>(buf, idx0, S * TXP, r, i);
     }
 }
 
@@ -88,7 +88,7 @@ __device__ __forceinline__ void ssplit(const float4* v, p2* r, p2* i)
 
 // ---- first forward stage: global rows j + k*S -> smem --------------------------------------------
 // U butterflies are loaded before any arithmetic (U*R float4 in flight per thread).
-template <int R, int L, int NW, int U, bool MASKED>
+template <int R, int L, int NW, int U, bool MASKED, int TXP = 8>
 __device__ __forceinline__ void sfirst_fwd(const float2* __restrict__ base, size_t stride, float4* __restrict__ sm,
                                            const float4* __restrict__ tw, int cp, int w,
                                            const unsigned char* __restrict__ rowMask)
@@ -122,13 +122,13 @@ __device__ __forceinline__ void sfirst_fwd(const float2* __restrict__ base, size
             Dft<R>::run(r, i);
 #pragma unroll
             for (int m = 1; m < R; ++m) cmul(r[m], i[m], tw[j * m]);
-            store_pairs<R>(sm, j * 8 + cp, S * 8, r, i);
+            store_pairs<R>(sm, j * TXP + cp, S * TXP, r, i);
         }
     }
 }
 
 // ---- first inverse stage: global rows rev(b*R) + k*(L/R) -> smem positions b*R + k ----------------
-template <int R, int L, int NW, int U>
+template <int R, int L, int NW, int U, int TXP = 8>
 __device__ __forceinline__ void sfirst_inv(const float2* __restrict__ base, size_t stride, float4* __restrict__ sm,
                                            const int* __restrict__ rev, int cp, int w)
 {
@@ -152,13 +152,13 @@ __device__ __forceinline__ void sfirst_inv(const float2* __restrict__ base, size
             p2 r[R], i[R];
             ssplit<R>(v[u], r, i);
             Dft<R>::run(i, r);
-            store_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
+            store_pairs<R>(sm, b * R * TXP + cp, TXP, r, i);
         }
     }
 }
 
 // ---- last forward stage: smem positions b*R + k -> global rows rev(b*R) + m*(L/R) -----------------
-template <int R, int L, int NW>
+template <int R, int L, int NW, int TXP = 8>
 __device__ __forceinline__ void slast_fwd(float2* __restrict__ base, size_t stride, const float4* __restrict__ sm,
                                           const int* __restrict__ rev, int cp, int w)
 {
@@ -169,7 +169,7 @@ __device__ __forceinline__ void slast_fwd(float2* __restrict__ base, size_t stri
         const int b = w + it * NW;
         if ((nb % NW) != 0 && b >= nb) break;
         p2 r[R], i[R];
-        load_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
+        load_pairs<R>(sm, b * R * TXP + cp, TXP, r, i);
         float2* p = base + (size_t)__ldg(rev + b * R) * stride;
         Dft<R>::run(r, i);
 #pragma unroll
@@ -178,7 +178,7 @@ __device__ __forceinline__ void slast_fwd(float2* __restrict__ base, size_t stri
 }
 
 // ---- last inverse stage: smem positions j + k*S -> global rows j + m*S -------------------------------
-template <int R, int L, int NW>
+template <int R, int L, int NW, int TXP = 8>
 __device__ __forceinline__ void slast_inv(float2* __restrict__ base, size_t stride, const float4* __restrict__ sm,
                                           const float4* __restrict__ tw, int cp, int w)
 {
@@ -189,7 +189,7 @@ __device__ __forceinline__ void slast_inv(float2* __restrict__ base, size_t stri
         const int j = w + it * NW;
         if ((S % NW) != 0 && j >= S) break;
         p2 r[R], i[R];
-        load_pairs<R>(sm, j * 8 + cp, S * 8, r, i);
+        load_pairs<R>(sm, j * TXP + cp, S * TXP, r, i);
 #pragma unroll
         for (int k = 1; k < R; ++k) cmulc(r[k], i[k], tw[j * k]);
         Dft<R>::run(i, r);
@@ -200,7 +200,7 @@ __device__ __forceinline__ void slast_inv(float2* __restrict__ base, size_t stri
 }
 
 // ---- fused middle: last forward stage, x H x c, first inverse stage (in registers) ---------------
-template <int R, int L, int NW, int U>
+template <int R, int L, int NW, int U, int TXP = 8>
 __device__ __forceinline__ void smid_fused(const float2* __restrict__ hbase, size_t stride, float4* __restrict__ sm,
                                            const int* __restrict__ rev, int cp, int w, float c)
 {
@@ -222,7 +222,7 @@ __device__ __forceinline__ void smid_fused(const float2* __restrict__ hbase, siz
             const int b = w + (it * U + u) * NW;
             if ((nb % (NW * U)) != 0 && b >= nb) continue;
             p2 r[R], i[R];
-            load_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
+            load_pairs<R>(sm, b * R * TXP + cp, TXP, r, i);
             Dft<R>::run(r, i);
             // Dst = c * (Src * Dst), Src = PSF spectrum (reference mulAndScale, src/convolution3Dfft.cu:41-45)
 #pragma unroll
@@ -234,7 +234,7 @@ __device__ __forceinline__ void smid_fused(const float2* __restrict__ hbase, siz
                 i[m] = xi;
             }
             Dft<R>::run(i, r);
-            store_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
+            store_pairs<R>(sm, b * R * TXP + cp, TXP, r, i);
         }
     }
 }
