@@ -21,8 +21,22 @@ std::vector<int> factorize(int L, bool* generic)
     std::vector<int> out;
     bool gen = false;
     int n = L;
-    static const int fast[] = {8, 4, 2, 3, 5, 7};
-    for (int r : fast)
+    // power-of-two part: fewest stages with radices <= 16, never a trailing radix 2 when avoidable
+    int e = 0;
+    while (n > 1 && (n & 1) == 0) {
+        n >>= 1;
+        ++e;
+    }
+    static const int pow2_plan[13][4] = {
+        {0, 0, 0, 0},    {2, 0, 0, 0},    {4, 0, 0, 0},    {8, 0, 0, 0},   {16, 0, 0, 0},  {8, 4, 0, 0},   {8, 8, 0, 0},
+        {16, 8, 0, 0},   {16, 16, 0, 0},  {8, 8, 8, 0},    {16, 16, 4, 0}, {16, 16, 8, 0}, {16, 16, 16, 0}};
+    while (e > 12) {
+        out.push_back(16);
+        e -= 4;
+    }
+    for (int i = 0; i < 4 && pow2_plan[e][i]; ++i) out.push_back(pow2_plan[e][i]);
+    static const int odd_fast[] = {3, 5, 7};
+    for (int r : odd_fast)
         while (n > 1 && n % r == 0) {
             out.push_back(r);
             n /= r;

@@ -180,6 +180,63 @@ struct Dft<8> {
     }
 };
 
+
+// Radix 16 = 4 x 4 with the internal twiddles w16^(b*c) folded in as constants.
+//   n = 4a + b, k = c + 4d:  X[c + 4d] = sum_b w4^(b d) [ w16^(b c) sum_a x[4a + b] w4^(a c) ]
+template <>
+struct Dft<16> {
+    // (xr + i xi) *= (c - i s)   with c, s > 0 constants (forward roots lie in the lower half plane)
+    static __device__ __forceinline__ void rot(p2& xr, p2& xi, float c, float s)
+    {
+        const p2 nr = pfmas(xi, s, pmuls(xr, c));
+        xi = pfmas(xr, -s, pmuls(xi, c));
+        xr = nr;
+    }
+    static __device__ __forceinline__ void run(p2* r, p2* i)
+    {
+        const float C1 = 0.92387953251128675613f;  // cos(pi/8)
+        const float S1 = 0.38268343236508977173f;  // sin(pi/8)
+        const float C2 = 0.70710678118654752440f;  // cos(pi/4)
+        p2 tr[16], ti[16];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            p2 ar[4] = {r[b], r[4 + b], r[8 + b], r[12 + b]};
+            p2 ai[4] = {i[b], i[4 + b], i[8 + b], i[12 + b]};
+            Dft<4>::run(ar, ai);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                tr[4 * c + b] = ar[c];
+                ti[4 * c + b] = ai[c];
+            }
+        }
+        // t_b[c] *= w16^(b c), index 4c + b
+        rot(tr[4 * 1 + 1], ti[4 * 1 + 1], C1, S1);                 // w16^1
+        rot(tr[4 * 1 + 2], ti[4 * 1 + 2], C2, C2);                 // w16^2
+        rot(tr[4 * 1 + 3], ti[4 * 1 + 3], S1, C1);                 // w16^3
+        rot(tr[4 * 2 + 1], ti[4 * 2 + 1], C2, C2);                 // w16^2
+        {                                                          // w16^4 = -i
+            const p2 t = tr[4 * 2 + 2];
+            tr[4 * 2 + 2] = ti[4 * 2 + 2];
+            ti[4 * 2 + 2] = pneg(t);
+        }
+        rot(tr[4 * 2 + 3], ti[4 * 2 + 3], -C2, C2);                // w16^6 = (-C2, -C2)
+        rot(tr[4 * 3 + 1], ti[4 * 3 + 1], S1, C1);                 // w16^3
+        rot(tr[4 * 3 + 2], ti[4 * 3 + 2], -C2, C2);                // w16^6
+        rot(tr[4 * 3 + 3], ti[4 * 3 + 3], -C1, -S1);               // w16^9 = (-C1, +S1)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            p2 ar[4] = {tr[4 * c], tr[4 * c + 1], tr[4 * c + 2], tr[4 * c + 3]};
+            p2 ai[4] = {ti[4 * c], ti[4 * c + 1], ti[4 * c + 2], ti[4 * c + 3]};
+            Dft<4>::run(ar, ai);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                r[c + 4 * d] = ar[d];
+                i[c + 4 * d] = ai[d];
+            }
+        }
+    }
+};
+
 // Twiddles are kept in shared memory as float4 (c, c, s, s): both packed operands come out of one
 // 128-bit load as aligned register pairs.
 // (xr + i*xi) *= (c + i*s)

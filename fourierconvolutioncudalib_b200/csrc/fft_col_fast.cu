@@ -200,6 +200,7 @@ __device__ __forceinline__ void mid_fused(const float2* __restrict__ hbase, long
         case 4: { constexpr int RR = 4; CALL; } break; \
         case 5: { constexpr int RR = 5; CALL; } break; \
         case 7: { constexpr int RR = 7; CALL; } break; \
+        case 16: { constexpr int RR = 16; CALL; } break; \
         default: { constexpr int RR = 8; CALL; } break; \
     }
 

@@ -13,7 +13,7 @@
 // reversal).  Inverse (DIT, stages mirrored) takes that order back to natural order.  Callers map
 // positions to global rows, so natural order in global memory costs nothing for the strided axes.
 //
-// Radices 2,3,4,5,7,8 run in registers.  Any other prime factor p runs as a direct O(p) sum per
+// Radices 2,3,4,5,7,8,16 run in registers.  Any other prime factor p runs as a direct O(p) sum per
 // output between two tile buffers (ping-pong), so every length the C ABI can receive is supported
 // (the reference's own tests use 79, 109, 173, 37, 23, 53, ... -- SURVEY.md section 4).
 //
@@ -128,7 +128,7 @@ __device__ __forceinline__ void stage_generic(const float4* __restrict__ src, fl
 
 __device__ __forceinline__ bool is_fast_radix(int R)
 {
-    return R == 1 || R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8;
+    return R == 1 || R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8 || R == 16;
 }
 
 template <bool INV>
@@ -144,6 +144,7 @@ __device__ __forceinline__ void stage_dispatch(int R, float4*& cur, float4*& oth
             case 5: stage_smem<5, INV>(cur, tw, L, Li, cp, w, W, txp); break;
             case 7: stage_smem<7, INV>(cur, tw, L, Li, cp, w, W, txp); break;
             case 8: stage_smem<8, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 16: stage_smem<16, INV>(cur, tw, L, Li, cp, w, W, txp); break;
             default: stage_generic<INV>(cur, oth, tw, L, Li, R, cp, w, W, txp); break;
         }
     }

@@ -138,12 +138,12 @@ bool static_enabled()
 // The radix sequences are exactly what the planner (fc_plan.cu: factorize) produces.
 typedef SPlan<32, 8, 4> P32;
 typedef SPlan<64, 8, 8> P64;
-typedef SPlan<128, 8, 8, 2> P128;
+typedef SPlan<128, 16, 8> P128;
 typedef SPlan<192, 8, 8, 3> P192;
-typedef SPlan<256, 8, 8, 4> P256;
-typedef SPlan<384, 8, 8, 2, 3> P384;
+typedef SPlan<256, 16, 16> P256;
+typedef SPlan<384, 16, 8, 3> P384;
 typedef SPlan<512, 8, 8, 8> P512;
-typedef SPlan<1024, 8, 8, 8, 2> P1024;
+typedef SPlan<1024, 16, 16, 4> P1024;
 
 }  // namespace
 
@@ -159,20 +159,20 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
     // tuning knob for the longest pencils (profiles/): CTA shape / tile width of the L = 512 kernels
     static const int v512 = env_int("FCB200_V512", 0);
     if (plan_matches<P64>(a.P)) run_col<P64, 64, 1, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P128>(a.P)) run_col<P128, 128, 1, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P256>(a.P)) run_col<P256, 128, 2, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P384>(a.P)) run_col<P384, 192, 2, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P128>(a.P)) run_col<P128, 64, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P256>(a.P)) run_col<P256, 128, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P384>(a.P)) run_col<P384, 192, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P512>(a.P)) {
         switch (v512) {
             case 1: run_col<P512, 256, 1, 8>(a, mode, ngroups, st); break;
             case 2: run_col<P512, 128, 2, 8>(a, mode, ngroups, st); break;
-            case 3: run_col<P512, 512, 1, 8>(a, mode, ngroups, st); break;
+            case 3: run_col<P512, 256, 2, 8>(a, mode, ngroups, st); break;
             case 4: run_col<P512, 128, 2, 4>(a, mode, ngroups, st); break;
             case 5: run_col<P512, 256, 1, 4>(a, mode, ngroups, st); break;
             case 6: run_col<P512, 128, 1, 4>(a, mode, ngroups, st); break;
-            default: run_col<P512, 256, 2, 8>(a, mode, ngroups, st); break;
+            default: run_col<P512, 512, 1, 8>(a, mode, ngroups, st); break;
         }
-    } else if (plan_matches<P1024>(a.P)) run_col<P1024, 512, 2, 8>(a, mode, ngroups, st);
+    } else if (plan_matches<P1024>(a.P)) run_col<P1024, 512, 1, 8>(a, mode, ngroups, st);
     else return false;
     return true;
 }

@@ -8,14 +8,26 @@ the CPU before the same formulas run on the GPU.
 """
 import numpy as np
 
-FAST_RADICES = (8, 4, 2, 3, 5, 7)
+FAST_RADICES = (2, 3, 4, 5, 7, 8, 16)
+
+_POW2_PLAN = {0: [], 1: [2], 2: [4], 3: [8], 4: [16], 5: [8, 4], 6: [8, 8], 7: [16, 8], 8: [16, 16], 9: [8, 8, 8],
+              10: [16, 16, 4], 11: [16, 16, 8], 12: [16, 16, 16]}
 
 
 def factorize(L):
-    """Same order as the C planner (plan.cpp: fc_factorize): 8s, then 4, 2, 3, 5, 7, then primes."""
+    """Same result as the C planner (fc_plan.cu: factorize): fewest stages for the power-of-two part
+    with radices <= 16, then 3, 5, 7, then the remaining primes (generic stages)."""
     out = []
     n = L
-    for r in FAST_RADICES:
+    e = 0
+    while n > 1 and n % 2 == 0:
+        n //= 2
+        e += 1
+    while e > 12:
+        out.append(16)
+        e -= 4
+    out += _POW2_PLAN[e]
+    for r in (3, 5, 7):
         while n % r == 0 and n > 1:
             out.append(r)
             n //= r
