@@ -18,6 +18,7 @@ ABI_SYMBOLS = (
 )
 EXT_SYMBOLS = (
     "fcb200_convolve_device_async", "fcb200_plan_radices", "fcb200_plan_tables",
+    "fcb200_plan_radices_style", "fcb200_plan_tables_style",
     "fcb200_spectrum_pitch", "fcb200_workspace_bytes", "fcb200_psf_active_rows",
     "fcb200_debug_rfft3", "fcb200_debug_irfft3", "fcb200_debug_psf_spectrum",
     "fcb200_release", "fcb200_launch_count", "fcb200_profile_enable", "fcb200_profile_read",
@@ -66,6 +67,8 @@ def load():
         "fcb200_convolve_device_async": (None, [vp, ip, vp, ip, i, vp]),
         "fcb200_plan_radices": (i, [i, ip, ip]),
         "fcb200_plan_tables": (None, [i, ip, ip, fp]),
+        "fcb200_plan_radices_style": (i, [i, i, ip, ip]),
+        "fcb200_plan_tables_style": (None, [i, i, ip, ip, fp]),
         "fcb200_spectrum_pitch": (i, [i]),
         "fcb200_workspace_bytes": (ctypes.c_longlong, [ip]),
         "fcb200_psf_active_rows": (ctypes.c_longlong, [ip, ip, ip, ctypes.c_longlong]),

@@ -135,20 +135,20 @@ def convolve_device_async(im_dev, imDim, kernel_dev, kernelDim, devCUDA, stream=
                                              int(devCUDA), ctypes.c_void_p(int(stream)))
 
 
-def plan_radices(L):
+def plan_radices(L, style=0):
     r = (ctypes.c_int * 16)()
     g = ctypes.c_int(0)
-    n = _load().fcb200_plan_radices(int(L), r, ctypes.byref(g))
+    n = _load().fcb200_plan_radices_style(int(L), int(style), r, ctypes.byref(g))
     return list(r[:n]), bool(g.value)
 
 
-def plan_tables(L):
+def plan_tables(L, style=0):
     rev = np.zeros(L, np.int32)
     pos = np.zeros(L, np.int32)
     tw = np.zeros(2 * L, np.float32)
-    _load().fcb200_plan_tables(int(L), rev.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
-                                   pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
-                                   tw.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    _load().fcb200_plan_tables_style(int(L), int(style), rev.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                                         pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                                         tw.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
     return rev, pos, tw[0::2] + 1j * tw[1::2]
 
 

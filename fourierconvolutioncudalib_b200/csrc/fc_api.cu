@@ -292,23 +292,27 @@ int gpu_mem_needed_mb(int* shape, int len)
 const char* fcb200_last_error(void) { return g_last_error.c_str(); }
 void fcb200_set_error_mode(int mode) { g_error_mode.store(mode == 1 ? 1 : 0); }
 
-int fcb200_plan_radices(int L, int* radices, int* generic)
+int fcb200_plan_radices(int L, int* radices, int* generic) { return fcb200_plan_radices_style(L, 0, radices, generic); }
+
+int fcb200_plan_radices_style(int L, int style, int* radices, int* generic)
 {
     return guarded([&] {
         if (L < 1) throw std::runtime_error("fcb200: L must be >= 1");
         bool gen = false;
-        std::vector<int> r = factorize(L, &gen);
+        std::vector<int> r = factorize(L, &gen, style);
         for (size_t i = 0; i < r.size(); ++i) radices[i] = r[i];
         if (generic) *generic = gen ? 1 : 0;
         return (int)r.size();
     });
 }
 
-void fcb200_plan_tables(int L, int* rev, int* pos, float* tw)
+void fcb200_plan_tables(int L, int* rev, int* pos, float* tw) { fcb200_plan_tables_style(L, 0, rev, pos, tw); }
+
+void fcb200_plan_tables_style(int L, int style, int* rev, int* pos, float* tw)
 {
     guarded([&] {
         bool gen = false;
-        std::vector<int> r = factorize(L, &gen), hrev, hpos;
+        std::vector<int> r = factorize(L, &gen, style), hrev, hpos;
         std::vector<float2> htw;
         build_tables(L, r, hrev, hpos, htw);
         if (rev) std::memcpy(rev, hrev.data(), sizeof(int) * L);

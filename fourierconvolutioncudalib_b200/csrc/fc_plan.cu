@@ -16,7 +16,7 @@ namespace fcb200 {
 // ------------------------------------------------------------------------------------------------
 // pure host planning
 // ------------------------------------------------------------------------------------------------
-std::vector<int> factorize(int L, bool* generic)
+std::vector<int> factorize(int L, bool* generic, int style)
 {
     std::vector<int> out;
     bool gen = false;
@@ -27,14 +27,19 @@ std::vector<int> factorize(int L, bool* generic)
         n >>= 1;
         ++e;
     }
-    static const int pow2_plan[13][4] = {
-        {0, 0, 0, 0},    {2, 0, 0, 0},    {4, 0, 0, 0},    {8, 0, 0, 0},   {16, 0, 0, 0},  {8, 4, 0, 0},   {8, 8, 0, 0},
-        {16, 8, 0, 0},   {16, 16, 0, 0},  {8, 8, 8, 0},    {16, 16, 4, 0}, {16, 16, 8, 0}, {16, 16, 16, 0}};
+    // style 0 (x and y axes): radix 16 where it saves a stage.  style 1 (fused z axis): radices <= 8,
+    // because the fused forward-multiply-inverse kernel is register-bound with radix 16.
+    static const int pow2_plan[2][13][4] = {
+        {{0, 0, 0, 0}, {2, 0, 0, 0}, {4, 0, 0, 0}, {8, 0, 0, 0}, {16, 0, 0, 0}, {8, 4, 0, 0}, {8, 8, 0, 0},
+         {16, 8, 0, 0}, {16, 16, 0, 0}, {8, 8, 8, 0}, {16, 16, 4, 0}, {16, 16, 8, 0}, {16, 16, 16, 0}},
+        {{0, 0, 0, 0}, {2, 0, 0, 0}, {4, 0, 0, 0}, {8, 0, 0, 0}, {4, 4, 0, 0}, {8, 4, 0, 0}, {8, 8, 0, 0},
+         {8, 4, 4, 0}, {8, 8, 4, 0}, {8, 8, 8, 0}, {8, 8, 4, 4}, {8, 8, 8, 4}, {8, 8, 8, 8}}};
+    const int st = style == 1 ? 1 : 0;
     while (e > 12) {
-        out.push_back(16);
-        e -= 4;
+        out.push_back(st ? 8 : 16);
+        e -= st ? 3 : 4;
     }
-    for (int i = 0; i < 4 && pow2_plan[e][i]; ++i) out.push_back(pow2_plan[e][i]);
+    for (int i = 0; i < 4 && pow2_plan[st][e][i]; ++i) out.push_back(pow2_plan[st][e][i]);
     static const int odd_fast[] = {3, 5, 7};
     for (int r : odd_fast)
         while (n > 1 && n % r == 0) {
@@ -186,10 +191,10 @@ struct PassTimer {
     }
 };
 
-static void make_axis(AxisPlan& a, int L)
+static void make_axis(AxisPlan& a, int L, int style)
 {
     a.L = L;
-    a.radix = factorize(L, &a.generic);
+    a.radix = factorize(L, &a.generic, style);
     std::vector<int> rev, pos;
     std::vector<float2> tw;
     build_tables(L, a.radix, rev, pos, tw);
@@ -279,9 +284,9 @@ static std::shared_ptr<ConvPlan> build_plan(int device, int nx, int ny, int nz)
     auto p = std::make_shared<ConvPlan>();
     p->device = device;
     p->g = make_geometry(nx, ny, nz);
-    make_axis(p->px, p->g.M);
-    make_axis(p->py, ny);
-    make_axis(p->pz, nz);
+    make_axis(p->px, p->g.M, 0);
+    make_axis(p->py, ny, 0);
+    make_axis(p->pz, nz, 1);
     if (!x_pass_supported(p->g, p->px.dev))
         throw std::runtime_error("fcb200: fastest image extent too large for the shared-memory x pass");
     p->txp_y = col_pick_txp(p->py.dev);

@@ -11,7 +11,7 @@
 namespace fcb200 {
 
 // ---- pure host planning (no CUDA calls; unit-tested on the CPU) -----------------------------------
-std::vector<int> factorize(int L, bool* generic);
+std::vector<int> factorize(int L, bool* generic, int style = 0);
 void build_tables(int L, const std::vector<int>& radix, std::vector<int>& rev, std::vector<int>& pos,
                   std::vector<float2>& tw);
 Geometry make_geometry(int nx, int ny, int nz);

@@ -89,17 +89,16 @@ __device__ __forceinline__ void cp_async_wait_all()
 
 // ------------------------------------------------------------------------------------------------
 // X passes.  16 rows per CTA, two shared-memory tiles:
-//   row tile    [16 rows][P float2], P odd: holds global rows verbatim (real rows as float2 = two
-//               consecutive samples; spectrum rows in pair-planar form).  Filled / drained with lanes
+//   row tile    [16 rows][P float2], P odd: global rows as interleaved float2 (real rows: two
+//               consecutive samples; spectrum rows: (re, im) per bin).  Filled / drained with lanes
 //               running along x (coalesced, conflict-free); read / written column-wise with lanes
 //               running along row pairs (conflict-free because P is odd);
 //   engine tile [L positions][8 row pairs] float4, pair-planar: the layout of fft_engine.cuh.
-// Moving data between the two tiles is the transposition; kx comes out in natural order.
+// Moving data between the two tiles is the transposition; kx comes out in natural order.  Spectrum
+// rows in GLOBAL memory are pair-planar (fc_common.h); the conversion from / to interleaved is one
+// lane shuffle in the coalesced copy loops.
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int x_row_pitch(int L, int xcp) { return (L > xcp ? L : xcp) | 1; }
-
-// float index of the real part of column k inside a pair-planar row (imaginary part at +2)
-__device__ __forceinline__ int pp(int k) { return ((k >> 1) << 2) | (k & 1); }
 
 struct XSmem {
     float4* A;
@@ -109,16 +108,79 @@ struct XSmem {
     int P;
 };
 
-__device__ __forceinline__ XSmem x_carve(float4* smem, const Geometry& g, const AxisPlanDev& pl)
+__device__ __forceinline__ XSmem x_carve(float4* smem, const Geometry& g, const AxisPlanDev& pl, int L)
 {
     XSmem s;
-    s.P = x_row_pitch(pl.L, g.xcp);
+    s.P = x_row_pitch(L, g.xcp);
     s.A = smem;
-    s.B = pl.generic ? (s.A + (size_t)pl.L * 8) : nullptr;
-    s.tw = s.A + (size_t)pl.L * 8 * (pl.generic ? 2 : 1);
-    s.rowt = reinterpret_cast<float2*>(s.tw + pl.L);
+    s.B = pl.generic ? (s.A + (size_t)L * 8) : nullptr;
+    s.tw = s.A + (size_t)L * 8 * (pl.generic ? 2 : 1);
+    s.rowt = reinterpret_cast<float2*>(s.tw + L);
     return s;
 }
+
+// ---- static-plan stages that touch the row tile directly ---------------------------------------------
+// forward first stage: row tile (rows 2cp, 2cp+1) -> registers -> engine tile
+template <int R, int L, int NW>
+__device__ __forceinline__ void sstage_rows_first(const float2* __restrict__ rowt, int P, float4* __restrict__ sm,
+                                                  const float4* __restrict__ tw, int cp, int w)
+{
+    constexpr int S = L / R;
+    constexpr int ITER = (S + NW - 1) / NW;
+    const float2* ra = rowt + (2 * cp) * P;
+    const float2* rb = ra + P;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int j = w + it * NW;
+        if ((S % NW) != 0 && j >= S) break;
+        p2 r[R], i[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const float2 u = ra[j + k * S], v = rb[j + k * S];
+            r[k] = make_float2(u.x, v.x);
+            i[k] = make_float2(u.y, v.y);
+        }
+        Dft<R>::run(r, i);
+#pragma unroll
+        for (int m = 1; m < R; ++m) cmul(r[m], i[m], tw[j * m]);
+        store_pairs<R>(sm, j * 8 + cp, S * 8, r, i);
+    }
+}
+
+// inverse last stage: engine tile -> registers -> row tile (natural order)
+template <int R, int L, int NW>
+__device__ __forceinline__ void sstage_rows_last_inv(const float4* __restrict__ sm, float2* __restrict__ rowt, int P,
+                                                     const float4* __restrict__ tw, int cp, int w)
+{
+    constexpr int S = L / R;
+    constexpr int ITER = (S + NW - 1) / NW;
+    float2* ra = rowt + (2 * cp) * P;
+    float2* rb = ra + P;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int j = w + it * NW;
+        if ((S % NW) != 0 && j >= S) break;
+        p2 r[R], i[R];
+        load_pairs<R>(sm, j * 8 + cp, S * 8, r, i);
+#pragma unroll
+        for (int k = 1; k < R; ++k) cmulc(r[k], i[k], tw[j * k]);
+        Dft<R>::run(i, r);
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            ra[j + m * S] = make_float2(r[m].x, i[m].x);
+            rb[j + m * S] = make_float2(r[m].y, i[m].y);
+        }
+    }
+}
+
+template <class PL>
+struct IsStaticPlan {
+    static constexpr bool value = true;
+};
+template <>
+struct IsStaticPlan<DynPlan> {
+    static constexpr bool value = false;
+};
 
 // P = DynPlan: run-time radices (any length);  P = SPlan<...>: compile-time specialised stages.
 template <int LOADER, class PL, int THREADS>  // LOADER 0: dense real rows, 1: PSF gather
@@ -127,9 +189,10 @@ __global__ void __launch_bounds__(THREADS) x_fwd_kernel(XArgs a)
     extern __shared__ float4 smem[];
     const Geometry g = a.g;
     const int L = PlanLen<PL>::get(a.P);  // complex transform length: nx/2 (even nx) or nx (odd nx)
-    const XSmem sm = x_carve(smem, g, a.P);
+    const XSmem sm = x_carve(smem, g, a.P, L);
     const int P = sm.P;
     float2* rowt = sm.rowt;
+    constexpr int NW = THREADS / 8;
 
     const int t = threadIdx.x;
     const int cp = t & 7, w = t >> 3, W = blockDim.x >> 3;
@@ -163,26 +226,39 @@ __global__ void __launch_bounds__(THREADS) x_fwd_kernel(XArgs a)
     cp_async_wait_all();
     __syncthreads();
 
-    // ---- row tile -> engine tile (lanes along row pairs: the transposition)
-    for (int pos = w; pos < L; pos += W) {
-        const float2 u = rowt[(2 * cp) * P + pos], v = rowt[(2 * cp + 1) * P + pos];
-        sm.A[pos * 8 + cp] = make_float4(u.x, v.x, u.y, v.y);
+    float4* cur;
+    if constexpr (IsStaticPlan<PL>::value) {
+        // first stage straight from the row tile (this is the transposition), the rest on the engine tile
+        sstage_rows_first<PL::R0, PL::L, NW>(rowt, P, sm.A, sm.tw, cp, w);
+        __syncthreads();
+        sstage<PL::R1, PL::L, PL::L / PL::R0, NW, false>(sm.A, sm.tw, cp, w);
+        __syncthreads();
+        if constexpr (PL::ns >= 3) {
+            sstage<PL::R2, PL::L, PL::L / (PL::R0 * PL::R1), NW, false>(sm.A, sm.tw, cp, w);
+            __syncthreads();
+        }
+        if constexpr (PL::ns >= 4) {
+            sstage<PL::R3, PL::L, PL::L / (PL::R0 * PL::R1 * PL::R2), NW, false>(sm.A, sm.tw, cp, w);
+            __syncthreads();
+        }
+        cur = sm.A;
+    } else {
+        for (int pos = w; pos < L; pos += W) {
+            const float2 u = rowt[(2 * cp) * P + pos], v = rowt[(2 * cp + 1) * P + pos];
+            sm.A[pos * 8 + cp] = make_float4(u.x, v.x, u.y, v.y);
+        }
+        __syncthreads();
+        cur = engine_run<false>(a.P, sm.A, sm.B, sm.tw, cp, w, W, 8, true);
     }
-    __syncthreads();
 
-    float4* cur = PlanRun<PL, THREADS / 8, false>::run(a.P, sm.A, sm.B, sm.tw, cp, w, W);
-
-    // ---- engine tile -> row tile (pair-planar spectrum rows, natural kx); even nx: split the
-    //      packed half-length transform into the spectrum of the real rows
+    // ---- engine tile -> row tile (interleaved spectrum rows, natural kx); even nx: split the packed
+    //      half-length transform into the spectrum of the real rows
     {
-        float* ra = reinterpret_cast<float*>(rowt + (2 * cp) * P);
-        float* rb = reinterpret_cast<float*>(rowt + (2 * cp + 1) * P);
+        float2* ra = rowt + (2 * cp) * P;
+        float2* rb = ra + P;
         auto put = [&](int k, p2 re, p2 im) {
-            const int f = pp(k);
-            ra[f] = re.x;
-            ra[f + 2] = im.x;
-            rb[f] = re.y;
-            rb[f + 2] = im.y;
+            ra[k] = make_float2(re.x, im.x);
+            rb[k] = make_float2(re.y, im.y);
         };
         if (g.odd) {
             for (int k = w; k < g.xc; k += W) {
@@ -218,14 +294,21 @@ __global__ void __launch_bounds__(THREADS) x_fwd_kernel(XArgs a)
     }
     __syncthreads();
 
-    // ---- row tile -> spectrum rows (verbatim)
+    // ---- row tile -> spectrum rows; interleaved -> pair-planar with one lane exchange:
+    //      float2 slot k of a row holds (re_k, re_k+1) for even k and (im_k-1, im_k) for odd k
     for (int lrow = warp; lrow < 16; lrow += nwarps) {
         const long long li = row0 + lrow;
         const long long grow = (li < a.nrows) ? (a.rowList ? (long long)a.rowList[li] : li) : -1;
-        if (grow < 0) continue;
+        if (grow < 0) continue;   // warp-uniform
         const float2* src = rowt + lrow * P;
         float2* dst = a.spec + grow * g.xcp;
-        for (int k = lane; k < g.xcp; k += 32) dst[k] = src[k];
+        for (int k0 = 0; k0 < g.xcp; k0 += 32) {
+            const int k = k0 + lane;
+            const float2 v = (k < g.xcp) ? src[k] : make_float2(0.f, 0.f);
+            const float ox = __shfl_xor_sync(0xffffffffu, v.x, 1);
+            const float oy = __shfl_xor_sync(0xffffffffu, v.y, 1);
+            if (k < g.xcp) dst[k] = (lane & 1) ? make_float2(oy, v.y) : make_float2(v.x, ox);
+        }
     }
 }
 
@@ -238,9 +321,10 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
     extern __shared__ float4 smem[];
     const Geometry g = a.g;
     const int L = PlanLen<PL>::get(a.P);
-    const XSmem sm = x_carve(smem, g, a.P);
+    const XSmem sm = x_carve(smem, g, a.P, L);
     const int P = sm.P;
     float2* rowt = sm.rowt;
+    constexpr int NW = THREADS / 8;
 
     const int t = threadIdx.x;
     const int cp = t & 7, w = t >> 3, W = blockDim.x >> 3;
@@ -249,28 +333,38 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
 
     load_twiddles(sm.tw, a.P.tw, L);
 
-    // ---- spectrum rows -> row tile (verbatim, asynchronous)
+    // ---- spectrum rows (pair-planar) -> row tile (interleaved); loads are issued four at a time
     for (int lrow = warp; lrow < 16; lrow += nwarps) {
         const long long grow = row0 + lrow;
         float2* dst = rowt + lrow * P;
-        if (grow < a.nrows) {
-            const float2* src = a.spec + grow * g.xcp;
-            for (int k = lane; k < g.xcp; k += 32) cp_async8(dst + k, src + k);
-        } else {
-            for (int k = lane; k < g.xcp; k += 32) dst[k] = make_float2(0.f, 0.f);
+        const bool have = grow < a.nrows;   // warp-uniform
+        const float2* src = a.spec + (have ? grow : 0) * g.xcp;
+        for (int k0 = 0; k0 < g.xcp; k0 += 128) {
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * 32 + lane;
+                v[u] = (have && k < g.xcp) ? src[k] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * 32 + lane;
+                const float ox = __shfl_xor_sync(0xffffffffu, v[u].x, 1);
+                const float oy = __shfl_xor_sync(0xffffffffu, v[u].y, 1);
+                if (k < g.xcp) dst[k] = (lane & 1) ? make_float2(oy, v[u].y) : make_float2(v[u].x, ox);
+            }
         }
     }
-    cp_async_wait_all();
     __syncthreads();
 
     // ---- row tile -> engine tile (positions), merging the half spectrum into the packed transform
     {
-        const float* ra = reinterpret_cast<const float*>(rowt + (2 * cp) * P);
-        const float* rb = reinterpret_cast<const float*>(rowt + (2 * cp + 1) * P);
+        const float2* ra = rowt + (2 * cp) * P;
+        const float2* rb = ra + P;
         auto get = [&](int k, p2& re, p2& im) {
-            const int f = pp(k);
-            re = make_float2(ra[f], rb[f]);
-            im = make_float2(ra[f + 2], rb[f + 2]);
+            const float2 u = ra[k], v = rb[k];
+            re = make_float2(u.x, v.x);
+            im = make_float2(u.y, v.y);
         };
         if (g.odd) {
             for (int k = w; k < g.xc; k += W) {
@@ -308,15 +402,30 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
     }
     __syncthreads();
 
-    float4* cur = PlanRun<PL, THREADS / 8, true>::run(a.P, sm.A, sm.B, sm.tw, cp, w, W);
-
-    // ---- engine tile -> row tile (real rows, natural order), then row tile -> global
-    for (int pos = w; pos < L; pos += W) {
-        const float4 v = cur[pos * 8 + cp];
-        rowt[(2 * cp) * P + pos] = make_float2(v.x, v.z);
-        rowt[(2 * cp + 1) * P + pos] = make_float2(v.y, v.w);
+    if constexpr (IsStaticPlan<PL>::value) {
+        // inverse stages on the engine tile; the last one writes the row tile (the transposition)
+        if constexpr (PL::ns >= 4) {
+            sstage<PL::R3, PL::L, PL::R3, NW, true>(sm.A, sm.tw, cp, w);
+            __syncthreads();
+        }
+        if constexpr (PL::ns >= 3) {
+            sstage<PL::R2, PL::L, PL::R2 * PL::R3, NW, true>(sm.A, sm.tw, cp, w);
+            __syncthreads();
+        }
+        sstage<PL::R1, PL::L, PL::R1 * PL::R2 * PL::R3, NW, true>(sm.A, sm.tw, cp, w);
+        __syncthreads();
+        sstage_rows_last_inv<PL::R0, PL::L, NW>(sm.A, rowt, P, sm.tw, cp, w);
+    } else {
+        float4* cur = engine_run<true>(a.P, sm.A, sm.B, sm.tw, cp, w, W, 8, true);
+        for (int pos = w; pos < L; pos += W) {
+            const float4 v = cur[pos * 8 + cp];
+            rowt[(2 * cp) * P + pos] = make_float2(v.x, v.z);
+            rowt[(2 * cp + 1) * P + pos] = make_float2(v.y, v.w);
+        }
     }
     __syncthreads();
+
+    // ---- row tile -> real rows
     for (int lrow = warp; lrow < 16; lrow += nwarps) {
         const long long grow = row0 + lrow;
         if (grow >= a.nrows) continue;

@@ -20,6 +20,10 @@ FUNCTION_PREFIX int fcb200_plan_radices(int L, int* radices, int* generic);
 /* rev[p]: frequency at position p after the forward transform; pos = inverse permutation;
  * tw: L interleaved (re,im) roots exp(-2*pi*i*t/L).  Any pointer may be NULL. */
 FUNCTION_PREFIX void fcb200_plan_tables(int L, int* rev, int* pos, float* tw);
+/* Same with an explicit planning style: 0 = fewest stages, radix 16 allowed (x and y axes);
+ * 1 = radices <= 8 (z axis, whose fused forward-multiply-inverse kernel is register-bound). */
+FUNCTION_PREFIX int fcb200_plan_radices_style(int L, int style, int* radices, int* generic);
+FUNCTION_PREFIX void fcb200_plan_tables_style(int L, int style, int* rev, int* pos, float* tw);
 /* Spectrum row pitch (complex elements) used for a volume whose fastest extent is nx. */
 FUNCTION_PREFIX int fcb200_spectrum_pitch(int nx);
 /* Bytes of device workspace a cached plan for imDim holds (spectrum + PSF spectrum + tables). */

@@ -36,13 +36,14 @@ def test_swizzle_is_conflict_free():
         assert len({em.swz(a + 2 * i + 1) for i in range(8)}) == 8
 
 
+@pytest.mark.parametrize("style", [0, 1])
 @pytest.mark.parametrize("L", LENGTHS)
-def test_c_planner_matches_model(fc, L):
-    radices, generic = fc.plan_radices(L)
-    assert radices == em.factorize(L)
+def test_c_planner_matches_model(fc, L, style):
+    radices, generic = fc.plan_radices(L, style)
+    assert radices == em.factorize(L, style)
     assert int(np.prod(radices)) == L
     assert generic == any(r not in (1, 2, 3, 4, 5, 7, 8, 16) for r in radices)
-    rev, pos, tw = fc.plan_tables(L)
+    rev, pos, tw = fc.plan_tables(L, style)
     assert np.array_equal(rev, em.rev_positions(L, radices))
     assert np.array_equal(pos[rev], np.arange(L))
     assert np.abs(tw - em.twiddles(L)).max() < 1e-7
