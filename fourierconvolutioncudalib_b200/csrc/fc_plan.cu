@@ -27,19 +27,21 @@ std::vector<int> factorize(int L, bool* generic, int style)
         n >>= 1;
         ++e;
     }
-    // style 0 (x and y axes): radix 16 where it saves a stage.  style 1 (fused z axis): radices <= 8,
-    // because the fused forward-multiply-inverse kernel is register-bound with radix 16.
-    static const int pow2_plan[2][13][4] = {
-        {{0, 0, 0, 0}, {2, 0, 0, 0}, {4, 0, 0, 0}, {8, 0, 0, 0}, {16, 0, 0, 0}, {8, 4, 0, 0}, {8, 8, 0, 0},
-         {16, 8, 0, 0}, {16, 16, 0, 0}, {8, 8, 8, 0}, {16, 16, 4, 0}, {16, 16, 8, 0}, {16, 16, 16, 0}},
-        {{0, 0, 0, 0}, {2, 0, 0, 0}, {4, 0, 0, 0}, {8, 0, 0, 0}, {4, 4, 0, 0}, {8, 4, 0, 0}, {8, 8, 0, 0},
-         {8, 4, 4, 0}, {8, 8, 4, 0}, {8, 8, 8, 0}, {8, 8, 4, 4}, {8, 8, 8, 4}, {8, 8, 8, 8}}};
-    const int st = style == 1 ? 1 : 0;
+    // style 0 (x and y axes): radix 16 where it saves a stage.  style 1 (fused z axis): the measured
+    // exception L = 256 -> (8,8,4), because the fused forward-multiply-inverse kernel is register-bound
+    // with two radix-16 stages (profiles/r01_notes.md).
+    static const int pow2_plan[13][4] = {
+        {0, 0, 0, 0},    {2, 0, 0, 0},    {4, 0, 0, 0},    {8, 0, 0, 0},   {16, 0, 0, 0},  {8, 4, 0, 0},   {8, 8, 0, 0},
+        {16, 8, 0, 0},   {16, 16, 0, 0},  {8, 8, 8, 0},    {16, 16, 4, 0}, {16, 16, 8, 0}, {16, 16, 16, 0}};
     while (e > 12) {
-        out.push_back(st ? 8 : 16);
-        e -= st ? 3 : 4;
+        out.push_back(16);
+        e -= 4;
     }
-    for (int i = 0; i < 4 && pow2_plan[st][e][i]; ++i) out.push_back(pow2_plan[st][e][i]);
+    if (style == 1 && L == 256) {
+        out = {8, 8, 4};
+    } else {
+        for (int i = 0; i < 4 && pow2_plan[e][i]; ++i) out.push_back(pow2_plan[e][i]);
+    }
     static const int odd_fast[] = {3, 5, 7};
     for (int r : odd_fast)
         while (n > 1 && n % r == 0) {

@@ -144,11 +144,8 @@ typedef SPlan<256, 16, 16> P256;
 typedef SPlan<384, 16, 8, 3> P384;
 typedef SPlan<512, 8, 8, 8> P512;
 typedef SPlan<1024, 16, 16, 4> P1024;
-// radix <= 8 flavours (planning style 1: the fused z axis)
-typedef SPlan<128, 8, 4, 4> P128b;
+// planning style 1 (fused z axis): L = 256 as (8,8,4)
 typedef SPlan<256, 8, 8, 4> P256b;
-typedef SPlan<384, 8, 8, 2, 3> P384b;
-typedef SPlan<1024, 8, 8, 4, 4> P1024b;
 
 }  // namespace
 
@@ -166,10 +163,7 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
     if (plan_matches<P64>(a.P)) run_col<P64, 64, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P128>(a.P)) run_col<P128, 64, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P256>(a.P)) run_col<P256, 128, 1, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P128b>(a.P)) run_col<P128b, 64, 2, 8>(a, mode, ngroups, st);
     else if (plan_matches<P256b>(a.P)) run_col<P256b, 128, 2, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P384b>(a.P)) run_col<P384b, 192, 2, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P1024b>(a.P)) run_col<P1024b, 512, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P384>(a.P)) run_col<P384, 192, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P512>(a.P)) {
         switch (v512) {

@@ -100,6 +100,8 @@ __device__ __forceinline__ void cp_async_wait_all()
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int x_row_pitch(int L, int xcp) { return (L > xcp ? L : xcp) | 1; }
 
+constexpr int XLB = 10;   // spectrum-row loads in flight per thread in the inverse x pass
+
 struct XSmem {
     float4* A;
     float4* B;
@@ -184,7 +186,7 @@ struct IsStaticPlan<DynPlan> {
 
 // P = DynPlan: run-time radices (any length);  P = SPlan<...>: compile-time specialised stages.
 template <int LOADER, class PL, int THREADS>  // LOADER 0: dense real rows, 1: PSF gather
-__global__ void __launch_bounds__(THREADS) x_fwd_kernel(XArgs a)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kernel(XArgs a)
 {
     extern __shared__ float4 smem[];
     const Geometry g = a.g;
@@ -333,21 +335,21 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
 
     load_twiddles(sm.tw, a.P.tw, L);
 
-    // ---- spectrum rows (pair-planar) -> row tile (interleaved); loads are issued four at a time
+    // ---- spectrum rows (pair-planar) -> row tile (interleaved); loads are issued XLB at a time
     for (int lrow = warp; lrow < 16; lrow += nwarps) {
         const long long grow = row0 + lrow;
         float2* dst = rowt + lrow * P;
         const bool have = grow < a.nrows;   // warp-uniform
         const float2* src = a.spec + (have ? grow : 0) * g.xcp;
-        for (int k0 = 0; k0 < g.xcp; k0 += 128) {
-            float2 v[4];
+        for (int k0 = 0; k0 < g.xcp; k0 += 32 * XLB) {
+            float2 v[XLB];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < XLB; ++u) {
                 const int k = k0 + u * 32 + lane;
                 v[u] = (have && k < g.xcp) ? src[k] : make_float2(0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < XLB; ++u) {
                 const int k = k0 + u * 32 + lane;
                 const float ox = __shfl_xor_sync(0xffffffffu, v[u].x, 1);
                 const float oy = __shfl_xor_sync(0xffffffffu, v[u].y, 1);

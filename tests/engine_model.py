@@ -14,10 +14,6 @@ _POW2_PLAN = {0: [], 1: [2], 2: [4], 3: [8], 4: [16], 5: [8, 4], 6: [8, 8], 7: [
               10: [16, 16, 4], 11: [16, 16, 8], 12: [16, 16, 16]}
 
 
-_POW2_PLAN_R8 = {0: [], 1: [2], 2: [4], 3: [8], 4: [4, 4], 5: [8, 4], 6: [8, 8], 7: [8, 4, 4], 8: [8, 8, 4],
-                 9: [8, 8, 8], 10: [8, 8, 4, 4], 11: [8, 8, 8, 4], 12: [8, 8, 8, 8]}
-
-
 def factorize(L, style=0):
     """Same result as the C planner (fc_plan.cu: factorize): fewest stages for the power-of-two part
     with radices <= 16, then 3, 5, 7, then the remaining primes (generic stages)."""
@@ -28,9 +24,9 @@ def factorize(L, style=0):
         n //= 2
         e += 1
     while e > 12:
-        out.append(8 if style == 1 else 16)
-        e -= 3 if style == 1 else 4
-    out += (_POW2_PLAN_R8 if style == 1 else _POW2_PLAN)[e]
+        out.append(16)
+        e -= 4
+    out += [8, 8, 4] if (style == 1 and L == 256) else _POW2_PLAN[e]
     for r in (3, 5, 7):
         while n % r == 0 and n > 1:
             out.append(r)
