@@ -117,9 +117,8 @@ def ncu_traffic(pass_name):
 
 def dist_setup(n_gpus):
     import torch
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from fourierconvolutioncudalib_b200 import tiles
+    rank, local, world = tiles.rank_info()
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -137,13 +136,8 @@ def barrier_sync(world):
 
 
 def max_over_ranks(x, world, device):
-    import torch
-    if world == 1:
-        return x
-    import torch.distributed as dist
-    t = torch.tensor([x], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    from fourierconvolutioncudalib_b200 import tiles
+    return tiles.max_over_ranks(x, device)
 
 
 def cpu_baseline_sample(max_seconds=30.0):
