@@ -21,6 +21,8 @@ EXT_SYMBOLS = (
     "fcb200_plan_radices_style", "fcb200_plan_tables_style",
     "fcb200_spectrum_pitch", "fcb200_workspace_bytes", "fcb200_psf_active_rows",
     "fcb200_debug_rfft3", "fcb200_debug_irfft3", "fcb200_debug_psf_spectrum",
+    "fcb200_slab_xy_forward", "fcb200_slab_z_fused", "fcb200_slab_yx_inverse", "fcb200_slab_psf_scratch_elems",
+    "fcb200_slab_psf",
     "fcb200_release", "fcb200_launch_count", "fcb200_profile_enable", "fcb200_profile_read",
 )
 
@@ -75,6 +77,11 @@ def load():
         "fcb200_debug_rfft3": (None, [fp, ip, fp, i, i]),
         "fcb200_debug_irfft3": (None, [fp, ip, fp, i]),
         "fcb200_debug_psf_spectrum": (None, [fp, ip, ip, fp, i]),
+        "fcb200_slab_xy_forward": (None, [vp, vp, vp, ip, i, i, i, vp]),
+        "fcb200_slab_z_fused": (None, [vp, vp, ip, i, i, vp]),
+        "fcb200_slab_yx_inverse": (None, [vp, vp, vp, ip, i, i, i, vp]),
+        "fcb200_slab_psf_scratch_elems": (ctypes.c_longlong, [ip, ip, i]),
+        "fcb200_slab_psf": (None, [vp, ip, ip, i, i, vp, vp, i, vp]),
         "fcb200_release": (None, []),
         "fcb200_launch_count": (ctypes.c_longlong, []),
         "fcb200_profile_enable": (None, [i]),

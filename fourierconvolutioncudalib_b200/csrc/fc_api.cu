@@ -397,6 +397,72 @@ void fcb200_debug_psf_spectrum(const imageType* kernel, const int* kernelDim, co
     });
 }
 
+// ---- slab-decomposed single volume ---------------------------------------------------------------
+void fcb200_slab_xy_forward(const imageType* real_slab, float* zslab_spec, float* send, const int* imDim, int nzl, int nyl,
+                            int devCUDA, void* stream)
+{
+    guarded([&] {
+        check_dims(imDim, nullptr);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        run_slab_xy_forward(*plan, real_slab, reinterpret_cast<float2*>(zslab_spec), reinterpret_cast<float2*>(send), nzl,
+                            nyl, (cudaStream_t)stream);
+    });
+}
+
+void fcb200_slab_z_fused(float* yslab_spec, const float* H_yslab, const int* imDim, int nyl, int devCUDA, void* stream)
+{
+    guarded([&] {
+        check_dims(imDim, nullptr);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        run_slab_z_fused(*plan, reinterpret_cast<float2*>(yslab_spec), reinterpret_cast<const float2*>(H_yslab), nyl,
+                         (cudaStream_t)stream);
+    });
+}
+
+void fcb200_slab_yx_inverse(const float* recv, float* zslab_spec, imageType* real_slab, const int* imDim, int nzl, int nyl,
+                            int devCUDA, void* stream)
+{
+    guarded([&] {
+        check_dims(imDim, nullptr);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        run_slab_yx_inverse(*plan, reinterpret_cast<const float2*>(recv), reinterpret_cast<float2*>(zslab_spec), real_slab,
+                            nzl, nyl, (cudaStream_t)stream);
+    });
+}
+
+long long fcb200_slab_psf_scratch_elems(const int* imDim, const int* kernelDim, int devCUDA)
+{
+    return guarded([&] {
+        check_dims(imDim, kernelDim);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
+        return (long long)psf_slab_scratch_elems(*plan, pdims);
+    });
+}
+
+void fcb200_slab_psf(const imageType* kernel_dev, const int* kernelDim, const int* imDim, int y0, int nyl, float* H_yslab,
+                     float* scratch, int devCUDA, void* stream)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        for (int i = 0; i < 3; ++i)
+            if (kernelDim[i] > imDim[i]) throw std::runtime_error("fcb200: kernel larger than image");
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
+        run_slab_psf(*plan, kernel_dev, pdims, y0, nyl, reinterpret_cast<float2*>(H_yslab),
+                     reinterpret_cast<float2*>(scratch), (cudaStream_t)stream);
+    });
+}
+
 void fcb200_release(void) { release_all_plans(); }
 void fcb200_profile_enable(int on) { profile_enable(on); }
 int fcb200_profile_read(float* ms_sum, long long* counts, int n) { return profile_read(ms_sum, counts, n); }

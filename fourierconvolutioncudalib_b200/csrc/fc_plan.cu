@@ -245,9 +245,10 @@ ConvPlan::~ConvPlan()
 }
 
 struct PlanKey {
-    int dev, nx, ny, nz;
+    int dev, nx, ny, nz, ws;
     bool operator<(const PlanKey& o) const
     {
+        if (ws != o.ws) return ws < o.ws;
         if (dev != o.dev) return dev < o.dev;
         if (nx != o.nx) return nx < o.nx;
         if (ny != o.ny) return ny < o.ny;
@@ -281,7 +282,7 @@ static void evict_lru_locked(size_t keep)
     }
 }
 
-static std::shared_ptr<ConvPlan> build_plan(int device, int nx, int ny, int nz)
+static std::shared_ptr<ConvPlan> build_plan(int device, int nx, int ny, int nz, bool workspace)
 {
     auto p = std::make_shared<ConvPlan>();
     p->device = device;
@@ -305,16 +306,18 @@ static std::shared_ptr<ConvPlan> build_plan(int device, int nx, int ny, int nz)
         FC_CUDA(cudaMalloc(&p->d_twx, sizeof(float2) * twx.size()));
         FC_CUDA(cudaMemcpy(p->d_twx, twx.data(), sizeof(float2) * twx.size(), cudaMemcpyHostToDevice));
     }
-    FC_CUDA(cudaMalloc(&p->d_spec, p->spec_bytes()));
-    FC_CUDA(cudaMalloc(&p->d_H, p->spec_bytes()));
+    if (workspace) {
+        FC_CUDA(cudaMalloc(&p->d_spec, p->spec_bytes()));
+        FC_CUDA(cudaMalloc(&p->d_H, p->spec_bytes()));
+    }
     FC_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     return p;
 }
 
-std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz)
+std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz, bool workspace)
 {
     std::lock_guard<std::mutex> lock(g_cache_mu);
-    PlanKey key{device, nx, ny, nz};
+    PlanKey key{device, nx, ny, nz, workspace ? 1 : 0};
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
         it->second->last_use = ++g_tick;
@@ -322,12 +325,12 @@ std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz)
     }
     std::shared_ptr<ConvPlan> p;
     try {
-        p = build_plan(device, nx, ny, nz);
+        p = build_plan(device, nx, ny, nz, workspace);
     } catch (const std::runtime_error&) {
         // most likely out of device memory: drop every idle cached plan and retry once
         cudaGetLastError();
         evict_lru_locked(0);
-        p = build_plan(device, nx, ny, nz);
+        p = build_plan(device, nx, ny, nz, workspace);
     }
     p->last_use = ++g_tick;
     g_cache[key] = p;
@@ -359,11 +362,18 @@ static ColArgs y_args(ConvPlan& p, float2* data)
     a.scale = 1.f;
     a.groupList = nullptr;
     a.rowMask = nullptr;
+    a.split = nullptr;
+    a.splitRows = 0;
+    a.splitBlock = a.splitGroup = 0;
     return a;
 }
 
 static void col_pass(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
+    if (a.split) {   // split (exchange-buffer) layout: implemented by the generic kernel
+        launch_col(a, mode, ngroups, st);
+        return;
+    }
     if (launch_col_static(a, mode, ngroups, st)) return;
     if (a.txp == 8 && col_fast_supported(a.P)) launch_col_fast(a, mode, ngroups, st);
     else launch_col(a, mode, ngroups, st);
@@ -385,6 +395,9 @@ static ColArgs z_args(ConvPlan& p, float2* data)
     a.scale = 1.f;
     a.groupList = nullptr;
     a.rowMask = nullptr;
+    a.split = nullptr;
+    a.splitRows = 0;
+    a.splitBlock = a.splitGroup = 0;
     return a;
 }
 
@@ -396,6 +409,7 @@ static XArgs x_args(ConvPlan& p)
     a.twx = p.d_twx;
     a.nrows = (long long)p.g.ny * p.g.nz;
     a.rowList = nullptr;
+    a.compactOut = 0;
     return a;
 }
 
@@ -421,11 +435,11 @@ void run_forward(ConvPlan& p, const float* d_real, float2* dst, int passes, cuda
     }
 }
 
-void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
+// PSF pruning lists (cached per placement dims): only z planes that receive a tap are non-zero before
+// the z pass.  The x pass runs on every row of those planes (rows without taps transform to zeros, so
+// nothing needs clearing), the y pass on those planes only, and the z pass reads only those planes.
+static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
 {
-    // PSF pruning: only z planes that receive a tap are non-zero before the z pass.  The x pass runs
-    // on every row of those planes (rows without taps transform to zeros, so nothing needs clearing),
-    // the y pass on those planes only, and the z pass reads only those planes.
     if (std::memcmp(p.psf_key, pdims, sizeof(int) * 6) != 0 || p.d_rows == nullptr) {
         std::vector<int> arows = psf_active_rows(pdims + 3, pdims, p.g.nx);
         std::vector<unsigned char> mask((size_t)p.g.nz, 0);
@@ -450,8 +464,14 @@ void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cuda
         FC_CUDA(cudaMemcpy(p.d_plane_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice));
         p.n_rows = (long long)rows.size();
         p.n_planes = (int)planes.size();
+        p.h_planes = planes;
         std::memcpy(p.psf_key, pdims, sizeof(int) * 6);
     }
+}
+
+void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
+{
+    psf_lists(p, pdims, st);
     XArgs xa = x_args(p);
     xa.spec = p.d_H;
     xa.nrows = p.n_rows;
@@ -530,6 +550,135 @@ void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st)
         launch_x_inv(xa, st);
     }
     count_launches(5);
+}
+
+// ------------------------------------------------------------------------------------------------
+// slab-decomposed single volume (multi-GPU)
+// ------------------------------------------------------------------------------------------------
+static void check_slab(const ConvPlan& p, int nzl, int nyl)
+{
+    if (nzl <= 0 || nzl > p.g.nz || nyl <= 0 || p.g.ny % nyl != 0)
+        throw std::runtime_error("fcb200: slab extents must be positive and nyl must divide ny");
+}
+
+void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2* send, int nzl, int nyl,
+                         cudaStream_t st)
+{
+    check_slab(p, nzl, nyl);
+    XArgs xa = x_args(p);
+    xa.in_real = d_real;
+    xa.spec = zslab;
+    xa.nrows = (long long)p.g.ny * nzl;
+    {
+        PassTimer t(kPassXFwd, st);
+        launch_x_fwd(xa, false, st);
+    }
+    ColArgs ya = y_args(p, zslab);
+    ya.split = send;
+    ya.splitRows = nyl;
+    ya.splitBlock = (long long)nzl * nyl * p.g.xcp;
+    ya.splitGroup = (long long)nyl * p.g.xcp;
+    {
+        PassTimer t(kPassYFwd, st);
+        col_pass(ya, 0, nzl, st);
+    }
+    count_launches(2);
+}
+
+void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, cudaStream_t st)
+{
+    check_slab(p, 1, nyl);
+    ColArgs za = z_args(p, yslab);
+    const long long C = (long long)nyl * p.g.xcp;
+    za.stride = C;
+    za.tilesPerGroup = (int)((C + 2 * za.txp - 1) / (2 * za.txp));
+    za.rowLen = (int)C;
+    za.H = Hslab;
+    za.scale = 1.0f / (float)((size_t)p.g.nx * (size_t)p.g.ny * (size_t)p.g.nz);
+    PassTimer t(kPassZFused, st);
+    col_pass(za, 2, 1, st);
+    count_launches(1);
+}
+
+void run_slab_yx_inverse(ConvPlan& p, const float2* recv, float2* zslab, float* d_real, int nzl, int nyl,
+                         cudaStream_t st)
+{
+    check_slab(p, nzl, nyl);
+    ColArgs ya = y_args(p, zslab);
+    ya.split = const_cast<float2*>(recv);
+    ya.splitRows = nyl;
+    ya.splitBlock = (long long)nzl * nyl * p.g.xcp;
+    ya.splitGroup = (long long)nyl * p.g.xcp;
+    {
+        PassTimer t(kPassYInv, st);
+        col_pass(ya, 1, nzl, st);
+    }
+    XArgs xa = x_args(p);
+    xa.spec = zslab;
+    xa.out_real = d_real;
+    xa.nrows = (long long)p.g.ny * nzl;
+    {
+        PassTimer t(kPassXInv, st);
+        launch_x_inv(xa, st);
+    }
+    count_launches(2);
+}
+
+size_t psf_slab_scratch_elems(ConvPlan& p, const int* pdims)
+{
+    std::vector<int> arows = psf_active_rows(pdims + 3, pdims, p.g.nx);
+    std::vector<unsigned char> mask((size_t)p.g.nz, 0);
+    for (int r : arows) mask[(size_t)(r / p.g.ny)] = 1;
+    size_t planes = 0;
+    for (unsigned char m : mask) planes += m;
+    return planes * (size_t)p.g.ny * p.g.xcp;
+}
+
+void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, int nyl, float2* Hslab,
+                  float2* scratch, cudaStream_t st)
+{
+    check_slab(p, 1, nyl);
+    if (y0 < 0 || y0 + nyl > p.g.ny) throw std::runtime_error("fcb200: PSF slab out of range");
+    psf_lists(p, pdims, st);
+    // x pass (gather loader) on every row of the planes that hold taps, written compactly
+    XArgs xa = x_args(p);
+    xa.spec = scratch;
+    xa.nrows = p.n_rows;
+    xa.rowList = p.d_rows;
+    xa.compactOut = 1;
+    xa.psf.kernel = d_kernel;
+    xa.psf.k0 = pdims[0];
+    xa.psf.k1 = pdims[1];
+    xa.psf.k2 = pdims[2];
+    xa.psf.d0 = pdims[3];
+    xa.psf.d1 = pdims[4];
+    xa.psf.d2 = pdims[5];
+    {
+        PassTimer t(kPassPsfX, st);
+        launch_x_fwd(xa, true, st);
+    }
+    {
+        PassTimer t(kPassPsfY, st);
+        col_pass(y_args(p, scratch), 0, p.n_planes, st);
+    }
+    // rows [y0, y0+nyl) of every active plane -> its place in the y-slab; the z pass skips other planes
+    const size_t row_bytes = (size_t)nyl * p.g.xcp * sizeof(float2);
+    for (int i = 0; i < p.n_planes; ++i) {
+        const int z = p.h_planes[(size_t)i];
+        FC_CUDA(cudaMemcpyAsync(Hslab + (size_t)z * nyl * p.g.xcp, scratch + ((size_t)i * p.g.ny + y0) * p.g.xcp,
+                                row_bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    ColArgs za = z_args(p, Hslab);
+    const long long C = (long long)nyl * p.g.xcp;
+    za.stride = C;
+    za.tilesPerGroup = (int)((C + 2 * za.txp - 1) / (2 * za.txp));
+    za.rowLen = (int)C;
+    za.rowMask = p.d_plane_mask;
+    {
+        PassTimer t(kPassPsfZ, st);
+        col_pass(za, 0, 1, st);
+    }
+    count_launches(3);
 }
 
 }  // namespace fcb200

@@ -49,6 +49,7 @@ struct ConvPlan {
     size_t rows_cap = 0;
     int* d_planes = nullptr;     // z planes that hold >= 1 tap
     int n_planes = 0;
+    std::vector<int> h_planes;   // host copy of d_planes
     unsigned char* d_plane_mask = nullptr;   // [nz] 1 = plane active
     cudaStream_t stream = nullptr;   // used for host-pointer calls
     std::mutex mu;
@@ -60,7 +61,8 @@ struct ConvPlan {
 
 // Returns the cached plan for (device, nx, ny, nz), creating it (tables + workspace) if needed.
 // The caller must hold plan->mu while using the workspace.
-std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz);
+// workspace = false: tables only (slab mode, where the caller owns the slab-sized buffers).
+std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz, bool workspace = true);
 void release_all_plans();
 long long launch_count();
 void count_launches(int n);
@@ -81,5 +83,24 @@ void run_forward(ConvPlan& p, const float* d_real, float2* dst, int passes, cuda
 // Image path: d_real (device, dense) is convolved in place with the PSF spectrum in plan.d_H.
 void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st);
 void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st);
+
+// ---- slab-decomposed single volume (multi-GPU): pass-level pieces on caller-owned device buffers ----
+// A rank owns nzl consecutive z planes of the real volume and, after the exchange, nyl consecutive ky
+// rows of every plane.  Buffers:  real slab [nzl][ny][nx];  z-slab spectrum [nzl][ny][xcp];
+// exchange buffer [P][nzl][nyl][xcp] (P = ny / nyl blocks);  y-slab spectrum [nz][nyl][xcp].
+// x + y forward on the slab; the y pass writes the exchange (send) buffer directly
+void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2* send, int nzl, int nyl,
+                         cudaStream_t st);
+// fused z pass on the y-slab spectrum (in place) with the y-slab of the PSF spectrum
+void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, cudaStream_t st);
+// y + x inverse; the y pass reads the exchange (receive) buffer directly
+void run_slab_yx_inverse(ConvPlan& p, const float2* recv, float2* zslab, float* d_real, int nzl, int nyl,
+                         cudaStream_t st);
+// PSF spectrum of the rank's y-slab: x and y passes on the planes that hold taps (into scratch, compact),
+// rows [y0, y0+nyl) copied into Hslab, z pass with the plane mask.  Returns nothing; scratch must hold
+// psf_slab_scratch_elems() float2.
+size_t psf_slab_scratch_elems(ConvPlan& p, const int* pdims);
+void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, int nyl, float2* Hslab,
+                  float2* scratch, cudaStream_t st);
 
 }  // namespace fcb200

@@ -42,6 +42,12 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
     const bool active = cp < npairs;
     const size_t off = (size_t)group * a.groupStride + col0 + 2 * cp;
     float2* base = a.data + off;
+    // split layout (see ColArgs): address of transform row r on the split side
+    float2* sbase = a.split ? a.split + (size_t)group * a.splitGroup + col0 + 2 * cp : nullptr;
+    auto split_row = [&](int r) {
+        const int blk = r / a.splitRows;
+        return sbase + (size_t)blk * a.splitBlock + (size_t)(r - blk * a.splitRows) * a.stride;
+    };
 
     load_twiddles(tw_s, a.P.tw, L);
 
@@ -49,7 +55,7 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
         for (int r = w; r < L; r += W) {
             const int p = (MODE == 1) ? __ldg(a.P.pos + r) : r;
             if (a.rowMask != nullptr && a.rowMask[r] == 0) A[p * txp + cp] = make_float4(0.f, 0.f, 0.f, 0.f);
-            else cp_async16(&A[p * txp + cp], base + (size_t)r * a.stride);
+            else cp_async16(&A[p * txp + cp], (MODE == 1 && sbase) ? split_row(r) : base + (size_t)r * a.stride);
         }
     }
     cp_async_wait_all();
@@ -88,7 +94,8 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
     if (active) {
         for (int p = w; p < L; p += W) {
             const int row = (MODE == 0) ? __ldg(a.P.rev + p) : p;
-            *reinterpret_cast<float4*>(base + (size_t)row * a.stride) = cur[p * txp + cp];
+            float2* dst = (MODE == 0 && sbase) ? split_row(row) : base + (size_t)row * a.stride;
+            *reinterpret_cast<float4*>(dst) = cur[p * txp + cp];
         }
     }
 }

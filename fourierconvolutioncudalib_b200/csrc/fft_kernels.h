@@ -13,6 +13,7 @@ struct XArgs {
     const float2* twx;      // exp(-2*pi*i*k/nx), k = 0..nx/2 (even nx only)
     long long nrows;        // rows to process (length of rowList when given, else ny*nz)
     const int* rowList;     // optional: global row index of each processed row (PSF pruning)
+    int compactOut;         // with rowList: write spectrum row i of the list to spec row i (not to its global row)
     PsfGather psf;          // PSF loader only
 };
 
@@ -28,6 +29,14 @@ struct ColArgs {
     float scale;            // fused mode: 1/N
     const int* groupList;   // optional: group index of each launched group (PSF pruning: active planes)
     const unsigned char* rowMask;  // optional, forward only: rowMask[r]==0 => input row r is all zero, not read
+    // Split layout (slab decomposition, multi-GPU): the transform axis is cut in blocks of splitRows rows,
+    // one block per peer.  Forward (mode 0) WRITES and inverse (mode 1) READS row r at
+    //   split + (r / splitRows) * splitBlock + group * splitGroup + (r % splitRows) * stride + column
+    // so the y pass produces / consumes the all-to-all send / receive buffer directly (no pack pass).
+    float2* split;
+    int splitRows;
+    long long splitBlock;
+    long long splitGroup;
 };
 
 bool x_pass_supported(const Geometry& g, const AxisPlanDev& P);

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kerne
         const long long grow = (li < a.nrows) ? (a.rowList ? (long long)a.rowList[li] : li) : -1;
         if (grow < 0) continue;   // warp-uniform
         const float2* src = rowt + lrow * P;
-        float2* dst = a.spec + grow * g.xcp;
+        float2* dst = a.spec + (a.compactOut ? li : grow) * g.xcp;
         for (int k0 = 0; k0 < g.xcp; k0 += 32) {
             const int k = k0 + lane;
             const float2 v = (k < g.xcp) ? src[k] : make_float2(0.f, 0.f);

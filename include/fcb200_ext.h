@@ -50,6 +50,30 @@ FUNCTION_PREFIX void fcb200_debug_psf_spectrum(const imageType* kernel, const in
 FUNCTION_PREFIX void fcb200_profile_enable(int on);
 FUNCTION_PREFIX int fcb200_profile_read(float* ms_sum, long long* counts, int n);
 
+/* ---- slab-decomposed single volume (one process per GPU; the transposes between the two
+ * decompositions are done by the caller, e.g. NCCL all-to-all) -----------------------------------
+ * A rank owns nzl consecutive z planes of the real volume [d2][d1][d0] and, after the exchange,
+ * nyl consecutive ky rows of every plane (d1 % nyl == 0, P = d1 / nyl ranks).  All pointers are
+ * DEVICE pointers; everything is enqueued on `stream` without host synchronisation.
+ *   real slab           [nzl][d1][d0]   float
+ *   z-slab spectrum     [nzl][d1][xcp]  complex (xcp = fcb200_spectrum_pitch(d0)), scratch for the passes
+ *   exchange buffer     [P][nzl][nyl][xcp] complex: block p goes to / comes from rank p
+ *   y-slab spectrum     [d2][nyl][xcp]  complex
+ * fcb200_slab_xy_forward : x + y forward passes; the y pass writes the exchange (send) buffer directly.
+ * fcb200_slab_z_fused    : forward z, multiply by the PSF-spectrum slab and 1/N, inverse z, in place.
+ * fcb200_slab_yx_inverse : y + x inverse passes; the y pass reads the exchange (receive) buffer directly.
+ * fcb200_slab_psf        : the rank's y-slab [y0, y0+nyl) of the PSF spectrum (placement fused, pruned);
+ *                          scratch must hold fcb200_slab_psf_scratch_elems() complex values. */
+FUNCTION_PREFIX void fcb200_slab_xy_forward(const imageType* real_slab, float* zslab_spec, float* send, const int* imDim,
+                                           int nzl, int nyl, int devCUDA, void* stream);
+FUNCTION_PREFIX void fcb200_slab_z_fused(float* yslab_spec, const float* H_yslab, const int* imDim, int nyl, int devCUDA,
+                                        void* stream);
+FUNCTION_PREFIX void fcb200_slab_yx_inverse(const float* recv, float* zslab_spec, imageType* real_slab, const int* imDim,
+                                           int nzl, int nyl, int devCUDA, void* stream);
+FUNCTION_PREFIX long long fcb200_slab_psf_scratch_elems(const int* imDim, const int* kernelDim, int devCUDA);
+FUNCTION_PREFIX void fcb200_slab_psf(const imageType* kernel_dev, const int* kernelDim, const int* imDim, int y0, int nyl,
+                                    float* H_yslab, float* scratch, int devCUDA, void* stream);
+
 /* Frees every cached plan and its device workspace on all devices. */
 FUNCTION_PREFIX void fcb200_release(void);
 /* Number of kernels this library has launched since load (for benchmark accounting). */
