@@ -3,6 +3,7 @@
 // Anything else falls back to the run-time-radix kernels (fft_col_fast.cu / fft_kernels.cu).
 #include "fft_xpass.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace fcb200 {
@@ -63,6 +64,171 @@ __global__ void __launch_bounds__(THREADS) col_static_kernel(ColArgs a, int tile
         __syncthreads();
     }
     if (active) slast_inv<P::R0, L, NW, TXP>(base, stride, sm, tw, cp, w);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Persistent, software-pipelined variant: one CTA per SM loops over tiles; the next NBUF-1 tiles are
+// in flight (cp.async, 16 bytes per copy, straight into shared memory, no registers) while the current
+// one is transformed.  HBM latency is hidden by the prefetch depth instead of by occupancy.
+//   MODE 0 forward, 1 inverse, 2 fused (the PSF-spectrum tile is prefetched next to the data tile).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cpa16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// last forward stage, x H x c, first inverse stage, with the PSF-spectrum tile in shared memory
+template <int R, int L, int NW>
+__device__ __forceinline__ void smid_fused_sm(const float4* __restrict__ hs, float4* __restrict__ sm, int cp, int w, float c)
+{
+    constexpr int nb = L / R;
+    constexpr int ITER = (nb + NW - 1) / NW;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int b = w + it * NW;
+        if ((nb % NW) != 0 && b >= nb) break;
+        p2 r[R], i[R];
+        load_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
+        Dft<R>::run(r, i);
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const float4 h = hs[(b * R + m) * 8 + cp];
+            const p2 hr = make_float2(h.x, h.y), hi = make_float2(h.z, h.w);
+            const p2 xr = pmuls(pfma(hr, r[m], pneg(pmul(hi, i[m]))), c);
+            const p2 xi = pmuls(pfma(hi, r[m], pmul(hr, i[m])), c);
+            r[m] = xr;
+            i[m] = xi;
+        }
+        Dft<R>::run(i, r);
+        store_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
+    }
+}
+
+template <int MODE, class P, int THREADS, int NBUF, bool MASKED>
+__global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int tilesPerGroup, int totalTiles)
+{
+    constexpr int L = P::L, NW = THREADS / 8, TILE = L * 8;
+    extern __shared__ float4 smem[];
+    float4* tw = smem;
+    float4* dbuf = tw + L;
+    float4* hbuf = dbuf + (size_t)NBUF * TILE;   // MODE 2 only
+
+    const int t = threadIdx.x;
+    const int cp = t & 7, w = t >> 3;
+    const size_t stride = (size_t)a.stride;
+
+    load_twiddles(tw, a.P.tw, L);
+
+    auto decode = [&](int tile, size_t& off) -> bool {
+        const int gi = tile / tilesPerGroup;
+        const int tt = tile - gi * tilesPerGroup;
+        const long long group = a.groupList ? (long long)a.groupList[gi] : (long long)gi;
+        const int col0 = tt * 16;
+        const int npairs = min(8, (a.rowLen - col0) >> 1);
+        off = (size_t)group * a.groupStride + col0 + 2 * cp;
+        return cp < npairs;
+    };
+    auto issue = [&](int tile, int slot) {
+        size_t off;
+        if (tile < totalTiles && decode(tile, off)) {
+            float4* d = dbuf + (size_t)slot * TILE + cp;
+            const float2* src = a.data + off;
+#pragma unroll 4
+            for (int r = w; r < L; r += NW) {
+                const int p = (MODE == 0) ? r : __ldg(a.P.pos + r);   // inverse / H: row k sits at position pos[k]
+                const int pd = (MODE == 1) ? p : r;
+                if (MASKED && a.rowMask[r] == 0) d[pd * 8] = make_float4(0.f, 0.f, 0.f, 0.f);
+                else cpa16(d + pd * 8, src + (size_t)r * stride);
+                if (MODE == 2) cpa16(hbuf + (size_t)slot * TILE + p * 8 + cp, a.H + off + (size_t)r * stride);
+            }
+        }
+        cpa_commit();
+    };
+
+    for (int k = 0; k < NBUF - 1; ++k) issue(blockIdx.x + k * gridDim.x, k);
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++it) {
+        const int slot = it % NBUF;
+        cpa_wait<NBUF - 2>();
+        __syncthreads();   // tile `it` has landed for every thread; everybody is done with tile it-1
+        issue(tile + (NBUF - 1) * (int)gridDim.x, (it + NBUF - 1) % NBUF);
+        size_t off;
+        const bool active = decode(tile, off);
+        float4* sm = dbuf + (size_t)slot * TILE;
+        float2* base = a.data + off;
+        if (MODE == 0 || MODE == 2) {
+            if (active) sstage<P::R0, L, L, NW, false>(sm, tw, cp, w);
+            __syncthreads();
+            if constexpr (P::ns >= 3) {
+                if (active) sstage<P::R1, L, L / P::R0, NW, false>(sm, tw, cp, w);
+                __syncthreads();
+            }
+            if constexpr (P::ns >= 4) {
+                if (active) sstage<P::R2, L, L / (P::R0 * P::R1), NW, false>(sm, tw, cp, w);
+                __syncthreads();
+            }
+            if (MODE == 0) {
+                if (active) slast_fwd<P::RL, L, NW>(base, stride, sm, a.P.rev, cp, w);
+                continue;
+            }
+            if (active) smid_fused_sm<P::RL, L, NW>(hbuf + (size_t)slot * TILE, sm, cp, w, a.scale);
+            __syncthreads();
+        } else {
+            if (active) sstage<P::RL, L, P::RL, NW, true>(sm, tw, cp, w);
+            __syncthreads();
+        }
+        if constexpr (P::ns >= 4) {
+            if (active) sstage<P::R2, L, P::R2 * P::R3, NW, true>(sm, tw, cp, w);
+            __syncthreads();
+        }
+        if constexpr (P::ns >= 3) {
+            if (active) sstage<P::R1, L, P::R1 * P::R2 * P::R3, NW, true>(sm, tw, cp, w);
+            __syncthreads();
+        }
+        if (active) slast_inv<P::R0, L, NW>(base, stride, sm, tw, cp, w);
+    }
+    cpa_wait<0>();
+}
+
+static int sm_count()
+{
+    static int n = [] {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return n;
+}
+
+template <class P, int THREADS, int NBUF>
+bool run_col_pipe(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
+{
+    const int tpg = (a.rowLen + 15) / 16;
+    const long long total = ngroups * tpg;
+    if (total == 0) return true;
+    if ((size_t)P::L * sizeof(float4) + (size_t)NBUF * P::L * 8 * sizeof(float4) * (mode == 2 ? 2 : 1) > (size_t)kMaxDynSmem)
+        return false;
+    if (total > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
+    const size_t tile = (size_t)P::L * 8 * sizeof(float4);
+    const size_t smem = (size_t)P::L * sizeof(float4) + (size_t)NBUF * tile * (mode == 2 ? 2 : 1);
+    const int grid = (int)std::min<long long>(total, sm_count());
+    auto go = [&](auto kernel) {
+        FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, THREADS, smem, st>>>(a, tpg, (int)total);
+        FC_CUDA_KERNEL();
+    };
+    if (mode == 0 && a.rowMask) go(col_pipe_kernel<0, P, THREADS, NBUF, true>);
+    else if (mode == 0) go(col_pipe_kernel<0, P, THREADS, NBUF, false>);
+    else if (mode == 1) go(col_pipe_kernel<1, P, THREADS, NBUF, false>);
+    else go(col_pipe_kernel<2, P, THREADS, NBUF, false>);
+    return true;
 }
 
 template <class P>
@@ -155,6 +321,12 @@ static int env_int(const char* name, int dflt)
     return e ? std::atoi(e) : dflt;
 }
 
+static int pipe_mode()
+{
+    static const int v = env_int("FCB200_PIPE", 0);
+    return v;
+}
+
 bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
     if (!static_enabled() || a.txp != 8) return false;
@@ -163,9 +335,16 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
     if (plan_matches<P64>(a.P)) run_col<P64, 64, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P128>(a.P)) run_col<P128, 64, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P256>(a.P)) run_col<P256, 128, 1, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P256b>(a.P)) run_col<P256b, 128, 2, 8>(a, mode, ngroups, st);
     else if (plan_matches<P384>(a.P)) run_col<P384, 192, 1, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P512>(a.P)) {
+    else if (plan_matches<P512>(a.P) && pipe_mode() > 0 &&
+             (pipe_mode() == 2   ? run_col_pipe<P512, 512, 2>(a, mode, ngroups, st)
+              : pipe_mode() == 3 ? run_col_pipe<P512, 1024, 3>(a, mode, ngroups, st)
+                                 : run_col_pipe<P512, 512, 3>(a, mode, ngroups, st))) {
+    } else if (plan_matches<P256b>(a.P) && pipe_mode() > 0 &&
+               (pipe_mode() == 2   ? run_col_pipe<P256b, 256, 2>(a, mode, ngroups, st)
+                : pipe_mode() == 3 ? run_col_pipe<P256b, 512, 3>(a, mode, ngroups, st)
+                                   : run_col_pipe<P256b, 256, 3>(a, mode, ngroups, st))) {
+    } else if (plan_matches<P512>(a.P)) {
         switch (v512) {
             case 1: run_col<P512, 256, 1, 8>(a, mode, ngroups, st); break;
             case 2: run_col<P512, 128, 2, 8>(a, mode, ngroups, st); break;
@@ -175,7 +354,8 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
             case 6: run_col<P512, 128, 1, 4>(a, mode, ngroups, st); break;
             default: run_col<P512, 512, 1, 8>(a, mode, ngroups, st); break;
         }
-    } else if (plan_matches<P1024>(a.P)) run_col<P1024, 512, 1, 8>(a, mode, ngroups, st);
+    } else if (plan_matches<P256b>(a.P)) run_col<P256b, 128, 2, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P1024>(a.P)) run_col<P1024, 512, 1, 8>(a, mode, ngroups, st);
     else return false;
     return true;
 }
