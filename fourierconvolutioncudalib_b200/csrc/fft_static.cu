@@ -2,6 +2,7 @@
 // dispatch that picks them when the run-time plan has exactly the same radix sequence.
 // Anything else falls back to the run-time-radix kernels (fft_col_fast.cu / fft_kernels.cu).
 #include "fft_xpass.cuh"
+#include "fft_xrow.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -366,11 +367,49 @@ static int xt256()
     return v;
 }
 
+// register-resident row-wise kernels (fft_xrow.cuh) for plans (R, R); FCB200_XROW=0 disables them
+static bool xrow_enabled()
+{
+    static const bool on = env_int("FCB200_XROW", 1) != 0;
+    return on;
+}
+
+template <int R, int THREADS>
+static bool try_xrow(const XArgs& a, bool inverse, cudaStream_t st)
+{
+    if (a.P.L != R * R || a.P.ns != 2 || a.P.radix[0] != R || a.P.radix[1] != R || a.g.odd || a.rowList) return false;
+    constexpr int RP = THREADS / R;
+    const long long grid = (a.nrows + 2 * RP - 1) / (2 * RP);
+    if (grid == 0) return true;
+    if (grid > 0x7fffffffLL) return false;
+    const size_t smem = (size_t)(R * R + RP * XRow<R>::PADM) * sizeof(float4);
+    auto go = [&](auto kernel) {
+        if (smem > 48 * 1024)
+            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<(unsigned)grid, THREADS, smem, st>>>(a);
+        FC_CUDA_KERNEL();
+    };
+    if (inverse) go(xrow_inv_kernel<R, THREADS>);
+    else go(xrow_fwd_kernel<R, THREADS>);
+    return true;
+}
+
+static int xrow_threads()
+{
+    static const int v = env_int("FCB200_XROW_T", 128);
+    return v;
+}
+
 bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st)
 {
     if (!static_enabled()) return false;
     const long long tiles = (a.nrows + 15) / 16;
     if (tiles == 0) return true;
+    if (!psf && xrow_enabled()) {
+        if (xrow_threads() == 64 && try_xrow<16, 64>(a, false, st)) return true;
+        if (xrow_threads() == 256 && try_xrow<16, 256>(a, false, st)) return true;
+        if (try_xrow<16, 128>(a, false, st) || try_xrow<8, 64>(a, false, st)) return true;
+    }
     return try_x_fwd<P32, 64>(a, psf, tiles, st) || try_x_fwd<P64, 64>(a, psf, tiles, st) ||
            try_x_fwd<P128, 128>(a, psf, tiles, st) || try_x_fwd<P192, 192>(a, psf, tiles, st) ||
            (xt256() == 128 && try_x_fwd<P256, 128>(a, psf, tiles, st)) ||
@@ -384,6 +423,11 @@ bool launch_x_inv_static(const XArgs& a, cudaStream_t st)
     if (!static_enabled()) return false;
     const long long tiles = (a.nrows + 15) / 16;
     if (tiles == 0) return true;
+    if (xrow_enabled()) {
+        if (xrow_threads() == 64 && try_xrow<16, 64>(a, true, st)) return true;
+        if (xrow_threads() == 256 && try_xrow<16, 256>(a, true, st)) return true;
+        if (try_xrow<16, 128>(a, true, st) || try_xrow<8, 64>(a, true, st)) return true;
+    }
     return try_x_inv<P32, 64>(a, tiles, st) || try_x_inv<P64, 64>(a, tiles, st) || try_x_inv<P128, 128>(a, tiles, st) ||
            try_x_inv<P192, 192>(a, tiles, st) || (xt256() == 128 && try_x_inv<P256, 128>(a, tiles, st)) ||
            (xt256() == 512 && try_x_inv<P256, 512>(a, tiles, st)) || try_x_inv<P256, 256>(a, tiles, st) ||
