@@ -27,7 +27,8 @@ std::vector<int> factorize(int L, bool* generic, int style)
         n >>= 1;
         ++e;
     }
-    // style 0 (x and y axes): radix 16 where it saves a stage.  style 1 (fused z axis): the measured
+    // style 0 (y axis): radix 16 where it saves a stage.  style 2 (x axis): the same except L = 1024.
+    // style 1 (fused z axis): the measured
     // exception L = 256 -> (8,8,4), because the fused forward-multiply-inverse kernel is register-bound
     // with two radix-16 stages (profiles/r01_notes.md).
     static const int pow2_plan[13][4] = {
@@ -39,6 +40,8 @@ std::vector<int> factorize(int L, bool* generic, int style)
     }
     if (style == 1 && L == 256) {
         out = {8, 8, 4};
+    } else if (style == 2 && L == 1024) {
+        out = {16, 8, 8};   // x axis: the row-wise register kernel needs stage strides that are multiples of 8
     } else {
         for (int i = 0; i < 4 && pow2_plan[e][i]; ++i) out.push_back(pow2_plan[e][i]);
     }
@@ -287,7 +290,7 @@ static std::shared_ptr<ConvPlan> build_plan(int device, int nx, int ny, int nz, 
     auto p = std::make_shared<ConvPlan>();
     p->device = device;
     p->g = make_geometry(nx, ny, nz);
-    make_axis(p->px, p->g.M, 0);
+    make_axis(p->px, p->g.M, 2);
     make_axis(p->py, ny, 0);
     make_axis(p->pz, nz, 1);
     if (!x_pass_supported(p->g, p->px.dev))

@@ -3,6 +3,7 @@
 // Anything else falls back to the run-time-radix kernels (fft_col_fast.cu / fft_kernels.cu).
 #include "fft_xpass.cuh"
 #include "fft_xrow.cuh"
+#include "fft_xrowg.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -394,6 +395,37 @@ static bool try_xrow(const XArgs& a, bool inverse, cudaStream_t st)
     return true;
 }
 
+template <int R0, int R1, int R2, int THREADS>
+static bool try_xrowg(const XArgs& a, bool inverse, cudaStream_t st)
+{
+    typedef XRowG<R0, R1, R2> G;
+    if (a.P.L != G::M || a.P.ns != G::NS || a.P.radix[0] != R0 || a.P.radix[1] != R1 ||
+        (G::NS == 3 && a.P.radix[2] != R2) || a.g.odd || a.rowList)
+        return false;
+    constexpr int RP = THREADS / G::TG;
+    static_assert(RP >= 1 && RP <= 15, "row pairs per CTA");
+    const long long grid = (a.nrows + 2 * RP - 1) / (2 * RP);
+    if (grid == 0) return true;
+    if (grid > 0x7fffffffLL) return false;
+    const size_t smem = (size_t)(G::TW1 + G::TW2 + RP * G::PADM) * sizeof(float4);
+    auto go = [&](auto kernel) {
+        if (smem > 48 * 1024)
+            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<(unsigned)grid, THREADS, smem, st>>>(a);
+        FC_CUDA_KERNEL();
+    };
+    if (inverse) go(xrowg_inv_kernel<R0, R1, R2, THREADS>);
+    else go(xrowg_fwd_kernel<R0, R1, R2, THREADS>);
+    return true;
+}
+
+static bool try_xrowg_all(const XArgs& a, bool inverse, cudaStream_t st)
+{
+    return try_xrowg<16, 8, 1, 64>(a, inverse, st) ||      // nx = 256
+           try_xrowg<8, 8, 8, 128>(a, inverse, st) ||      // nx = 1024
+           try_xrowg<16, 8, 8, 128>(a, inverse, st);       // nx = 2048 (x-axis planning style)
+}
+
 static int xrow_threads()
 {
     static const int v = env_int("FCB200_XROW_T", 128);
@@ -409,6 +441,7 @@ bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st)
         if (xrow_threads() == 64 && try_xrow<16, 64>(a, false, st)) return true;
         if (xrow_threads() == 256 && try_xrow<16, 256>(a, false, st)) return true;
         if (try_xrow<16, 128>(a, false, st) || try_xrow<8, 64>(a, false, st)) return true;
+        if (try_xrowg_all(a, false, st)) return true;
     }
     return try_x_fwd<P32, 64>(a, psf, tiles, st) || try_x_fwd<P64, 64>(a, psf, tiles, st) ||
            try_x_fwd<P128, 128>(a, psf, tiles, st) || try_x_fwd<P192, 192>(a, psf, tiles, st) ||
@@ -427,6 +460,7 @@ bool launch_x_inv_static(const XArgs& a, cudaStream_t st)
         if (xrow_threads() == 64 && try_xrow<16, 64>(a, true, st)) return true;
         if (xrow_threads() == 256 && try_xrow<16, 256>(a, true, st)) return true;
         if (try_xrow<16, 128>(a, true, st) || try_xrow<8, 64>(a, true, st)) return true;
+        if (try_xrowg_all(a, true, st)) return true;
     }
     return try_x_inv<P32, 64>(a, tiles, st) || try_x_inv<P64, 64>(a, tiles, st) || try_x_inv<P128, 128>(a, tiles, st) ||
            try_x_inv<P192, 192>(a, tiles, st) || (xt256() == 128 && try_x_inv<P256, 128>(a, tiles, st)) ||

@@ -22,7 +22,7 @@ FUNCTION_PREFIX int fcb200_plan_radices(int L, int* radices, int* generic);
 FUNCTION_PREFIX void fcb200_plan_tables(int L, int* rev, int* pos, float* tw);
 /* Same with an explicit planning style: 0 = fewest stages, radix 16 allowed (x and y axes);
  * 1 = z axis, whose fused forward-multiply-inverse kernel is register-bound: L = 256 is planned as
- * (8,8,4) instead of (16,16). */
+ * (8,8,4) instead of (16,16);  2 = x axis: L = 1024 is planned as (16,8,8) for the row-wise kernel. */
 FUNCTION_PREFIX int fcb200_plan_radices_style(int L, int style, int* radices, int* generic);
 FUNCTION_PREFIX void fcb200_plan_tables_style(int L, int style, int* rev, int* pos, float* tw);
 /* Spectrum row pitch (complex elements) used for a volume whose fastest extent is nx. */

@@ -26,7 +26,12 @@ def factorize(L, style=0):
     while e > 12:
         out.append(16)
         e -= 4
-    out += [8, 8, 4] if (style == 1 and L == 256) else _POW2_PLAN[e]
+    if style == 1 and L == 256:
+        out += [8, 8, 4]
+    elif style == 2 and L == 1024:
+        out += [16, 8, 8]
+    else:
+        out += _POW2_PLAN[e]
     for r in (3, 5, 7):
         while n % r == 0 and n > 1:
             out.append(r)

@@ -36,7 +36,7 @@ def test_swizzle_is_conflict_free():
         assert len({em.swz(a + 2 * i + 1) for i in range(8)}) == 8
 
 
-@pytest.mark.parametrize("style", [0, 1])
+@pytest.mark.parametrize("style", [0, 1, 2])
 @pytest.mark.parametrize("L", LENGTHS)
 def test_c_planner_matches_model(fc, L, style):
     radices, generic = fc.plan_radices(L, style)
