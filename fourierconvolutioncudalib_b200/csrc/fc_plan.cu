@@ -413,6 +413,7 @@ static XArgs x_args(ConvPlan& p)
     a.nrows = (long long)p.g.ny * p.g.nz;
     a.rowList = nullptr;
     a.compactOut = 0;
+    a.txp = 8;
     return a;
 }
 

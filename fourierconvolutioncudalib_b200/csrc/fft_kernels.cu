@@ -103,13 +103,20 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-size_t x_smem_bytes(const Geometry& g, const AxisPlanDev& P)
+size_t x_smem_bytes(const Geometry& g, const AxisPlanDev& P, int txp)
 {
-    const size_t rowt = 16 * (size_t)x_row_pitch(P.L, g.xcp) * sizeof(float2);
-    return (size_t)P.L * 8 * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)P.L * sizeof(float4) + rowt;
+    const size_t rowt = 2 * (size_t)txp * (size_t)x_row_pitch(P.L, g.xcp) * sizeof(float2);
+    return (size_t)P.L * txp * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)P.L * sizeof(float4) + rowt;
 }
 
-bool x_pass_supported(const Geometry& g, const AxisPlanDev& P) { return x_smem_bytes(g, P) <= (size_t)kMaxDynSmem; }
+int x_pick_txp(const Geometry& g, const AxisPlanDev& P)
+{
+    for (int txp = 8; txp >= 1; txp >>= 1)
+        if (x_smem_bytes(g, P, txp) <= (size_t)kMaxDynSmem) return txp;
+    return 0;
+}
+
+bool x_pass_supported(const Geometry& g, const AxisPlanDev& P) { return x_pick_txp(g, P) > 0; }
 
 int col_pick_txp(const AxisPlanDev& P)
 {
@@ -140,15 +147,18 @@ static int x_threads()
 void launch_x_fwd(const XArgs& a, bool psf, cudaStream_t st)
 {
     if (launch_x_fwd_static(a, psf, st)) return;
-    const size_t smem = x_smem_bytes(a.g, a.P);
-    const long long tiles = (a.nrows + 15) / 16;
+    XArgs b = a;
+    b.txp = x_pick_txp(a.g, a.P);
+    const XArgs& a2 = b;
+    const size_t smem = x_smem_bytes(a.g, a.P, b.txp);
+    const long long tiles = (a.nrows + 2 * b.txp - 1) / (2 * b.txp);
     if (tiles == 0) return;
     if (psf) {
         set_smem(x_fwd_kernel<1, DynPlan, kColThreads>, smem);
-        x_fwd_kernel<1, DynPlan, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a);
+        x_fwd_kernel<1, DynPlan, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a2);
     } else {
         set_smem(x_fwd_kernel<0, DynPlan, kColThreads>, smem);
-        x_fwd_kernel<0, DynPlan, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a);
+        x_fwd_kernel<0, DynPlan, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a2);
     }
     FC_CUDA_KERNEL();
 }
@@ -156,11 +166,14 @@ void launch_x_fwd(const XArgs& a, bool psf, cudaStream_t st)
 void launch_x_inv(const XArgs& a, cudaStream_t st)
 {
     if (launch_x_inv_static(a, st)) return;
-    const size_t smem = x_smem_bytes(a.g, a.P);
-    const long long tiles = (a.nrows + 15) / 16;
+    XArgs b = a;
+    b.txp = x_pick_txp(a.g, a.P);
+    const XArgs& a2 = b;
+    const size_t smem = x_smem_bytes(a.g, a.P, b.txp);
+    const long long tiles = (a.nrows + 2 * b.txp - 1) / (2 * b.txp);
     if (tiles == 0) return;
     set_smem(x_inv_kernel<DynPlan, kColThreads>, smem);
-    x_inv_kernel<DynPlan, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a);
+    x_inv_kernel<DynPlan, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a2);
     FC_CUDA_KERNEL();
 }
 

@@ -13,6 +13,7 @@ struct XArgs {
     const float2* twx;      // exp(-2*pi*i*k/nx), k = 0..nx/2 (even nx only)
     long long nrows;        // rows to process (length of rowList when given, else ny*nz)
     const int* rowList;     // optional: global row index of each processed row (PSF pruning)
+    int txp;                // run-time-plan kernels: row pairs per CTA (8, or fewer when the row is very long)
     int compactOut;         // with rowList: write spectrum row i of the list to spec row i (not to its global row)
     PsfGather psf;          // PSF loader only
 };
@@ -40,7 +41,8 @@ struct ColArgs {
 };
 
 bool x_pass_supported(const Geometry& g, const AxisPlanDev& P);
-size_t x_smem_bytes(const Geometry& g, const AxisPlanDev& P);
+size_t x_smem_bytes(const Geometry& g, const AxisPlanDev& P, int txp = 8);
+int x_pick_txp(const Geometry& g, const AxisPlanDev& P);   // largest of 8,4,2,1 that fits; 0 if none
 int col_pick_txp(const AxisPlanDev& P);
 void launch_x_fwd(const XArgs& a, bool psf, cudaStream_t st);
 void launch_x_inv(const XArgs& a, cudaStream_t st);

@@ -271,6 +271,7 @@ bool try_x_fwd(const XArgs& a, bool psf, long long tiles, cudaStream_t st)
 {
     if (!plan_matches<P>(a.P)) return false;
     const size_t smem = x_smem_bytes(a.g, a.P);
+    if (smem > (size_t)kMaxDynSmem) return false;
     auto go = [&](auto kernel) {
         if (smem > 48 * 1024)
             FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -287,6 +288,7 @@ bool try_x_inv(const XArgs& a, long long tiles, cudaStream_t st)
 {
     if (!plan_matches<P>(a.P)) return false;
     const size_t smem = x_smem_bytes(a.g, a.P);
+    if (smem > (size_t)kMaxDynSmem) return false;
     auto kernel = x_inv_kernel<P, THREADS>;
     if (smem > 48 * 1024) FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<(unsigned)tiles, THREADS, smem, st>>>(a);

@@ -110,13 +110,13 @@ struct XSmem {
     int P;
 };
 
-__device__ __forceinline__ XSmem x_carve(float4* smem, const Geometry& g, const AxisPlanDev& pl, int L)
+__device__ __forceinline__ XSmem x_carve(float4* smem, const Geometry& g, const AxisPlanDev& pl, int L, int txp)
 {
     XSmem s;
     s.P = x_row_pitch(L, g.xcp);
     s.A = smem;
-    s.B = pl.generic ? (s.A + (size_t)L * 8) : nullptr;
-    s.tw = s.A + (size_t)L * 8 * (pl.generic ? 2 : 1);
+    s.B = pl.generic ? (s.A + (size_t)L * txp) : nullptr;
+    s.tw = s.A + (size_t)L * txp * (pl.generic ? 2 : 1);
     s.rowt = reinterpret_cast<float2*>(s.tw + L);
     return s;
 }
@@ -191,20 +191,23 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kerne
     extern __shared__ float4 smem[];
     const Geometry g = a.g;
     const int L = PlanLen<PL>::get(a.P);  // complex transform length: nx/2 (even nx) or nx (odd nx)
-    const XSmem sm = x_carve(smem, g, a.P, L);
+    // rows per CTA = 2 * TXP: 16 for the static plans, fewer for very long rows (run-time plans)
+    const int TXP = IsStaticPlan<PL>::value ? 8 : a.txp;
+    const int NROWS = 2 * TXP;
+    const XSmem sm = x_carve(smem, g, a.P, L, TXP);
     const int P = sm.P;
     float2* rowt = sm.rowt;
     constexpr int NW = THREADS / 8;
 
     const int t = threadIdx.x;
-    const int cp = t & 7, w = t >> 3, W = blockDim.x >> 3;
+    const int cp = t % TXP, w = t / TXP, W = blockDim.x / TXP;
     const int lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
-    const long long row0 = (long long)blockIdx.x * 16;
+    const long long row0 = (long long)blockIdx.x * NROWS;
 
     load_twiddles(sm.tw, a.P.tw, L);
 
     // ---- global rows -> row tile (one warp per row at a time, lanes along x)
-    for (int lrow = warp; lrow < 16; lrow += nwarps) {
+    for (int lrow = warp; lrow < NROWS; lrow += nwarps) {
         const long long li = row0 + lrow;
         const long long grow = (li < a.nrows) ? (a.rowList ? (long long)a.rowList[li] : li) : -1;
         float2* dst = rowt + lrow * P;
@@ -247,10 +250,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kerne
     } else {
         for (int pos = w; pos < L; pos += W) {
             const float2 u = rowt[(2 * cp) * P + pos], v = rowt[(2 * cp + 1) * P + pos];
-            sm.A[pos * 8 + cp] = make_float4(u.x, v.x, u.y, v.y);
+            sm.A[pos * TXP + cp] = make_float4(u.x, v.x, u.y, v.y);
         }
         __syncthreads();
-        cur = engine_run<false>(a.P, sm.A, sm.B, sm.tw, cp, w, W, 8, true);
+        cur = engine_run<false>(a.P, sm.A, sm.B, sm.tw, cp, w, W, TXP, true);
     }
 
     // ---- engine tile -> row tile (interleaved spectrum rows, natural kx); even nx: split the packed
@@ -264,21 +267,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kerne
         };
         if (g.odd) {
             for (int k = w; k < g.xc; k += W) {
-                const float4 v = cur[__ldg(a.P.pos + k) * 8 + cp];
+                const float4 v = cur[__ldg(a.P.pos + k) * TXP + cp];
                 put(k, make_float2(v.x, v.y), make_float2(v.z, v.w));
             }
         } else {
             const int M = g.M;
             for (int k = w; k <= M / 2; k += W) {
                 if (k == 0) {
-                    const float4 v = cur[__ldg(a.P.pos) * 8 + cp];
+                    const float4 v = cur[__ldg(a.P.pos) * TXP + cp];
                     const p2 r = make_float2(v.x, v.y), i = make_float2(v.z, v.w), z = make_float2(0.f, 0.f);
                     put(0, padd(r, i), z);
                     put(M, psub(r, i), z);
                 } else {
                     const int k2 = M - k;
-                    const float4 va = cur[__ldg(a.P.pos + k) * 8 + cp];
-                    const float4 vb = cur[__ldg(a.P.pos + k2) * 8 + cp];
+                    const float4 va = cur[__ldg(a.P.pos + k) * TXP + cp];
+                    const float4 vb = cur[__ldg(a.P.pos + k2) * TXP + cp];
                     const float2 tk = __ldg(a.twx + k);  // exp(-2*pi*i*k/nx)
                     const p2 ar = make_float2(va.x, va.y), ai = make_float2(va.z, va.w);
                     const p2 br = make_float2(vb.x, vb.y), bi = make_float2(vb.z, vb.w);
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kerne
 
     // ---- row tile -> spectrum rows; interleaved -> pair-planar with one lane exchange:
     //      float2 slot k of a row holds (re_k, re_k+1) for even k and (im_k-1, im_k) for odd k
-    for (int lrow = warp; lrow < 16; lrow += nwarps) {
+    for (int lrow = warp; lrow < NROWS; lrow += nwarps) {
         const long long li = row0 + lrow;
         const long long grow = (li < a.nrows) ? (a.rowList ? (long long)a.rowList[li] : li) : -1;
         if (grow < 0) continue;   // warp-uniform
@@ -323,20 +326,23 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
     extern __shared__ float4 smem[];
     const Geometry g = a.g;
     const int L = PlanLen<PL>::get(a.P);
-    const XSmem sm = x_carve(smem, g, a.P, L);
+    // rows per CTA = 2 * TXP: 16 for the static plans, fewer for very long rows (run-time plans)
+    const int TXP = IsStaticPlan<PL>::value ? 8 : a.txp;
+    const int NROWS = 2 * TXP;
+    const XSmem sm = x_carve(smem, g, a.P, L, TXP);
     const int P = sm.P;
     float2* rowt = sm.rowt;
     constexpr int NW = THREADS / 8;
 
     const int t = threadIdx.x;
-    const int cp = t & 7, w = t >> 3, W = blockDim.x >> 3;
+    const int cp = t % TXP, w = t / TXP, W = blockDim.x / TXP;
     const int lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
-    const long long row0 = (long long)blockIdx.x * 16;
+    const long long row0 = (long long)blockIdx.x * NROWS;
 
     load_twiddles(sm.tw, a.P.tw, L);
 
     // ---- spectrum rows (pair-planar) -> row tile (interleaved); loads are issued XLB at a time
-    for (int lrow = warp; lrow < 16; lrow += nwarps) {
+    for (int lrow = warp; lrow < NROWS; lrow += nwarps) {
         const long long grow = row0 + lrow;
         float2* dst = rowt + lrow * P;
         const bool have = grow < a.nrows;   // warp-uniform
@@ -372,8 +378,8 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
             for (int k = w; k < g.xc; k += W) {
                 p2 re, im;
                 get(k, re, im);
-                sm.A[__ldg(a.P.pos + k) * 8 + cp] = make_float4(re.x, re.y, im.x, im.y);
-                if (k > 0) sm.A[__ldg(a.P.pos + (g.nx - k)) * 8 + cp] = make_float4(re.x, re.y, -im.x, -im.y);
+                sm.A[__ldg(a.P.pos + k) * TXP + cp] = make_float4(re.x, re.y, im.x, im.y);
+                if (k > 0) sm.A[__ldg(a.P.pos + (g.nx - k)) * TXP + cp] = make_float4(re.x, re.y, -im.x, -im.y);
             }
         } else {
             const int M = g.M;
@@ -383,7 +389,7 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
                     get(0, x0r, x0i);
                     get(M, xmr, xmi);
                     const p2 zr = padd(x0r, xmr), zi = psub(x0r, xmr);
-                    sm.A[__ldg(a.P.pos) * 8 + cp] = make_float4(zr.x, zr.y, zi.x, zi.y);
+                    sm.A[__ldg(a.P.pos) * TXP + cp] = make_float4(zr.x, zr.y, zi.x, zi.y);
                 } else {
                     const int k2 = M - k;
                     p2 ar, ai, br, bi;
@@ -396,8 +402,8 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
                     const p2 di = pfmas(Di, tk.x, pmuls(Dr, -tk.y));
                     const p2 z1r = psub(sr, di), z1i = padd(si, dr);
                     const p2 z2r = padd(sr, di), z2i = psub(dr, si);
-                    sm.A[__ldg(a.P.pos + k) * 8 + cp] = make_float4(z1r.x, z1r.y, z1i.x, z1i.y);
-                    if (k2 != k) sm.A[__ldg(a.P.pos + k2) * 8 + cp] = make_float4(z2r.x, z2r.y, z2i.x, z2i.y);
+                    sm.A[__ldg(a.P.pos + k) * TXP + cp] = make_float4(z1r.x, z1r.y, z1i.x, z1i.y);
+                    if (k2 != k) sm.A[__ldg(a.P.pos + k2) * TXP + cp] = make_float4(z2r.x, z2r.y, z2i.x, z2i.y);
                 }
             }
         }
@@ -418,9 +424,9 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
         __syncthreads();
         sstage_rows_last_inv<PL::R0, PL::L, NW>(sm.A, rowt, P, sm.tw, cp, w);
     } else {
-        float4* cur = engine_run<true>(a.P, sm.A, sm.B, sm.tw, cp, w, W, 8, true);
+        float4* cur = engine_run<true>(a.P, sm.A, sm.B, sm.tw, cp, w, W, TXP, true);
         for (int pos = w; pos < L; pos += W) {
-            const float4 v = cur[pos * 8 + cp];
+            const float4 v = cur[pos * TXP + cp];
             rowt[(2 * cp) * P + pos] = make_float2(v.x, v.z);
             rowt[(2 * cp + 1) * P + pos] = make_float2(v.y, v.w);
         }
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
     __syncthreads();
 
     // ---- row tile -> real rows
-    for (int lrow = warp; lrow < 16; lrow += nwarps) {
+    for (int lrow = warp; lrow < NROWS; lrow += nwarps) {
         const long long grow = row0 + lrow;
         if (grow >= a.nrows) continue;
         const float2* src = rowt + lrow * P;
