@@ -243,6 +243,9 @@ ConvPlan::~ConvPlan()
     cudaFree(d_rows);
     cudaFree(d_planes);
     cudaFree(d_plane_mask);
+    cudaFree(d_tap_start);
+    cudaFree(d_tap_x);
+    cudaFree(d_tap_idx);
     if (stream) cudaStreamDestroy(stream);
     if (prev >= 0) cudaSetDevice(prev);
 }
@@ -414,6 +417,7 @@ static XArgs x_args(ConvPlan& p)
     a.rowList = nullptr;
     a.compactOut = 0;
     a.txp = 8;
+    a.tapStart = a.tapX = a.tapIdx = nullptr;
     return a;
 }
 
@@ -469,6 +473,77 @@ static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
         p.n_rows = (long long)rows.size();
         p.n_planes = (int)planes.size();
         p.h_planes = planes;
+        // window of 16 consecutive planes (mod nz) that holds every active plane, if there is one
+        p.psf_window_z0 = -1;
+        for (int z0 : planes) {
+            bool ok = true;
+            for (int z : planes) ok = ok && (((z - z0) % p.g.nz + p.g.nz) % p.g.nz < 16);
+            if (ok) {
+                p.psf_window_z0 = z0;
+                break;
+            }
+        }
+        // CSR tap lists over the processed rows: tap (a,b,c) -> flat position (reference placement,
+        // src/convolution3Dfft.cu:145-164) -> (row, x)
+        {
+            std::vector<int> plane_slot((size_t)p.g.nz, -1);
+            for (size_t i = 0; i < planes.size(); ++i) plane_slot[(size_t)planes[i]] = (int)i;
+            const long long d0 = pdims[3], d1 = pdims[4], d2 = pdims[5];
+            const int k0 = pdims[0], k1 = pdims[1], k2 = pdims[2];
+            const size_t K = (size_t)k0 * k1 * k2;
+            std::vector<int> start(rows.size() + 1, 0), tx(K), tidx(K), lrow(K);
+            size_t t = 0;
+            for (int a = 0; a < k0; ++a) {
+                long long aq = a - k0 / 2;
+                if (aq < 0) aq += d0;
+                for (int b = 0; b < k1; ++b) {
+                    long long bq = b - k1 / 2;
+                    if (bq < 0) bq += d1;
+                    for (int c = 0; c < k2; ++c, ++t) {
+                        long long cq = c - k2 / 2;
+                        if (cq < 0) cq += d2;
+                        const long long flat = cq + d2 * (bq + d1 * aq);
+                        const long long grow = flat / p.g.nx;
+                        const int slot = plane_slot[(size_t)(grow / p.g.ny)];
+                        lrow[t] = slot * p.g.ny + (int)(grow % p.g.ny);
+                        start[(size_t)lrow[t] + 1]++;
+                    }
+                }
+            }
+            for (size_t i = 0; i < rows.size(); ++i) start[i + 1] += start[i];
+            std::vector<int> fill(start.begin(), start.end() - 1);
+            t = 0;
+            for (int a = 0; a < k0; ++a) {
+                long long aq = a - k0 / 2;
+                if (aq < 0) aq += d0;
+                for (int b = 0; b < k1; ++b) {
+                    long long bq = b - k1 / 2;
+                    if (bq < 0) bq += d1;
+                    for (int c = 0; c < k2; ++c, ++t) {
+                        long long cq = c - k2 / 2;
+                        if (cq < 0) cq += d2;
+                        const long long flat = cq + d2 * (bq + d1 * aq);
+                        const int at = fill[(size_t)lrow[t]]++;
+                        tx[(size_t)at] = (int)(flat % p.g.nx);
+                        tidx[(size_t)at] = (int)t;
+                    }
+                }
+            }
+            cudaFree(p.d_tap_start);
+            p.d_tap_start = nullptr;
+            FC_CUDA(cudaMalloc(&p.d_tap_start, sizeof(int) * start.size()));
+            if (K > p.taps_cap) {
+                cudaFree(p.d_tap_x);
+                cudaFree(p.d_tap_idx);
+                p.d_tap_x = p.d_tap_idx = nullptr;
+                FC_CUDA(cudaMalloc(&p.d_tap_x, sizeof(int) * K));
+                FC_CUDA(cudaMalloc(&p.d_tap_idx, sizeof(int) * K));
+                p.taps_cap = K;
+            }
+            FC_CUDA(cudaMemcpy(p.d_tap_start, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
+            FC_CUDA(cudaMemcpy(p.d_tap_x, tx.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+            FC_CUDA(cudaMemcpy(p.d_tap_idx, tidx.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+        }
         std::memcpy(p.psf_key, pdims, sizeof(int) * 6);
     }
 }
@@ -487,6 +562,9 @@ void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cuda
     xa.psf.d0 = pdims[3];
     xa.psf.d1 = pdims[4];
     xa.psf.d2 = pdims[5];
+    xa.tapStart = p.d_tap_start;
+    xa.tapX = p.d_tap_x;
+    xa.tapIdx = p.d_tap_idx;
     {
         PassTimer t(kPassPsfX, st);
         launch_x_fwd(xa, true, st);
@@ -501,7 +579,7 @@ void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cuda
         PassTimer t(kPassPsfZ, st);
         ColArgs za = z_args(p, p.d_H);
         za.rowMask = p.d_plane_mask;
-        col_pass(za, 0, 1, st);
+        if (!(p.psf_window_z0 >= 0 && launch_psf_z_pruned(za, p.psf_window_z0, st))) col_pass(za, 0, 1, st);
     }
     count_launches(3);
 }
@@ -657,6 +735,9 @@ void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, 
     xa.psf.d0 = pdims[3];
     xa.psf.d1 = pdims[4];
     xa.psf.d2 = pdims[5];
+    xa.tapStart = p.d_tap_start;
+    xa.tapX = p.d_tap_x;
+    xa.tapIdx = p.d_tap_idx;
     {
         PassTimer t(kPassPsfX, st);
         launch_x_fwd(xa, true, st);
@@ -680,7 +761,7 @@ void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, 
     za.rowMask = p.d_plane_mask;
     {
         PassTimer t(kPassPsfZ, st);
-        col_pass(za, 0, 1, st);
+        if (!(p.psf_window_z0 >= 0 && launch_psf_z_pruned(za, p.psf_window_z0, st))) col_pass(za, 0, 1, st);
     }
     count_launches(3);
 }

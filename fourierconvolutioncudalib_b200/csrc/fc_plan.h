@@ -50,6 +50,11 @@ struct ConvPlan {
     int* d_planes = nullptr;     // z planes that hold >= 1 tap
     int n_planes = 0;
     std::vector<int> h_planes;   // host copy of d_planes
+    int psf_window_z0 = -1;      // >= 0: every active plane lies in [z0, z0+16) mod nz (pruned z pass applies)
+    int* d_tap_start = nullptr;  // CSR tap lists over d_rows (see XArgs)
+    int* d_tap_x = nullptr;
+    int* d_tap_idx = nullptr;
+    size_t taps_cap = 0;
     unsigned char* d_plane_mask = nullptr;   // [nz] 1 = plane active
     cudaStream_t stream = nullptr;   // used for host-pointer calls
     std::mutex mu;

@@ -322,4 +322,68 @@ void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t
     FC_CUDA_KERNEL();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Input-pruned PSF z pass: the placed PSF is non-zero on at most 16 consecutive z planes (mod L), so
+//   X[k1*(L/16) + k2] = w16^(z0 k1) * sum_{n<16} [ x[z0+n] w_L^((z0+n) k2) ] w16^(n k1)
+// i.e. one radix-16 butterfly per output residue k2 on the 16 twiddled inputs: no shared-memory
+// stages, no barriers after the 2 KB window is staged.  L % 16 == 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) psf_z_pruned_kernel(ColArgs a, int z0)
+{
+    __shared__ float4 win[16 * 8];
+    const int L = a.P.L, Q = L / 16;
+    const int t = threadIdx.x, cp = t & 7, w = t >> 3;   // w = residue k2 in [0, Q)
+    const int col0 = blockIdx.x * 16;
+    const int npairs = min(8, (a.rowLen - col0) >> 1);
+    const bool active = cp < npairs;
+    float2* base = a.data + col0 + 2 * cp;
+    const size_t stride = (size_t)a.stride;
+
+    if (t < 128) {
+        const int n = t >> 3;
+        int z = z0 + n;
+        if (z >= L) z -= L;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && (a.rowMask == nullptr || a.rowMask[z])) v = *reinterpret_cast<const float4*>(base + (size_t)z * stride);
+        win[n * 8 + cp] = v;
+    }
+    __syncthreads();
+    if (!active) return;
+
+    p2 r[16], i[16];
+    int e = (int)(((long long)z0 * w) % L);   // exponent (z0 + n) * k2 mod L, advanced by k2 per input
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+        const float4 v = win[n * 8 + cp];
+        const float2 tw = __ldg(a.P.tw + e);
+        r[n] = make_float2(v.x, v.y);
+        i[n] = make_float2(v.z, v.w);
+        cmul(r[n], i[n], make_float4(tw.x, tw.x, tw.y, tw.y));
+        e += w;
+        if (e >= L) e -= L;
+    }
+    Dft<16>::run(r, i);
+    const int s16 = z0 & 15;   // w16^(z0 k1) = w_L^((z0 k1 mod 16) * Q)
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+        if (s16 != 0 && k1 != 0) {
+            const float2 tw = __ldg(a.P.tw + ((s16 * k1) & 15) * Q);
+            cmul(r[k1], i[k1], make_float4(tw.x, tw.x, tw.y, tw.y));
+        }
+        *reinterpret_cast<float4*>(base + (size_t)(k1 * Q + w) * stride) = make_float4(r[k1].x, r[k1].y, i[k1].x, i[k1].y);
+    }
+}
+
+bool launch_psf_z_pruned(const ColArgs& a, int z0, cudaStream_t st)
+{
+    static const bool on = env_int("FCB200_PSF_PRUNED", 1) != 0;
+    const int L = a.P.L;
+    if (!on || L % 16 != 0 || L / 16 * 8 > 1024 || L / 16 * 8 < 128 || a.groupStride != 0) return false;
+    const int tiles = (a.rowLen + 15) / 16;
+    if (tiles == 0) return true;
+    psf_z_pruned_kernel<<<tiles, L / 16 * 8, 0, st>>>(a, z0);
+    FC_CUDA_KERNEL();
+    return true;
+}
+
 }  // namespace fcb200

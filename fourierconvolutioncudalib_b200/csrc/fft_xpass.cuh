@@ -219,6 +219,18 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kerne
         } else if (LOADER == 0) {
             const float* src = a.in_real + grow * g.nx;
             for (int pos = lane; pos < L; pos += 32) dst[pos] = make_float2(__ldg(src + pos), 0.f);
+        } else if (a.tapStart != nullptr) {
+            // PSF row from its tap list: clear, then scatter the few taps that land in this row
+            for (int pos = lane; pos < L; pos += 32) dst[pos] = make_float2(0.f, 0.f);
+            __syncwarp();
+            float* dstf = reinterpret_cast<float*>(dst);
+            const int t0 = __ldg(a.tapStart + li), t1 = __ldg(a.tapStart + li + 1);
+            for (int q = t0 + lane; q < t1; q += 32) {
+                const int xq = __ldg(a.tapX + q);
+                const float v = __ldg(a.psf.kernel + __ldg(a.tapIdx + q));
+                if (g.odd) dstf[2 * xq] = v;       // (x, 0) per complex slot
+                else dstf[xq] = v;                 // two consecutive samples per complex slot
+            }
         } else if (!g.odd) {
             const long long f0 = grow * g.nx;
             for (int pos = lane; pos < L; pos += 32)
