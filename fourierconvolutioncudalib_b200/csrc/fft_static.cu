@@ -316,6 +316,17 @@ typedef SPlan<512, 8, 8, 8> P512;
 typedef SPlan<1024, 16, 16, 4> P1024;
 // planning style 1 (fused z axis): L = 256 as (8,8,4)
 typedef SPlan<256, 8, 8, 4> P256b;
+// 7-smooth extents of caller-padded volumes (BASELINE configs 2-4 padded: 270, 300, 420, 448, 560) and
+// the half-lengths of their x transforms
+typedef SPlan<560, 16, 5, 7> P560;
+typedef SPlan<448, 8, 8, 7> P448;
+typedef SPlan<420, 4, 3, 5, 7> P420;
+typedef SPlan<300, 4, 3, 5, 5> P300;
+typedef SPlan<280, 8, 5, 7> P280;
+typedef SPlan<224, 8, 4, 7> P224;
+typedef SPlan<210, 2, 3, 5, 7> P210;
+typedef SPlan<150, 2, 3, 5, 5> P150;
+typedef SPlan<135, 3, 3, 3, 5> P135;
 
 }  // namespace
 
@@ -359,6 +370,10 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
             default: run_col<P512, 512, 1, 8>(a, mode, ngroups, st); break;
         }
     } else if (plan_matches<P256b>(a.P)) run_col<P256b, 128, 2, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P560>(a.P)) run_col<P560, 320, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P448>(a.P)) run_col<P448, 512, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P420>(a.P)) run_col<P420, 384, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P300>(a.P)) run_col<P300, 256, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P1024>(a.P)) run_col<P1024, 512, 1, 8>(a, mode, ngroups, st);
     else return false;
     return true;
@@ -450,7 +465,9 @@ bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st)
            (xt256() == 128 && try_x_fwd<P256, 128>(a, psf, tiles, st)) ||
            (xt256() == 512 && try_x_fwd<P256, 512>(a, psf, tiles, st)) ||
            try_x_fwd<P256, 256>(a, psf, tiles, st) || try_x_fwd<P512, 256>(a, psf, tiles, st) ||
-           try_x_fwd<P1024, 512>(a, psf, tiles, st);
+           try_x_fwd<P1024, 512>(a, psf, tiles, st) || try_x_fwd<P280, 256>(a, psf, tiles, st) ||
+           try_x_fwd<P224, 256>(a, psf, tiles, st) || try_x_fwd<P210, 256>(a, psf, tiles, st) ||
+           try_x_fwd<P150, 256>(a, psf, tiles, st) || try_x_fwd<P135, 256>(a, psf, tiles, st);
 }
 
 bool launch_x_inv_static(const XArgs& a, cudaStream_t st)
@@ -467,7 +484,9 @@ bool launch_x_inv_static(const XArgs& a, cudaStream_t st)
     return try_x_inv<P32, 64>(a, tiles, st) || try_x_inv<P64, 64>(a, tiles, st) || try_x_inv<P128, 128>(a, tiles, st) ||
            try_x_inv<P192, 192>(a, tiles, st) || (xt256() == 128 && try_x_inv<P256, 128>(a, tiles, st)) ||
            (xt256() == 512 && try_x_inv<P256, 512>(a, tiles, st)) || try_x_inv<P256, 256>(a, tiles, st) ||
-           try_x_inv<P512, 256>(a, tiles, st) || try_x_inv<P1024, 512>(a, tiles, st);
+           try_x_inv<P512, 256>(a, tiles, st) || try_x_inv<P1024, 512>(a, tiles, st) ||
+           try_x_inv<P280, 256>(a, tiles, st) || try_x_inv<P224, 256>(a, tiles, st) || try_x_inv<P210, 256>(a, tiles, st) ||
+           try_x_inv<P150, 256>(a, tiles, st) || try_x_inv<P135, 256>(a, tiles, st);
 }
 
 }  // namespace fcb200

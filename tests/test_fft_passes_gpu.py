@@ -11,6 +11,7 @@ SHAPES = [  # imDim = (d0 fastest, d1, d2)
     (13, 17, 19), (46, 46, 106), (130, 130, 132), (66, 66, 66),
     (158, 22, 18),           # 2*79: generic radix
     (256, 256, 16), (512, 32, 8), (270, 30, 20), (300, 40, 28), (2, 2, 2), (4, 1, 1), (6, 2, 1),
+    (560, 300, 8), (448, 420, 4), (420, 560, 3), (270, 448, 2), (32, 6, 300), (32, 4, 448), (300, 4, 560),
     (1024, 16, 4), (2048, 8, 6), (128, 34, 3), (256, 5, 3), (384, 12, 4), (32, 1024, 2), (16, 4, 1024),
 ]
 

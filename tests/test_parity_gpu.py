@@ -44,6 +44,8 @@ CASES = [  # (imDim, kernelDim): cubic, non-cubic (placement quirk), odd, generi
     ((512, 512, 32), (31, 31, 21)),
     ((96, 80, 48), (9, 7, 5)),
     ((30, 20, 50), (4, 6, 2)),            # even kernel extents
+    ((560, 300, 24), (9, 9, 5)),          # 7-smooth static plans (caller-padded config 3 extents)
+    ((420, 448, 16), (7, 7, 5)),
     ((1024, 64, 16), (9, 5, 7)),          # row-wise x kernel, 3 stages
     ((2048, 16, 8), (5, 3, 3)),           # row-wise x kernel, (16,8,8)
 ]
