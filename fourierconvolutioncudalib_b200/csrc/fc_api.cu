@@ -94,7 +94,7 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
         FC_CUDA(cudaMemcpyAsync(p.d_kernel, kernel, ktaps * sizeof(float), cudaMemcpyHostToDevice, st));
         d_kernel = p.d_kernel;
     }
-    run_psf_spectrum(p, d_kernel, pdims, st);
+    run_psf_spectrum(p, d_kernel, pdims, st, /*materialize=*/false);
 
     float* d_im = im;
     if (!im_dev) {
@@ -189,6 +189,7 @@ imageType* convolution3DfftCUDA_test(imageType* im, int* imDim, imageType* kerne
         // kernel is already image-sized and used as is (no shift), reference :253, :270
         FC_CUDA(cudaMemcpyAsync(p.d_real, kernel, n * sizeof(float), cudaMemcpyHostToDevice, st));
         run_forward(p, p.d_real, p.d_H, 3, st);
+        p.H_window_only = false;   // a full, materialised spectrum of the image-sized kernel
         FC_CUDA(cudaMemcpyAsync(p.d_real, im, n * sizeof(float), cudaMemcpyHostToDevice, st));
         run_convolve(p, p.d_real, st);
         FC_CUDA(cudaMemcpyAsync(out.get(), p.d_real, n * sizeof(float), cudaMemcpyDeviceToHost, st));

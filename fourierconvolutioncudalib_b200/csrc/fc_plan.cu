@@ -548,7 +548,7 @@ static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
     }
 }
 
-void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
+void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st, bool materialize)
 {
     psf_lists(p, pdims, st);
     XArgs xa = x_args(p);
@@ -574,6 +574,15 @@ void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cuda
         ColArgs ya = y_args(p, p.d_H);
         ya.groupList = p.d_planes;
         col_pass(ya, 0, p.n_planes, st);
+    }
+    p.H_window_only = false;
+    if (!materialize && p.psf_window_z0 >= 0) {
+        ColArgs za = z_args(p, p.d_spec);
+        if (launch_col_otf(za, 1, p.psf_window_z0, st, true)) {
+            p.H_window_only = true;   // the fused z pass will derive the PSF spectrum on the fly
+            count_launches(2);
+            return;
+        }
     }
     {
         PassTimer t(kPassPsfZ, st);
@@ -620,7 +629,13 @@ void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st)
     za.scale = 1.0f / (float)((size_t)p.g.nx * (size_t)p.g.ny * (size_t)p.g.nz);
     {
         PassTimer t(kPassZFused, st);
-        col_pass(za, 2, 1, st);
+        if (p.H_window_only) {
+            za.rowMask = p.d_plane_mask;
+            if (!launch_col_otf(za, 1, p.psf_window_z0, st, false))
+                throw std::runtime_error("fcb200: internal error, on-the-fly z pass unavailable");
+        } else {
+            col_pass(za, 2, 1, st);
+        }
     }
     {
         PassTimer t(kPassYInv, st);

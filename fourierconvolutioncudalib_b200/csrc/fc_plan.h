@@ -50,6 +50,7 @@ struct ConvPlan {
     int* d_planes = nullptr;     // z planes that hold >= 1 tap
     int n_planes = 0;
     std::vector<int> h_planes;   // host copy of d_planes
+    bool H_window_only = false;  // d_H holds only the (x,y)-transformed window planes (on-the-fly path)
     int psf_window_z0 = -1;      // >= 0: every active plane lies in [z0, z0+16) mod nz (pruned z pass applies)
     int* d_tap_start = nullptr;  // CSR tap lists over d_rows (see XArgs)
     int* d_tap_x = nullptr;
@@ -81,7 +82,9 @@ int profile_read(float* ms_sum, long long* counts, int n);
 // ---- pipeline pieces (all enqueue on `st`) -------------------------------------------------------
 // PSF spectrum into plan.d_H.  pdims = the six ints handed to fftShiftKernel by the reference
 // (k0,k1,k2,d0,d1,d2); d_kernel = taps on the device.
-void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st);
+// materialize = false lets the plan skip the PSF z pass when the fused z kernel can derive the PSF
+// spectrum on the fly (run_convolve then uses that kernel)
+void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st, bool materialize = true);
 // Spectrum of a dense image-sized volume into dst (used for the image and for the legacy
 // convolution3DfftCUDA_test whose kernel is already image-sized).
 void run_forward(ConvPlan& p, const float* d_real, float2* dst, int passes, cudaStream_t st);

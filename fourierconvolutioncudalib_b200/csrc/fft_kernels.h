@@ -61,6 +61,9 @@ bool col_fast_supported(const AxisPlanDev& P);
 void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
 // compile-time specialised kernels (fft_static.cu); return false when none matches the plan
 bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
+// fused z pass that derives the PSF-spectrum tile on the fly from the <=16 window planes starting at z0;
+// a.H = buffer holding those planes (after the x and y passes); probe = only test applicability
+bool launch_col_otf(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, bool probe);
 bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st);
 bool launch_x_inv_static(const XArgs& a, cudaStream_t st);
 

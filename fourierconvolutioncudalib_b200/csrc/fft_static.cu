@@ -330,6 +330,140 @@ typedef SPlan<135, 3, 3, 3, 5> P135;
 
 }  // namespace
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused z pass with the PSF spectrum computed ON THE FLY (SaveMemory path): when the placed PSF spans
+// at most 16 consecutive z planes (mod L), every CTA derives the H tile of its 16 pencils from the 16
+// window rows of the (x,y)-transformed PSF -- one input-pruned radix-16 butterfly per output residue
+// (see psf_z_pruned_kernel) -- into shared memory, then runs forward z, x H x 1/N, inverse z as usual.
+// No image-sized PSF spectrum is ever written or read: -1/3 of the fused pass's HBM traffic and no PSF z
+// kernel at all.  a.H points at the buffer that holds the window planes at their z positions.
+// ------------------------------------------------------------------------------------------------
+template <int R, int L, int NW>
+__device__ __forceinline__ void smid_fused_nat(const float4* __restrict__ hs, float4* __restrict__ sm,
+                                               const int* __restrict__ rev, int cp, int w, float c)
+{
+    constexpr int nb = L / R, fs = L / R;
+    constexpr int ITER = (nb + NW - 1) / NW;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int b = w + it * NW;
+        if ((nb % NW) != 0 && b >= nb) break;
+        p2 r[R], i[R];
+        load_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
+        const int k0 = __ldg(rev + b * R);
+        Dft<R>::run(r, i);
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const float4 h = hs[(k0 + m * fs) * 8 + cp];   // H tile is in natural frequency order
+            const p2 hr = make_float2(h.x, h.y), hi = make_float2(h.z, h.w);
+            const p2 xr = pmuls(pfma(hr, r[m], pneg(pmul(hi, i[m]))), c);
+            const p2 xi = pmuls(pfma(hi, r[m], pmul(hr, i[m])), c);
+            r[m] = xr;
+            i[m] = xi;
+        }
+        Dft<R>::run(i, r);
+        store_pairs<R>(sm, b * R * 8 + cp, 8, r, i);
+    }
+}
+
+template <class P, int THREADS, int U>
+__global__ void __launch_bounds__(THREADS) col_otf_kernel(ColArgs a, int tilesPerGroup, int z0)
+{
+    constexpr int L = P::L, NW = THREADS / 8, Q = L / 16;
+    static_assert(L % 16 == 0, "on-the-fly PSF spectrum needs L % 16 == 0");
+    extern __shared__ float4 smem[];
+    float4* sm = smem;
+    float4* tw = sm + (size_t)L * 8;
+    float4* ht = tw + L;                 // H tile, natural frequency order
+    float4* win = ht + (size_t)L * 8;    // 16 window rows
+
+    const int t = threadIdx.x;
+    const int cp = t & 7, w = t >> 3;
+    const int gi = blockIdx.x / tilesPerGroup;
+    const int tt = blockIdx.x - gi * tilesPerGroup;
+    const long long group = a.groupList ? (long long)a.groupList[gi] : (long long)gi;
+    const int col0 = tt * 16;
+    const int npairs = min(8, (a.rowLen - col0) >> 1);
+    const bool active = cp < npairs;
+    const size_t off = (size_t)group * a.groupStride + col0 + 2 * cp;
+    float2* base = a.data + off;
+    const size_t stride = (size_t)a.stride;
+
+    load_twiddles(tw, a.P.tw, L);
+    for (int q = t; q < 128; q += THREADS) {   // q & 7 == cp because THREADS % 8 == 0
+        int z = z0 + (q >> 3);
+        if (z >= L) z -= L;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && (a.rowMask == nullptr || a.rowMask[z])) v = __ldg(reinterpret_cast<const float4*>(a.H + off + (size_t)z * stride));
+        win[q] = v;
+    }
+    __syncthreads();
+
+    if (active) {
+        sfirst_fwd<P::R0, L, NW, U, false, 8>(base, stride, sm, tw, cp, w, nullptr);
+        // H[k1*Q + k2] = w16^(z0 k1) sum_n [ win[n] w_L^((z0+n) k2) ] w16^(n k1)
+        const int s16 = z0 & 15;
+        for (int k2 = w; k2 < Q; k2 += NW) {
+            p2 r[16], i[16];
+            int e = (z0 * k2) % L;
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+                const float4 v = win[n * 8 + cp];
+                r[n] = make_float2(v.x, v.y);
+                i[n] = make_float2(v.z, v.w);
+                cmul(r[n], i[n], tw[e]);
+                e += k2;
+                if (e >= L) e -= L;
+            }
+            Dft<16>::run(r, i);
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) {
+                if (s16 != 0 && k1 != 0) cmul(r[k1], i[k1], tw[((s16 * k1) & 15) * Q]);
+                ht[(k1 * Q + k2) * 8 + cp] = make_float4(r[k1].x, r[k1].y, i[k1].x, i[k1].y);
+            }
+        }
+    }
+    __syncthreads();
+    if constexpr (P::ns >= 3) {
+        if (active) sstage<P::R1, L, L / P::R0, NW, false, 8>(sm, tw, cp, w);
+        __syncthreads();
+    }
+    if constexpr (P::ns >= 4) {
+        if (active) sstage<P::R2, L, L / (P::R0 * P::R1), NW, false, 8>(sm, tw, cp, w);
+        __syncthreads();
+    }
+    if (active) smid_fused_nat<P::RL, L, NW>(ht, sm, a.P.rev, cp, w, a.scale);
+    __syncthreads();
+    if constexpr (P::ns >= 4) {
+        if (active) sstage<P::R2, L, P::R2 * P::R3, NW, true, 8>(sm, tw, cp, w);
+        __syncthreads();
+    }
+    if constexpr (P::ns >= 3) {
+        if (active) sstage<P::R1, L, P::R1 * P::R2 * P::R3, NW, true, 8>(sm, tw, cp, w);
+        __syncthreads();
+    }
+    if (active) slast_inv<P::R0, L, NW, 8>(base, stride, sm, tw, cp, w);
+}
+
+template <class P, int THREADS, int U>
+bool try_col_otf(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, bool probe)
+{
+    if (!plan_matches<P>(a.P)) return false;
+    const size_t smem = ((size_t)P::L * 8 * 2 + P::L + 128) * sizeof(float4);
+    if (2 * smem > (size_t)kMaxDynSmem) return false;   // keep at least two CTAs per SM
+    if (probe) return true;
+    const int tpg = (a.rowLen + 15) / 16;
+    const long long grid = ngroups * tpg;
+    if (grid == 0) return true;
+    if (grid > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
+    auto kernel = col_otf_kernel<P, THREADS, U>;
+    if (smem > 48 * 1024) FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)grid, THREADS, smem, st>>>(a, tpg, z0);
+    FC_CUDA_KERNEL();
+    return true;
+}
+
 static int env_int(const char* name, int dflt)
 {
     const char* e = std::getenv(name);
@@ -447,6 +581,15 @@ static int xrow_threads()
 {
     static const int v = env_int("FCB200_XROW_T", 128);
     return v;
+}
+
+// Fused z pass with on-the-fly PSF spectrum; probe = only report whether a kernel exists for the plan.
+bool launch_col_otf(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, bool probe)
+{
+    static const bool on = env_int("FCB200_OTF", 1) != 0;
+    if (!on || !static_enabled() || a.txp != 8) return false;
+    return try_col_otf<P256b, 128, 2>(a, ngroups, z0, st, probe) || try_col_otf<P128, 64, 1>(a, ngroups, z0, st, probe) ||
+           try_col_otf<P64, 64, 1>(a, ngroups, z0, st, probe) || try_col_otf<P384, 192, 1>(a, ngroups, z0, st, probe);
 }
 
 bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st)
