@@ -391,17 +391,30 @@ __global__ void __launch_bounds__(THREADS) col_otf_kernel(ColArgs a, int tilesPe
     const size_t stride = (size_t)a.stride;
 
     load_twiddles(tw, a.P.tw, L);
-    for (int q = t; q < 128; q += THREADS) {   // q & 7 == cp because THREADS % 8 == 0
+    // window rows: issued now, consumed after the first stage so that their latency overlaps with the
+    // first-stage loads (q & 7 == cp because THREADS % 8 == 0)
+    constexpr int NWIN = (128 + THREADS - 1) / THREADS;
+    float4 wv[NWIN];
+#pragma unroll
+    for (int u = 0; u < NWIN; ++u) {
+        const int q = t + u * THREADS;
         int z = z0 + (q >> 3);
         if (z >= L) z -= L;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active && (a.rowMask == nullptr || a.rowMask[z])) v = __ldg(reinterpret_cast<const float4*>(a.H + off + (size_t)z * stride));
-        win[q] = v;
+        wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < 128 && active && (a.rowMask == nullptr || a.rowMask[z]))
+            wv[u] = __ldg(reinterpret_cast<const float4*>(a.H + off + (size_t)z * stride));
     }
-    __syncthreads();
+    __syncthreads();   // twiddles ready
+
+    if (active) sfirst_fwd<P::R0, L, NW, U, false, 8>(base, stride, sm, tw, cp, w, nullptr);
+#pragma unroll
+    for (int u = 0; u < NWIN; ++u) {
+        const int q = t + u * THREADS;
+        if (q < 128) win[q] = wv[u];
+    }
+    __syncthreads();   // first-stage outputs and window rows ready
 
     if (active) {
-        sfirst_fwd<P::R0, L, NW, U, false, 8>(base, stride, sm, tw, cp, w, nullptr);
         // H[k1*Q + k2] = w16^(z0 k1) sum_n [ win[n] w_L^((z0+n) k2) ] w16^(n k1)
         const int s16 = z0 & 15;
         for (int k2 = w; k2 < Q; k2 += NW) {
@@ -424,7 +437,8 @@ __global__ void __launch_bounds__(THREADS) col_otf_kernel(ColArgs a, int tilesPe
             }
         }
     }
-    __syncthreads();
+    // the H tile is consumed by the mid stage only: the next stage barrier covers it (ns >= 3)
+    if constexpr (P::ns == 2) __syncthreads();
     if constexpr (P::ns >= 3) {
         if (active) sstage<P::R1, L, L / P::R0, NW, false, 8>(sm, tw, cp, w);
         __syncthreads();
@@ -588,7 +602,9 @@ bool launch_col_otf(const ColArgs& a, long long ngroups, int z0, cudaStream_t st
 {
     static const bool on = env_int("FCB200_OTF", 1) != 0;
     if (!on || !static_enabled() || a.txp != 8) return false;
-    return try_col_otf<P256b, 128, 2>(a, ngroups, z0, st, probe) || try_col_otf<P128, 64, 1>(a, ngroups, z0, st, probe) ||
+    static const int t256 = env_int("FCB200_OTF_T", 256);
+    if (t256 == 128 && try_col_otf<P256b, 128, 2>(a, ngroups, z0, st, probe)) return true;
+    return try_col_otf<P256b, 256, 1>(a, ngroups, z0, st, probe) || try_col_otf<P128, 64, 1>(a, ngroups, z0, st, probe) ||
            try_col_otf<P64, 64, 1>(a, ngroups, z0, st, probe) || try_col_otf<P384, 192, 1>(a, ngroups, z0, st, probe);
 }
 
