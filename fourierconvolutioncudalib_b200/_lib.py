@@ -17,7 +17,7 @@ ABI_SYMBOLS = (
     "fcb200_last_error", "fcb200_set_error_mode", "fcb200_free_result",
 )
 EXT_SYMBOLS = (
-    "fcb200_convolve_device_async", "fcb200_plan_radices", "fcb200_plan_tables",
+    "fcb200_convolve_device_async", "fcb200_convolve_device_async_savememory", "fcb200_plan_radices", "fcb200_plan_tables",
     "fcb200_plan_radices_style", "fcb200_plan_tables_style",
     "fcb200_spectrum_pitch", "fcb200_workspace_bytes", "fcb200_psf_active_rows",
     "fcb200_debug_rfft3", "fcb200_debug_irfft3", "fcb200_debug_psf_spectrum",
@@ -67,6 +67,7 @@ def load():
         "fcb200_free_result": (None, [vp]),
         "fcb200_set_error_mode": (None, [i]),
         "fcb200_convolve_device_async": (None, [vp, ip, vp, ip, i, vp]),
+        "fcb200_convolve_device_async_savememory": (None, [vp, ip, vp, ip, i, vp]),
         "fcb200_plan_radices": (i, [i, ip, ip]),
         "fcb200_plan_tables": (None, [i, ip, ip, fp]),
         "fcb200_plan_radices_style": (i, [i, i, ip, ip]),

@@ -135,6 +135,11 @@ def convolve_device_async(im_dev, imDim, kernel_dev, kernelDim, devCUDA, stream=
                                              int(devCUDA), ctypes.c_void_p(int(stream)))
 
 
+def convolve_device_async_savememory(im_dev, imDim, kernel_dev, kernelDim, devCUDA, stream=0):
+    _load().fcb200_convolve_device_async_savememory(_ptr(im_dev), _ints(imDim), _ptr(kernel_dev), _ints(kernelDim),
+                                                        int(devCUDA), ctypes.c_void_p(int(stream)))
+
+
 def plan_radices(L, style=0):
     r = (ctypes.c_int * 16)()
     g = ctypes.c_int(0)

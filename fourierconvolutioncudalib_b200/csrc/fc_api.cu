@@ -69,7 +69,7 @@ struct DeviceGuard {
 //   nx,ny,nz : geometry of the real volume as consumed (nx fastest)
 //   pdims    : (k0,k1,k2,d0,d1,d2) handed to the PSF placement (reference fftShiftKernel arguments)
 void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const int* pdims, int dev,
-                   bool force_async, cudaStream_t user_stream)
+                   bool force_async, cudaStream_t user_stream, bool save_memory = false)
 {
     DeviceGuard guard(dev);
     for (int i = 0; i < 3; ++i)
@@ -94,7 +94,10 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
         FC_CUDA(cudaMemcpyAsync(p.d_kernel, kernel, ktaps * sizeof(float), cudaMemcpyHostToDevice, st));
         d_kernel = p.d_kernel;
     }
-    run_psf_spectrum(p, d_kernel, pdims, st, /*materialize=*/false);
+    // SaveMemory: PSF spectrum derived on the fly inside the fused z kernel from <= 16 PSF planes (no
+    // image-sized PSF buffer); falls back to the materialised spectrum when the PSF spans more planes
+    const bool window = save_memory && run_psf_window(p, d_kernel, pdims, st);
+    if (!window) run_psf_spectrum(p, d_kernel, pdims, st);
 
     float* d_im = im;
     if (!im_dev) {
@@ -104,7 +107,8 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
     } else if ((reinterpret_cast<uintptr_t>(im) & 7) != 0) {
         throw std::runtime_error("fcb200: device image pointer must be 8-byte aligned");
     }
-    run_convolve(p, d_im, st);
+    if (window) run_convolve_window(p, d_im, st);
+    else run_convolve(p, d_im, st);
     if (!im_dev) FC_CUDA(cudaMemcpyAsync(im, p.d_real, p.real_bytes(), cudaMemcpyDeviceToHost, st));
     if (!force_async) FC_CUDA(cudaStreamSynchronize(st));
 }
@@ -143,8 +147,23 @@ void convolution3DfftCUDAInPlace(imageType* im, int* imDim, imageType* kernel, i
 
 void convolution3DfftCUDAInPlaceSaveMemory(imageType* im, int* imDim, imageType* kernel, int* kernelDim, int devCUDA)
 {
-    // Same contract and same numbers as InPlace ("SaveMemory").
-    convolution3DfftCUDAInPlace(im, imDim, kernel, kernelDim, devCUDA);
+    // Same contract as InPlace, same numbers up to fp32 round-off, but the image-sized PSF spectrum is never
+    // materialised when the placed PSF spans <= 16 z planes ("SaveMemory").
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
+        convolve_core(im, imDim[0], imDim[1], imDim[2], kernel, pdims, devCUDA, false, nullptr, true);
+    });
+}
+
+void fcb200_convolve_device_async_savememory(imageType* im_dev, const int* imDim, const imageType* kernel_dev,
+                                             const int* kernelDim, int devCUDA, void* stream)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
+        convolve_core(im_dev, imDim[0], imDim[1], imDim[2], kernel_dev, pdims, devCUDA, true, (cudaStream_t)stream, true);
+    });
 }
 
 void fcb200_convolve_device_async(imageType* im_dev, const int* imDim, const imageType* kernel_dev,
@@ -188,8 +207,8 @@ imageType* convolution3DfftCUDA_test(imageType* im, int* imDim, imageType* kerne
         if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
         // kernel is already image-sized and used as is (no shift), reference :253, :270
         FC_CUDA(cudaMemcpyAsync(p.d_real, kernel, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        ensure_full_workspace(p);
         run_forward(p, p.d_real, p.d_H, 3, st);
-        p.H_window_only = false;   // a full, materialised spectrum of the image-sized kernel
         FC_CUDA(cudaMemcpyAsync(p.d_real, im, n * sizeof(float), cudaMemcpyHostToDevice, st));
         run_convolve(p, p.d_real, st);
         FC_CUDA(cudaMemcpyAsync(out.get(), p.d_real, n * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -238,6 +238,8 @@ ConvPlan::~ConvPlan()
     cudaFree(d_twx);
     cudaFree(d_spec);
     cudaFree(d_H);
+    cudaFree(d_Hwin);
+    cudaFree(d_win_slot);
     cudaFree(d_real);
     cudaFree(d_kernel);
     cudaFree(d_rows);
@@ -312,10 +314,7 @@ static std::shared_ptr<ConvPlan> build_plan(int device, int nx, int ny, int nz, 
         FC_CUDA(cudaMalloc(&p->d_twx, sizeof(float2) * twx.size()));
         FC_CUDA(cudaMemcpy(p->d_twx, twx.data(), sizeof(float2) * twx.size(), cudaMemcpyHostToDevice));
     }
-    if (workspace) {
-        FC_CUDA(cudaMalloc(&p->d_spec, p->spec_bytes()));
-        FC_CUDA(cudaMalloc(&p->d_H, p->spec_bytes()));
-    }
+    if (workspace) FC_CUDA(cudaMalloc(&p->d_spec, p->spec_bytes()));   // d_H / d_Hwin: on first use
     FC_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     return p;
 }
@@ -371,6 +370,7 @@ static ColArgs y_args(ConvPlan& p, float2* data)
     a.split = nullptr;
     a.splitRows = 0;
     a.splitBlock = a.splitGroup = 0;
+    a.winSlot = nullptr;
     return a;
 }
 
@@ -404,6 +404,7 @@ static ColArgs z_args(ConvPlan& p, float2* data)
     a.split = nullptr;
     a.splitRows = 0;
     a.splitBlock = a.splitGroup = 0;
+    a.winSlot = nullptr;
     return a;
 }
 
@@ -548,8 +549,14 @@ static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
     }
 }
 
-void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st, bool materialize)
+void ensure_full_workspace(ConvPlan& p)
 {
+    if (!p.d_H) FC_CUDA(cudaMalloc(&p.d_H, p.spec_bytes()));
+}
+
+void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
+{
+    ensure_full_workspace(p);
     psf_lists(p, pdims, st);
     XArgs xa = x_args(p);
     xa.spec = p.d_H;
@@ -575,15 +582,6 @@ void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cuda
         ya.groupList = p.d_planes;
         col_pass(ya, 0, p.n_planes, st);
     }
-    p.H_window_only = false;
-    if (!materialize && p.psf_window_z0 >= 0) {
-        ColArgs za = z_args(p, p.d_spec);
-        if (launch_col_otf(za, 1, p.psf_window_z0, st, true)) {
-            p.H_window_only = true;   // the fused z pass will derive the PSF spectrum on the fly
-            count_launches(2);
-            return;
-        }
-    }
     {
         PassTimer t(kPassPsfZ, st);
         ColArgs za = z_args(p, p.d_H);
@@ -591,6 +589,89 @@ void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cuda
         if (!(p.psf_window_z0 >= 0 && launch_psf_z_pruned(za, p.psf_window_z0, st))) col_pass(za, 0, 1, st);
     }
     count_launches(3);
+}
+
+bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
+{
+    psf_lists(p, pdims, st);
+    if (p.psf_window_z0 < 0 || p.n_planes > 16) return false;
+    {
+        ColArgs probe = z_args(p, p.d_spec);
+        if (!launch_col_otf(probe, 1, p.psf_window_z0, st, true)) return false;
+    }
+    if (!p.d_Hwin) FC_CUDA(cudaMalloc(&p.d_Hwin, (size_t)16 * p.g.ny * p.g.xcp * sizeof(float2)));
+    if (!p.d_win_slot) FC_CUDA(cudaMalloc(&p.d_win_slot, 16 * sizeof(int)));
+    if (std::memcmp(p.win_key, pdims, sizeof(int) * 6) != 0) {
+        int slots[16];
+        for (int n = 0; n < 16; ++n) {
+            const int z = (p.psf_window_z0 + n) % p.g.nz;
+            slots[n] = -1;
+            for (int i = 0; i < p.n_planes; ++i)
+                if (p.h_planes[(size_t)i] == z) slots[n] = i;
+        }
+        FC_CUDA(cudaStreamSynchronize(st));
+        FC_CUDA(cudaMemcpy(p.d_win_slot, slots, sizeof(slots), cudaMemcpyHostToDevice));
+        std::memcpy(p.win_key, pdims, sizeof(int) * 6);
+    }
+    XArgs xa = x_args(p);
+    xa.spec = p.d_Hwin;
+    xa.nrows = p.n_rows;
+    xa.rowList = p.d_rows;
+    xa.compactOut = 1;
+    xa.psf.kernel = d_kernel;
+    xa.psf.k0 = pdims[0];
+    xa.psf.k1 = pdims[1];
+    xa.psf.k2 = pdims[2];
+    xa.psf.d0 = pdims[3];
+    xa.psf.d1 = pdims[4];
+    xa.psf.d2 = pdims[5];
+    xa.tapStart = p.d_tap_start;
+    xa.tapX = p.d_tap_x;
+    xa.tapIdx = p.d_tap_idx;
+    {
+        PassTimer t(kPassPsfX, st);
+        launch_x_fwd(xa, true, st);
+    }
+    {
+        PassTimer t(kPassPsfY, st);
+        col_pass(y_args(p, p.d_Hwin), 0, p.n_planes, st);
+    }
+    count_launches(2);
+    return true;
+}
+
+void run_convolve_window(ConvPlan& p, float* d_real, cudaStream_t st)
+{
+    XArgs xa = x_args(p);
+    xa.in_real = d_real;
+    xa.spec = p.d_spec;
+    {
+        PassTimer t(kPassXFwd, st);
+        launch_x_fwd(xa, false, st);
+    }
+    {
+        PassTimer t(kPassYFwd, st);
+        col_pass(y_args(p, p.d_spec), 0, p.g.nz, st);
+    }
+    ColArgs za = z_args(p, p.d_spec);
+    za.H = p.d_Hwin;
+    za.winSlot = p.d_win_slot;
+    za.scale = 1.0f / (float)((size_t)p.g.nx * (size_t)p.g.ny * (size_t)p.g.nz);
+    {
+        PassTimer t(kPassZFused, st);
+        if (!launch_col_otf(za, 1, p.psf_window_z0, st, false))
+            throw std::runtime_error("fcb200: internal error, on-the-fly z pass unavailable");
+    }
+    {
+        PassTimer t(kPassYInv, st);
+        col_pass(y_args(p, p.d_spec), 1, p.g.nz, st);
+    }
+    xa.out_real = d_real;
+    {
+        PassTimer t(kPassXInv, st);
+        launch_x_inv(xa, st);
+    }
+    count_launches(5);
 }
 
 void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st)
@@ -629,13 +710,7 @@ void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st)
     za.scale = 1.0f / (float)((size_t)p.g.nx * (size_t)p.g.ny * (size_t)p.g.nz);
     {
         PassTimer t(kPassZFused, st);
-        if (p.H_window_only) {
-            za.rowMask = p.d_plane_mask;
-            if (!launch_col_otf(za, 1, p.psf_window_z0, st, false))
-                throw std::runtime_error("fcb200: internal error, on-the-fly z pass unavailable");
-        } else {
-            col_pass(za, 2, 1, st);
-        }
+        col_pass(za, 2, 1, st);
     }
     {
         PassTimer t(kPassYInv, st);

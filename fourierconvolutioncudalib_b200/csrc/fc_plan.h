@@ -44,13 +44,15 @@ struct ConvPlan {
     size_t kernel_cap = 0;
     // PSF pruning lists, cached per kernel shape / placement dims
     int psf_key[6] = {0, 0, 0, 0, 0, 0};
+    int win_key[6] = {0, 0, 0, 0, 0, 0};
     int* d_rows = nullptr;       // rows (z*ny+y) the PSF x pass processes: every row of every active plane
     long long n_rows = 0;
     size_t rows_cap = 0;
     int* d_planes = nullptr;     // z planes that hold >= 1 tap
     int n_planes = 0;
     std::vector<int> h_planes;   // host copy of d_planes
-    bool H_window_only = false;  // d_H holds only the (x,y)-transformed window planes (on-the-fly path)
+    float2* d_Hwin = nullptr;    // SaveMemory path: compact (x,y)-transformed PSF planes [n_planes<=16][ny][xcp]
+    int* d_win_slot = nullptr;   // [16] compact plane of window position n, -1 = none
     int psf_window_z0 = -1;      // >= 0: every active plane lies in [z0, z0+16) mod nz (pruned z pass applies)
     int* d_tap_start = nullptr;  // CSR tap lists over d_rows (see XArgs)
     int* d_tap_x = nullptr;
@@ -82,9 +84,13 @@ int profile_read(float* ms_sum, long long* counts, int n);
 // ---- pipeline pieces (all enqueue on `st`) -------------------------------------------------------
 // PSF spectrum into plan.d_H.  pdims = the six ints handed to fftShiftKernel by the reference
 // (k0,k1,k2,d0,d1,d2); d_kernel = taps on the device.
-// materialize = false lets the plan skip the PSF z pass when the fused z kernel can derive the PSF
-// spectrum on the fly (run_convolve then uses that kernel)
-void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st, bool materialize = true);
+void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st);
+// SaveMemory path: only the <=16 z planes that hold taps are (x,y)-transformed, into a compact buffer; the
+// fused z kernel derives the PSF spectrum on the fly.  Returns false (nothing done) when the path does
+// not apply (taps span more than 16 planes, or no kernel for the z length): use the functions above.
+bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st);
+void run_convolve_window(ConvPlan& p, float* d_real, cudaStream_t st);
+void ensure_full_workspace(ConvPlan& p);   // allocates the image-sized PSF spectrum buffer on first use
 // Spectrum of a dense image-sized volume into dst (used for the image and for the legacy
 // convolution3DfftCUDA_test whose kernel is already image-sized).
 void run_forward(ConvPlan& p, const float* d_real, float2* dst, int passes, cudaStream_t st);

@@ -39,6 +39,7 @@ struct ColArgs {
     // one block per peer.  Forward (mode 0) WRITES and inverse (mode 1) READS row r at
     //   split + (r / splitRows) * splitBlock + group * splitGroup + (r % splitRows) * stride + column
     // so the y pass produces / consumes the all-to-all send / receive buffer directly (no pack pass).
+    const int* winSlot;     // on-the-fly PSF path: compact plane slot of window position n (16 ints, -1 = no taps)
     float2* split;
     int splitRows;
     long long splitBlock;

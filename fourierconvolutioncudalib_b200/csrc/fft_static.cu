@@ -337,7 +337,8 @@ typedef SPlan<135, 3, 3, 3, 5> P135;
 // window rows of the (x,y)-transformed PSF -- one input-pruned radix-16 butterfly per output residue
 // (see psf_z_pruned_kernel) -- into shared memory, then runs forward z, x H x 1/N, inverse z as usual.
 // No image-sized PSF spectrum is ever written or read: -1/3 of the fused pass's HBM traffic and no PSF z
-// kernel at all.  a.H points at the buffer that holds the window planes at their z positions.
+// kernel at all.  a.H points at the COMPACT buffer [<=16 planes][ny][xcp] of (x,y)-transformed PSF planes;
+// a.winSlot[n] is the compact plane of window position n (z = (z0 + n) mod L), -1 when it holds no tap.
 // ------------------------------------------------------------------------------------------------
 template <int R, int L, int NW>
 __device__ __forceinline__ void smid_fused_nat(const float4* __restrict__ hs, float4* __restrict__ sm,
@@ -398,11 +399,11 @@ __global__ void __launch_bounds__(THREADS) col_otf_kernel(ColArgs a, int tilesPe
 #pragma unroll
     for (int u = 0; u < NWIN; ++u) {
         const int q = t + u * THREADS;
-        int z = z0 + (q >> 3);
-        if (z >= L) z -= L;
         wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q < 128 && active && (a.rowMask == nullptr || a.rowMask[z]))
-            wv[u] = __ldg(reinterpret_cast<const float4*>(a.H + off + (size_t)z * stride));
+        if (q < 128 && active) {
+            const int slot = __ldg(a.winSlot + (q >> 3));   // compact plane that holds window position n
+            if (slot >= 0) wv[u] = __ldg(reinterpret_cast<const float4*>(a.H + off + (size_t)slot * stride));
+        }
     }
     __syncthreads();   // twiddles ready
 

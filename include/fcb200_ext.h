@@ -13,6 +13,11 @@
 FUNCTION_PREFIX void fcb200_convolve_device_async(imageType* im_dev, const int* imDim, const imageType* kernel_dev,
                                                  const int* kernelDim, int devCUDA, void* stream);
 
+/* Same for convolution3DfftCUDAInPlaceSaveMemory (PSF spectrum derived on the fly). */
+FUNCTION_PREFIX void fcb200_convolve_device_async_savememory(imageType* im_dev, const int* imDim,
+                                                            const imageType* kernel_dev, const int* kernelDim,
+                                                            int devCUDA, void* stream);
+
 /* Planner introspection (pure host code; callable without a GPU).
  * fcb200_plan_radices: writes the stage radices of a length-L transform (at most 16), returns the
  * number of stages; *generic is 1 when a radix outside {2,3,4,5,7,8} is needed. */
