@@ -1,16 +1,12 @@
-// Compile-time specialised kernels (fft_static.cuh) for the hot transform lengths, and the
-// dispatch that picks them when the run-time plan has exactly the same radix sequence.
-// Anything else falls back to the run-time-radix kernels (fft_col_fast.cu / fft_kernels.cu).
-#include "fft_xpass.cuh"
-#include "fft_xrow.cuh"
-#include "fft_xrowg.cuh"
-
-#include <algorithm>
-#include <cstdlib>
+// Compile-time specialised strided-axis (y / z) kernels for the hot transform lengths, and the dispatch
+// that picks them when the run-time plan has exactly the same radix sequence.  Anything else falls back
+// to the run-time-radix kernels (fft_col_fast.cu / fft_kernels.cu).
+#include "fft_static_plans.h"
 
 namespace fcb200 {
 
 namespace {
+
 
 // MODE 0 forward, 1 inverse, 2 fused forward x H x scale inverse (see fft_col_fast.cu)
 template <int MODE, class P, int THREADS, int U, bool MASKED, int TXP>
@@ -233,16 +229,6 @@ bool run_col_pipe(const ColArgs& a, int mode, long long ngroups, cudaStream_t st
     return true;
 }
 
-template <class P>
-bool plan_matches(const AxisPlanDev& d)
-{
-    if (d.L != P::L || d.ns != P::ns || d.generic) return false;
-    const int r[4] = {P::R0, P::R1, P::R2, P::R3};
-    for (int i = 0; i < P::ns; ++i)
-        if (d.radix[i] != r[i]) return false;
-    return true;
-}
-
 template <typename K>
 void launch(K kernel, long long grid, int threads, size_t smem, cudaStream_t st, const ColArgs& a, int tpg)
 {
@@ -266,70 +252,8 @@ void run_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
     else launch(col_static_kernel<2, P, THREADS, U, false, TXP>, grid, THREADS, smem, st, a, tpg);
 }
 
-template <class P, int THREADS>
-bool try_x_fwd(const XArgs& a, bool psf, long long tiles, cudaStream_t st)
-{
-    if (!plan_matches<P>(a.P)) return false;
-    const size_t smem = x_smem_bytes(a.g, a.P);
-    if (smem > (size_t)kMaxDynSmem) return false;
-    auto go = [&](auto kernel) {
-        if (smem > 48 * 1024)
-            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<(unsigned)tiles, THREADS, smem, st>>>(a);
-        FC_CUDA_KERNEL();
-    };
-    if (psf) go(x_fwd_kernel<1, P, THREADS>);
-    else go(x_fwd_kernel<0, P, THREADS>);
-    return true;
-}
-
-template <class P, int THREADS>
-bool try_x_inv(const XArgs& a, long long tiles, cudaStream_t st)
-{
-    if (!plan_matches<P>(a.P)) return false;
-    const size_t smem = x_smem_bytes(a.g, a.P);
-    if (smem > (size_t)kMaxDynSmem) return false;
-    auto kernel = x_inv_kernel<P, THREADS>;
-    if (smem > 48 * 1024) FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<(unsigned)tiles, THREADS, smem, st>>>(a);
-    FC_CUDA_KERNEL();
-    return true;
-}
-
-bool static_enabled()
-{
-    static const bool on = [] {
-        const char* e = std::getenv("FCB200_STATIC");
-        return !(e && std::atoi(e) == 0);
-    }();
-    return on;
-}
-
-// The radix sequences are exactly what the planner (fc_plan.cu: factorize) produces.
-typedef SPlan<32, 8, 4> P32;
-typedef SPlan<64, 8, 8> P64;
-typedef SPlan<128, 16, 8> P128;
-typedef SPlan<192, 8, 8, 3> P192;
-typedef SPlan<256, 16, 16> P256;
-typedef SPlan<384, 16, 8, 3> P384;
-typedef SPlan<512, 8, 8, 8> P512;
-typedef SPlan<1024, 16, 16, 4> P1024;
-// planning style 1 (fused z axis): L = 256 as (8,8,4)
-typedef SPlan<256, 8, 8, 4> P256b;
-// 7-smooth extents of caller-padded volumes (BASELINE configs 2-4 padded: 270, 300, 420, 448, 560) and
-// the half-lengths of their x transforms
-typedef SPlan<560, 16, 5, 7> P560;
-typedef SPlan<448, 8, 8, 7> P448;
-typedef SPlan<420, 4, 3, 5, 7> P420;
-typedef SPlan<300, 4, 3, 5, 5> P300;
-typedef SPlan<280, 8, 5, 7> P280;
-typedef SPlan<224, 8, 4, 7> P224;
-typedef SPlan<210, 2, 3, 5, 7> P210;
-typedef SPlan<150, 2, 3, 5, 5> P150;
-typedef SPlan<135, 3, 3, 3, 5> P135;
 
 }  // namespace
-
 
 // ------------------------------------------------------------------------------------------------
 // Fused z pass with the PSF spectrum computed ON THE FLY (SaveMemory path): when the placed PSF spans
@@ -479,17 +403,12 @@ bool try_col_otf(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, b
     return true;
 }
 
-static int env_int(const char* name, int dflt)
-{
-    const char* e = std::getenv(name);
-    return e ? std::atoi(e) : dflt;
-}
-
 static int pipe_mode()
 {
     static const int v = env_int("FCB200_PIPE", 0);
     return v;
 }
+
 
 bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
@@ -528,77 +447,6 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
     return true;
 }
 
-static int xt256()
-{
-    static const int v = env_int("FCB200_XT256", 256);
-    return v;
-}
-
-// register-resident row-wise kernels (fft_xrow.cuh) for plans (R, R); FCB200_XROW=0 disables them
-static bool xrow_enabled()
-{
-    static const bool on = env_int("FCB200_XROW", 1) != 0;
-    return on;
-}
-
-template <int R, int THREADS>
-static bool try_xrow(const XArgs& a, bool inverse, cudaStream_t st)
-{
-    if (a.P.L != R * R || a.P.ns != 2 || a.P.radix[0] != R || a.P.radix[1] != R || a.g.odd || a.rowList) return false;
-    constexpr int RP = THREADS / R;
-    const long long grid = (a.nrows + 2 * RP - 1) / (2 * RP);
-    if (grid == 0) return true;
-    if (grid > 0x7fffffffLL) return false;
-    const size_t smem = (size_t)(R * R + RP * XRow<R>::PADM) * sizeof(float4);
-    auto go = [&](auto kernel) {
-        if (smem > 48 * 1024)
-            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<(unsigned)grid, THREADS, smem, st>>>(a);
-        FC_CUDA_KERNEL();
-    };
-    if (inverse) go(xrow_inv_kernel<R, THREADS>);
-    else go(xrow_fwd_kernel<R, THREADS>);
-    return true;
-}
-
-template <int R0, int R1, int R2, int THREADS>
-static bool try_xrowg(const XArgs& a, bool inverse, cudaStream_t st)
-{
-    typedef XRowG<R0, R1, R2> G;
-    if (a.P.L != G::M || a.P.ns != G::NS || a.P.radix[0] != R0 || a.P.radix[1] != R1 ||
-        (G::NS == 3 && a.P.radix[2] != R2) || a.g.odd || a.rowList)
-        return false;
-    constexpr int RP = THREADS / G::TG;
-    static_assert(RP >= 1 && RP <= 15, "row pairs per CTA");
-    const long long grid = (a.nrows + 2 * RP - 1) / (2 * RP);
-    if (grid == 0) return true;
-    if (grid > 0x7fffffffLL) return false;
-    const size_t smem = (size_t)(G::TW1 + G::TW2 + RP * G::PADM) * sizeof(float4);
-    auto go = [&](auto kernel) {
-        if (smem > 48 * 1024)
-            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<(unsigned)grid, THREADS, smem, st>>>(a);
-        FC_CUDA_KERNEL();
-    };
-    if (inverse) go(xrowg_inv_kernel<R0, R1, R2, THREADS>);
-    else go(xrowg_fwd_kernel<R0, R1, R2, THREADS>);
-    return true;
-}
-
-static bool try_xrowg_all(const XArgs& a, bool inverse, cudaStream_t st)
-{
-    return try_xrowg<16, 8, 1, 64>(a, inverse, st) ||      // nx = 256
-           try_xrowg<8, 8, 8, 128>(a, inverse, st) ||      // nx = 1024
-           try_xrowg<16, 8, 8, 128>(a, inverse, st);       // nx = 2048 (x-axis planning style)
-}
-
-static int xrow_threads()
-{
-    static const int v = env_int("FCB200_XROW_T", 128);
-    return v;
-}
-
-// Fused z pass with on-the-fly PSF spectrum; probe = only report whether a kernel exists for the plan.
 bool launch_col_otf(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, bool probe)
 {
     static const bool on = env_int("FCB200_OTF", 1) != 0;
@@ -609,44 +457,5 @@ bool launch_col_otf(const ColArgs& a, long long ngroups, int z0, cudaStream_t st
            try_col_otf<P64, 64, 1>(a, ngroups, z0, st, probe) || try_col_otf<P384, 192, 1>(a, ngroups, z0, st, probe);
 }
 
-bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st)
-{
-    if (!static_enabled()) return false;
-    const long long tiles = (a.nrows + 15) / 16;
-    if (tiles == 0) return true;
-    if (!psf && xrow_enabled()) {
-        if (xrow_threads() == 64 && try_xrow<16, 64>(a, false, st)) return true;
-        if (xrow_threads() == 256 && try_xrow<16, 256>(a, false, st)) return true;
-        if (try_xrow<16, 128>(a, false, st) || try_xrow<8, 64>(a, false, st)) return true;
-        if (try_xrowg_all(a, false, st)) return true;
-    }
-    return try_x_fwd<P32, 64>(a, psf, tiles, st) || try_x_fwd<P64, 64>(a, psf, tiles, st) ||
-           try_x_fwd<P128, 128>(a, psf, tiles, st) || try_x_fwd<P192, 192>(a, psf, tiles, st) ||
-           (xt256() == 128 && try_x_fwd<P256, 128>(a, psf, tiles, st)) ||
-           (xt256() == 512 && try_x_fwd<P256, 512>(a, psf, tiles, st)) ||
-           try_x_fwd<P256, 256>(a, psf, tiles, st) || try_x_fwd<P512, 256>(a, psf, tiles, st) ||
-           try_x_fwd<P1024, 512>(a, psf, tiles, st) || try_x_fwd<P280, 256>(a, psf, tiles, st) ||
-           try_x_fwd<P224, 256>(a, psf, tiles, st) || try_x_fwd<P210, 256>(a, psf, tiles, st) ||
-           try_x_fwd<P150, 256>(a, psf, tiles, st) || try_x_fwd<P135, 256>(a, psf, tiles, st);
-}
-
-bool launch_x_inv_static(const XArgs& a, cudaStream_t st)
-{
-    if (!static_enabled()) return false;
-    const long long tiles = (a.nrows + 15) / 16;
-    if (tiles == 0) return true;
-    if (xrow_enabled()) {
-        if (xrow_threads() == 64 && try_xrow<16, 64>(a, true, st)) return true;
-        if (xrow_threads() == 256 && try_xrow<16, 256>(a, true, st)) return true;
-        if (try_xrow<16, 128>(a, true, st) || try_xrow<8, 64>(a, true, st)) return true;
-        if (try_xrowg_all(a, true, st)) return true;
-    }
-    return try_x_inv<P32, 64>(a, tiles, st) || try_x_inv<P64, 64>(a, tiles, st) || try_x_inv<P128, 128>(a, tiles, st) ||
-           try_x_inv<P192, 192>(a, tiles, st) || (xt256() == 128 && try_x_inv<P256, 128>(a, tiles, st)) ||
-           (xt256() == 512 && try_x_inv<P256, 512>(a, tiles, st)) || try_x_inv<P256, 256>(a, tiles, st) ||
-           try_x_inv<P512, 256>(a, tiles, st) || try_x_inv<P1024, 512>(a, tiles, st) ||
-           try_x_inv<P280, 256>(a, tiles, st) || try_x_inv<P224, 256>(a, tiles, st) || try_x_inv<P210, 256>(a, tiles, st) ||
-           try_x_inv<P150, 256>(a, tiles, st) || try_x_inv<P135, 256>(a, tiles, st);
-}
 
 }  // namespace fcb200

@@ -1,0 +1,157 @@
+// Compile-time specialised x-pass kernels: the transposing two-tile kernels (fft_xpass.cuh) for static
+// plans and the register-resident row-wise kernels (fft_xrow.cuh, fft_xrowg.cuh), with their dispatch.
+#include "fft_xpass.cuh"
+#include "fft_xrow.cuh"
+#include "fft_xrowg.cuh"
+#include "fft_static_plans.h"
+
+namespace fcb200 {
+
+namespace {
+
+template <class P, int THREADS>
+bool try_x_fwd(const XArgs& a, bool psf, long long tiles, cudaStream_t st)
+{
+    if (!plan_matches<P>(a.P)) return false;
+    const size_t smem = x_smem_bytes(a.g, a.P);
+    if (smem > (size_t)kMaxDynSmem) return false;
+    auto go = [&](auto kernel) {
+        if (smem > 48 * 1024)
+            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<(unsigned)tiles, THREADS, smem, st>>>(a);
+        FC_CUDA_KERNEL();
+    };
+    if (psf) go(x_fwd_kernel<1, P, THREADS>);
+    else go(x_fwd_kernel<0, P, THREADS>);
+    return true;
+}
+
+template <class P, int THREADS>
+bool try_x_inv(const XArgs& a, long long tiles, cudaStream_t st)
+{
+    if (!plan_matches<P>(a.P)) return false;
+    const size_t smem = x_smem_bytes(a.g, a.P);
+    if (smem > (size_t)kMaxDynSmem) return false;
+    auto kernel = x_inv_kernel<P, THREADS>;
+    if (smem > 48 * 1024) FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)tiles, THREADS, smem, st>>>(a);
+    FC_CUDA_KERNEL();
+    return true;
+}
+
+
+}  // namespace
+
+static int xt256()
+{
+    static const int v = env_int("FCB200_XT256", 256);
+    return v;
+}
+
+// register-resident row-wise kernels (fft_xrow.cuh) for plans (R, R); FCB200_XROW=0 disables them
+static bool xrow_enabled()
+{
+    static const bool on = env_int("FCB200_XROW", 1) != 0;
+    return on;
+}
+
+template <int R, int THREADS>
+static bool try_xrow(const XArgs& a, bool inverse, cudaStream_t st)
+{
+    if (a.P.L != R * R || a.P.ns != 2 || a.P.radix[0] != R || a.P.radix[1] != R || a.g.odd || a.rowList) return false;
+    constexpr int RP = THREADS / R;
+    const long long grid = (a.nrows + 2 * RP - 1) / (2 * RP);
+    if (grid == 0) return true;
+    if (grid > 0x7fffffffLL) return false;
+    const size_t smem = (size_t)(R * R + RP * XRow<R>::PADM) * sizeof(float4);
+    auto go = [&](auto kernel) {
+        if (smem > 48 * 1024)
+            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<(unsigned)grid, THREADS, smem, st>>>(a);
+        FC_CUDA_KERNEL();
+    };
+    if (inverse) go(xrow_inv_kernel<R, THREADS>);
+    else go(xrow_fwd_kernel<R, THREADS>);
+    return true;
+}
+
+template <int R0, int R1, int R2, int THREADS>
+static bool try_xrowg(const XArgs& a, bool inverse, cudaStream_t st)
+{
+    typedef XRowG<R0, R1, R2> G;
+    if (a.P.L != G::M || a.P.ns != G::NS || a.P.radix[0] != R0 || a.P.radix[1] != R1 ||
+        (G::NS == 3 && a.P.radix[2] != R2) || a.g.odd || a.rowList)
+        return false;
+    constexpr int RP = THREADS / G::TG;
+    static_assert(RP >= 1 && RP <= 15, "row pairs per CTA");
+    const long long grid = (a.nrows + 2 * RP - 1) / (2 * RP);
+    if (grid == 0) return true;
+    if (grid > 0x7fffffffLL) return false;
+    const size_t smem = (size_t)(G::TW1 + G::TW2 + RP * G::PADM) * sizeof(float4);
+    auto go = [&](auto kernel) {
+        if (smem > 48 * 1024)
+            FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<(unsigned)grid, THREADS, smem, st>>>(a);
+        FC_CUDA_KERNEL();
+    };
+    if (inverse) go(xrowg_inv_kernel<R0, R1, R2, THREADS>);
+    else go(xrowg_fwd_kernel<R0, R1, R2, THREADS>);
+    return true;
+}
+
+static bool try_xrowg_all(const XArgs& a, bool inverse, cudaStream_t st)
+{
+    return try_xrowg<16, 8, 1, 64>(a, inverse, st) ||      // nx = 256
+           try_xrowg<8, 8, 8, 128>(a, inverse, st) ||      // nx = 1024
+           try_xrowg<16, 8, 8, 128>(a, inverse, st);       // nx = 2048 (x-axis planning style)
+}
+
+static int xrow_threads()
+{
+    static const int v = env_int("FCB200_XROW_T", 128);
+    return v;
+}
+
+// Fused z pass with on-the-fly PSF spectrum; probe = only report whether a kernel exists for the plan.
+bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st)
+{
+    if (!static_enabled()) return false;
+    const long long tiles = (a.nrows + 15) / 16;
+    if (tiles == 0) return true;
+    if (!psf && xrow_enabled()) {
+        if (xrow_threads() == 64 && try_xrow<16, 64>(a, false, st)) return true;
+        if (xrow_threads() == 256 && try_xrow<16, 256>(a, false, st)) return true;
+        if (try_xrow<16, 128>(a, false, st) || try_xrow<8, 64>(a, false, st)) return true;
+        if (try_xrowg_all(a, false, st)) return true;
+    }
+    return try_x_fwd<P32, 64>(a, psf, tiles, st) || try_x_fwd<P64, 64>(a, psf, tiles, st) ||
+           try_x_fwd<P128, 128>(a, psf, tiles, st) || try_x_fwd<P192, 192>(a, psf, tiles, st) ||
+           (xt256() == 128 && try_x_fwd<P256, 128>(a, psf, tiles, st)) ||
+           (xt256() == 512 && try_x_fwd<P256, 512>(a, psf, tiles, st)) ||
+           try_x_fwd<P256, 256>(a, psf, tiles, st) || try_x_fwd<P512, 256>(a, psf, tiles, st) ||
+           try_x_fwd<P1024, 512>(a, psf, tiles, st) || try_x_fwd<P280, 256>(a, psf, tiles, st) ||
+           try_x_fwd<P224, 256>(a, psf, tiles, st) || try_x_fwd<P210, 256>(a, psf, tiles, st) ||
+           try_x_fwd<P150, 256>(a, psf, tiles, st) || try_x_fwd<P135, 256>(a, psf, tiles, st);
+}
+
+bool launch_x_inv_static(const XArgs& a, cudaStream_t st)
+{
+    if (!static_enabled()) return false;
+    const long long tiles = (a.nrows + 15) / 16;
+    if (tiles == 0) return true;
+    if (xrow_enabled()) {
+        if (xrow_threads() == 64 && try_xrow<16, 64>(a, true, st)) return true;
+        if (xrow_threads() == 256 && try_xrow<16, 256>(a, true, st)) return true;
+        if (try_xrow<16, 128>(a, true, st) || try_xrow<8, 64>(a, true, st)) return true;
+        if (try_xrowg_all(a, true, st)) return true;
+    }
+    return try_x_inv<P32, 64>(a, tiles, st) || try_x_inv<P64, 64>(a, tiles, st) || try_x_inv<P128, 128>(a, tiles, st) ||
+           try_x_inv<P192, 192>(a, tiles, st) || (xt256() == 128 && try_x_inv<P256, 128>(a, tiles, st)) ||
+           (xt256() == 512 && try_x_inv<P256, 512>(a, tiles, st)) || try_x_inv<P256, 256>(a, tiles, st) ||
+           try_x_inv<P512, 256>(a, tiles, st) || try_x_inv<P1024, 512>(a, tiles, st) ||
+           try_x_inv<P280, 256>(a, tiles, st) || try_x_inv<P224, 256>(a, tiles, st) || try_x_inv<P210, 256>(a, tiles, st) ||
+           try_x_inv<P150, 256>(a, tiles, st) || try_x_inv<P135, 256>(a, tiles, st);
+}
+
+
+}  // namespace fcb200
