@@ -1,0 +1,110 @@
+"""Edge cases through the C ABI: degenerate extents, kernel as large as the image, legacy entry points,
+concurrent callers, failures that must raise instead of exiting.  Tolerance 1e-4 / 1e-5 as everywhere."""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import fc_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+def check(got, want, max_rel=1e-4, l2_rel=1e-5):
+    got = np.asarray(got, np.float64).ravel()
+    want = np.asarray(want, np.float64).ravel()
+    scale = max(np.abs(want).max(), 1e-30)
+    assert np.abs(got - want).max() <= max_rel * scale
+    assert np.linalg.norm(got - want) <= l2_rel * max(np.linalg.norm(want), 1e-30)
+
+
+DEGENERATE = [  # imDim, kernelDim
+    ((1, 1, 1), (1, 1, 1)), ((8, 1, 1), (3, 1, 1)), ((1, 8, 1), (1, 3, 1)), ((1, 1, 8), (1, 1, 3)),
+    ((2, 3, 1), (1, 1, 1)), ((7, 1, 5), (3, 1, 3)), ((16, 16, 1), (5, 5, 1)), ((3, 5, 7), (3, 5, 7)),
+    ((8, 8, 8), (8, 8, 8)), ((12, 10, 6), (12, 1, 1)), ((5, 4, 3), (1, 4, 1)), ((64, 2, 2), (9, 1, 1)),
+    ((2, 2, 64), (1, 1, 9)), ((31, 29, 23), (5, 3, 7)), ((97, 4, 4), (3, 3, 3)),
+]
+
+
+@pytest.mark.parametrize("imDim,kDim", DEGENERATE, ids=lambda v: "x".join(map(str, v)))
+def test_degenerate_and_full_size_kernels(fc, dev, imDim, kDim):
+    rng = np.random.default_rng(sum(imDim) * 31 + sum(kDim))
+    im = rng.random(int(np.prod(imDim)), dtype=np.float32) + 0.5
+    k = rng.random(int(np.prod(kDim)), dtype=np.float32)
+    want = fo.convolve_inplace_ref(im, imDim, k, kDim)
+    for entry in (fc.convolution3DfftCUDAInPlace, fc.convolution3DfftCUDAInPlaceSaveMemory):
+        got = im.copy()
+        entry(got, imDim, k.copy(), kDim, dev)
+        check(got, want)
+
+
+def test_legacy_out_of_place_entry_points(fc, dev):
+    """convolution3DfftCUDA / _test (reference src/convolution3Dfft.cu:216-391): legacy convention, imDim[2]
+    fastest for image, kernel and placement, i.e. a plain centred circular convolution of [d0][d1][d2] arrays."""
+    rng = np.random.default_rng(8)
+    imDim, kDim = (12, 20, 16), (3, 5, 7)
+    im = rng.random(imDim).astype(np.float32)
+    k = rng.random(kDim).astype(np.float32)
+    S = np.zeros(imDim)
+    for a in range(kDim[0]):
+        for b in range(kDim[1]):
+            for c in range(kDim[2]):
+                S[(a - kDim[0] // 2) % imDim[0], (b - kDim[1] // 2) % imDim[1], (c - kDim[2] // 2) % imDim[2]] = k[a, b, c]
+    want = np.fft.irfftn(np.fft.rfftn(im.astype(np.float64)) * np.fft.rfftn(S), s=imDim, axes=(0, 1, 2))
+    before = im.copy()
+    got = fc.convolution3DfftCUDA(im.reshape(-1), imDim, k.reshape(-1), kDim, dev)
+    assert np.array_equal(im, before)                      # out of place: the input is untouched
+    check(got, want)
+    got2 = fc.convolution3DfftCUDA_test(im.reshape(-1), imDim, S.astype(np.float32).reshape(-1), dev)
+    check(got2, want)
+
+
+def test_concurrent_host_threads(fc, dev):
+    """the reference is stateless and thread-safe by construction; the plan cache must keep that property"""
+    shapes = [((64, 48, 40), (5, 5, 5)), ((64, 48, 40), (7, 3, 5)), ((96, 32, 16), (3, 3, 3)), ((30, 20, 50), (4, 6, 2))]
+    rng = np.random.default_rng(0)
+    jobs = []
+    for imDim, kDim in shapes * 2:
+        im = rng.random(int(np.prod(imDim)), dtype=np.float32)
+        k = rng.random(int(np.prod(kDim)), dtype=np.float32)
+        jobs.append((imDim, kDim, im, k, fo.convolve_inplace_ref(im, imDim, k, kDim)))
+    errors = []
+
+    def work(job):
+        imDim, kDim, im, k, want = job
+        try:
+            for _ in range(3):
+                got = im.copy()
+                fc.convolution3DfftCUDAInPlace(got, imDim, k.copy(), kDim, dev)
+                check(got, want)
+        except Exception as exc:          # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=work, args=(j,)) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+def test_out_of_memory_raises_and_library_stays_usable(fc, dev):
+    with pytest.raises(fc.api.FourierConvolutionError):
+        fc.convolution3DfftCUDAInPlace(np.zeros(8, np.float32), (4096, 4096, 4096), np.ones(1, np.float32), (1, 1, 1), dev)
+    im = np.arange(64, dtype=np.float32)
+    k = np.zeros(27, np.float32)
+    k[13] = 1
+    got = im.copy()
+    fc.convolution3DfftCUDAInPlace(got, (4, 4, 4), k, (3, 3, 3), dev)
+    check(got, im)
+
+
+def test_release_frees_the_plan_cache(fc, dev):
+    import torch
+    im = np.ones(128 * 128 * 64, np.float32)
+    fc.convolution3DfftCUDAInPlace(im, (128, 128, 64), np.ones(27, np.float32) / 27, (3, 3, 3), dev)
+    free_before, _ = torch.cuda.mem_get_info(dev)
+    fc.release()
+    free_after, _ = torch.cuda.mem_get_info(dev)
+    assert free_after > free_before
+    fc.convolution3DfftCUDAInPlace(im, (128, 128, 64), np.ones(27, np.float32) / 27, (3, 3, 3), dev)   # rebuilds
