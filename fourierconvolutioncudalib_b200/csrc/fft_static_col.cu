@@ -435,7 +435,12 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
             case 4: run_col<P512, 128, 2, 4>(a, mode, ngroups, st); break;
             case 5: run_col<P512, 256, 1, 4>(a, mode, ngroups, st); break;
             case 6: run_col<P512, 128, 1, 4>(a, mode, ngroups, st); break;
-            default: run_col<P512, 512, 1, 8>(a, mode, ngroups, st); break;
+            default:
+                // measured (profiles/r01_notes.md): plain passes like 512-thread CTAs (more warps), the fused
+                // pass is register-bound there and prefers 256 threads with two butterflies in flight
+                if (mode == 2) run_col<P512, 256, 2, 8>(a, mode, ngroups, st);
+                else run_col<P512, 512, 1, 8>(a, mode, ngroups, st);
+                break;
         }
     } else if (plan_matches<P256b>(a.P)) run_col<P256b, 128, 2, 8>(a, mode, ngroups, st);
     else if (plan_matches<P560>(a.P)) run_col<P560, 320, 1, 8>(a, mode, ngroups, st);
