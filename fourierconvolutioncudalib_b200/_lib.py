@@ -22,7 +22,8 @@ EXT_SYMBOLS = (
     "fcb200_spectrum_pitch", "fcb200_workspace_bytes", "fcb200_psf_active_rows",
     "fcb200_debug_rfft3", "fcb200_debug_irfft3", "fcb200_debug_psf_spectrum",
     "fcb200_slab_xy_forward", "fcb200_slab_z_fused", "fcb200_slab_yx_inverse", "fcb200_slab_psf_scratch_elems",
-    "fcb200_slab_psf",
+    "fcb200_slab_psf", "fcb200_slab_xy_forward_peer", "fcb200_slab_z_fused_peer", "fcb200_device_malloc",
+    "fcb200_device_free", "fcb200_ipc_get_handle", "fcb200_ipc_open_handle", "fcb200_ipc_close_handle",
     "fcb200_release", "fcb200_launch_count", "fcb200_profile_enable", "fcb200_profile_read",
 )
 
@@ -83,6 +84,13 @@ def load():
         "fcb200_slab_yx_inverse": (None, [vp, vp, vp, ip, i, i, i, vp]),
         "fcb200_slab_psf_scratch_elems": (ctypes.c_longlong, [ip, ip, i]),
         "fcb200_slab_psf": (None, [vp, ip, ip, i, i, vp, vp, i, vp]),
+        "fcb200_slab_xy_forward_peer": (None, [vp, vp, vp, ip, i, i, i, i, vp]),
+        "fcb200_slab_z_fused_peer": (None, [vp, vp, vp, ip, i, i, i, i, vp]),
+        "fcb200_device_malloc": (vp, [ctypes.c_longlong, i]),
+        "fcb200_device_free": (None, [vp, i]),
+        "fcb200_ipc_get_handle": (None, [vp, ctypes.c_char_p]),
+        "fcb200_ipc_open_handle": (vp, [ctypes.c_char_p, i]),
+        "fcb200_ipc_close_handle": (None, [vp, i]),
         "fcb200_release": (None, []),
         "fcb200_launch_count": (ctypes.c_longlong, []),
         "fcb200_profile_enable": (None, [i]),

@@ -456,6 +456,80 @@ void fcb200_slab_yx_inverse(const float* recv, float* zslab_spec, imageType* rea
     });
 }
 
+void fcb200_slab_xy_forward_peer(const imageType* real_slab, float* zslab_spec, void* const* peer_yslabs, const int* imDim,
+                                 int nzl, int nyl, int rank, int devCUDA, void* stream)
+{
+    guarded([&] {
+        check_dims(imDim, nullptr);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        run_slab_xy_forward(*plan, real_slab, reinterpret_cast<float2*>(zslab_spec), nullptr, nzl, nyl, (cudaStream_t)stream,
+                            reinterpret_cast<float2* const*>(peer_yslabs), rank);
+    });
+}
+
+void fcb200_slab_z_fused_peer(float* yslab_spec, const float* H_yslab, void* const* peer_recv, const int* imDim, int nzl,
+                              int nyl, int rank, int devCUDA, void* stream)
+{
+    guarded([&] {
+        check_dims(imDim, nullptr);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        run_slab_z_fused(*plan, reinterpret_cast<float2*>(yslab_spec), reinterpret_cast<const float2*>(H_yslab), nyl,
+                         (cudaStream_t)stream, reinterpret_cast<float2* const*>(peer_recv), rank, nzl);
+    });
+}
+
+void* fcb200_device_malloc(long long bytes, int devCUDA)
+{
+    return guarded([&]() -> void* {
+        DeviceGuard guard(devCUDA);
+        void* p = nullptr;
+        FC_CUDA(cudaMalloc(&p, (size_t)bytes));
+        return p;
+    });
+}
+
+void fcb200_device_free(void* p, int devCUDA)
+{
+    guarded([&] {
+        DeviceGuard guard(devCUDA);
+        FC_CUDA(cudaFree(p));
+    });
+}
+
+void fcb200_ipc_get_handle(void* dev_ptr, char* handle64)
+{
+    guarded([&] {
+        cudaIpcMemHandle_t h;
+        FC_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::memcpy(handle64, &h, 64);
+    });
+}
+
+void* fcb200_ipc_open_handle(const char* handle64, int devCUDA)
+{
+    return guarded([&]() -> void* {
+        DeviceGuard guard(devCUDA);
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, 64);
+        void* p = nullptr;
+        FC_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        return p;
+    });
+}
+
+void fcb200_ipc_close_handle(void* mapped_ptr, int devCUDA)
+{
+    guarded([&] {
+        DeviceGuard guard(devCUDA);
+        FC_CUDA(cudaIpcCloseMemHandle(mapped_ptr));
+    });
+}
+
 long long fcb200_slab_psf_scratch_elems(const int* imDim, const int* kernelDim, int devCUDA)
 {
     return guarded([&] {

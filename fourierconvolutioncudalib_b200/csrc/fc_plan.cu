@@ -371,16 +371,18 @@ static ColArgs y_args(ConvPlan& p, float2* data)
     a.splitRows = 0;
     a.splitBlock = a.splitGroup = 0;
     a.winSlot = nullptr;
+    a.splitPeers = nullptr;
+    a.splitPeerOffset = 0;
     return a;
 }
 
 static void col_pass(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
-    if (a.split) {   // split (exchange-buffer) layout: implemented by the generic kernel
+    if (launch_col_static(a, mode, ngroups, st)) return;
+    if (a.split || a.splitPeers) {   // split (exchange-buffer / peer) layout: static kernels or the generic one
         launch_col(a, mode, ngroups, st);
         return;
     }
-    if (launch_col_static(a, mode, ngroups, st)) return;
     if (a.txp == 8 && col_fast_supported(a.P)) launch_col_fast(a, mode, ngroups, st);
     else launch_col(a, mode, ngroups, st);
 }
@@ -405,6 +407,8 @@ static ColArgs z_args(ConvPlan& p, float2* data)
     a.splitRows = 0;
     a.splitBlock = a.splitGroup = 0;
     a.winSlot = nullptr;
+    a.splitPeers = nullptr;
+    a.splitPeerOffset = 0;
     return a;
 }
 
@@ -734,7 +738,7 @@ static void check_slab(const ConvPlan& p, int nzl, int nyl)
 }
 
 void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2* send, int nzl, int nyl,
-                         cudaStream_t st)
+                         cudaStream_t st, float2* const* peers, int rank)
 {
     check_slab(p, nzl, nyl);
     XArgs xa = x_args(p);
@@ -750,6 +754,11 @@ void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2
     ya.splitRows = nyl;
     ya.splitBlock = (long long)nzl * nyl * p.g.xcp;
     ya.splitGroup = (long long)nyl * p.g.xcp;
+    if (peers) {   // store straight into the peers' y-slab buffers [nz][nyl][xcp]: my planes start at rank*nzl
+        ya.split = nullptr;
+        ya.splitPeers = peers;
+        ya.splitPeerOffset = (long long)rank * nzl * nyl * p.g.xcp;
+    }
     {
         PassTimer t(kPassYFwd, st);
         col_pass(ya, 0, nzl, st);
@@ -757,7 +766,8 @@ void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2
     count_launches(2);
 }
 
-void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, cudaStream_t st)
+void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, cudaStream_t st,
+                      float2* const* peers, int rank, int nzl)
 {
     check_slab(p, 1, nyl);
     ColArgs za = z_args(p, yslab);
@@ -767,6 +777,12 @@ void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, 
     za.rowLen = (int)C;
     za.H = Hslab;
     za.scale = 1.0f / (float)((size_t)p.g.nx * (size_t)p.g.ny * (size_t)p.g.nz);
+    if (peers) {   // output plane z goes to rank z / nzl, into its receive buffer [P][nzl][nyl][xcp] at block `rank`
+        za.splitPeers = peers;
+        za.splitRows = nzl;
+        za.splitPeerOffset = (long long)rank * nzl * C;
+        za.splitGroup = 0;
+    }
     PassTimer t(kPassZFused, st);
     col_pass(za, 2, 1, st);
     count_launches(1);

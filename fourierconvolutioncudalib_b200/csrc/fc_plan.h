@@ -103,10 +103,13 @@ void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st);
 // rows of every plane.  Buffers:  real slab [nzl][ny][nx];  z-slab spectrum [nzl][ny][xcp];
 // exchange buffer [P][nzl][nyl][xcp] (P = ny / nyl blocks);  y-slab spectrum [nz][nyl][xcp].
 // x + y forward on the slab; the y pass writes the exchange (send) buffer directly
+// peers != nullptr: the y pass stores straight into the peers' y-slab buffers (NVLink), `send` is unused
 void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2* send, int nzl, int nyl,
-                         cudaStream_t st);
+                         cudaStream_t st, float2* const* peers = nullptr, int rank = 0);
 // fused z pass on the y-slab spectrum (in place) with the y-slab of the PSF spectrum
-void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, cudaStream_t st);
+// peers != nullptr: the last inverse stage stores each output plane straight into its owner's receive buffer
+void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, cudaStream_t st,
+                      float2* const* peers = nullptr, int rank = 0, int nzl = 0);
 // y + x inverse; the y pass reads the exchange (receive) buffer directly
 void run_slab_yx_inverse(ConvPlan& p, const float2* recv, float2* zslab, float* d_real, int nzl, int nyl,
                          cudaStream_t st);

@@ -42,11 +42,13 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
     const bool active = cp < npairs;
     const size_t off = (size_t)group * a.groupStride + col0 + 2 * cp;
     float2* base = a.data + off;
-    // split layout (see ColArgs): address of transform row r on the split side
-    float2* sbase = a.split ? a.split + (size_t)group * a.splitGroup + col0 + 2 * cp : nullptr;
+    // split layout (see ColArgs): address of transform row r on the split side (local buffer or peer GPUs)
+    const bool has_split = a.split != nullptr || a.splitPeers != nullptr;
+    float2* sbase = has_split ? reinterpret_cast<float2*>(1) : nullptr;   // only a flag below
     auto split_row = [&](int r) {
         const int blk = r / a.splitRows;
-        return sbase + (size_t)blk * a.splitBlock + (size_t)(r - blk * a.splitRows) * a.stride;
+        float2* b0 = a.splitPeers ? a.splitPeers[blk] + a.splitPeerOffset : a.split + (size_t)blk * a.splitBlock;
+        return b0 + (size_t)group * a.splitGroup + col0 + 2 * cp + (size_t)(r - blk * a.splitRows) * a.stride;
     };
 
     load_twiddles(tw_s, a.P.tw, L);
@@ -94,7 +96,8 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
     if (active) {
         for (int p = w; p < L; p += W) {
             const int row = (MODE == 0) ? __ldg(a.P.rev + p) : p;
-            float2* dst = (MODE == 0 && sbase) ? split_row(row) : base + (size_t)row * a.stride;
+            float2* dst = ((MODE == 0 || MODE == 2) && sbase && (MODE == 0 || a.splitPeers)) ? split_row(row)
+                                                                                            : base + (size_t)row * a.stride;
             *reinterpret_cast<float4*>(dst) = cur[p * txp + cp];
         }
     }

@@ -44,6 +44,11 @@ struct ColArgs {
     int splitRows;
     long long splitBlock;
     long long splitGroup;
+    // Peer form of the split layout (fused compute + exchange over NVLink): block b of the transform axis lives
+    // in ANOTHER GPU's buffer, splitPeers[b] (peer-mapped device pointers), at element offset splitPeerOffset.
+    // Mode 0 and mode 2 (fused z) write their output rows there; mode 1 reads from the plain split buffer.
+    float2* const* splitPeers;
+    long long splitPeerOffset;
 };
 
 bool x_pass_supported(const Geometry& g, const AxisPlanDev& P);

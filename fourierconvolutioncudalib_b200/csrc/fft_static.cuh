@@ -86,6 +86,35 @@ __device__ __forceinline__ void ssplit(const float4* v, p2* r, p2* i)
     }
 }
 
+// ---- global row addressing of the strided side ----------------------------------------------------
+// rows(r0, dr) = pointer to transform row r0 + dr (dr is a compile-time constant after unrolling).
+struct RowsLinear {
+    float2* base;
+    size_t stride;
+    __device__ __forceinline__ float2* operator()(int r0, int dr) const
+    {
+        return base + (size_t)r0 * stride + (size_t)dr * stride;
+    }
+};
+// split layout (ColArgs): block r / splitRows of the axis lives in its own buffer -- a slice of the local
+// exchange buffer, or ANOTHER GPU's buffer mapped over NVLink (the fused compute + exchange path)
+struct RowsSplit {
+    float2* const* peers;
+    float2* local;
+    long long blockStride;
+    long long offset;   // peer offset + group * splitGroup + first column
+    int splitRows;
+    float invRows;
+    size_t stride;
+    __device__ __forceinline__ float2* operator()(int r0, int dr) const
+    {
+        const int r = r0 + dr;
+        const int blk = __float2int_rz(((float)r + 0.5f) * invRows);
+        float2* b0 = peers ? peers[blk] : local + (size_t)blk * blockStride;
+        return b0 + offset + (size_t)(r - blk * splitRows) * stride;
+    }
+};
+
 // ---- first forward stage: global rows j + k*S -> smem --------------------------------------------
 // U butterflies are loaded before any arithmetic (U*R float4 in flight per thread).
 template <int R, int L, int NW, int U, bool MASKED, int TXP = 8>
@@ -128,9 +157,9 @@ __device__ __forceinline__ void sfirst_fwd(const float2* __restrict__ base, size
 }
 
 // ---- first inverse stage: global rows rev(b*R) + k*(L/R) -> smem positions b*R + k ----------------
-template <int R, int L, int NW, int U, int TXP = 8>
-__device__ __forceinline__ void sfirst_inv(const float2* __restrict__ base, size_t stride, float4* __restrict__ sm,
-                                           const int* __restrict__ rev, int cp, int w)
+template <int R, int L, int NW, int U, int TXP = 8, class ROWS>
+__device__ __forceinline__ void sfirst_inv(const ROWS& rows, float4* __restrict__ sm, const int* __restrict__ rev, int cp,
+                                           int w)
 {
     constexpr int nb = L / R, fs = L / R;
     constexpr int ITER = (nb + NW * U - 1) / (NW * U);
@@ -141,9 +170,9 @@ __device__ __forceinline__ void sfirst_inv(const float2* __restrict__ base, size
         for (int u = 0; u < U; ++u) {
             const int b = w + (it * U + u) * NW;
             if ((nb % (NW * U)) != 0 && b >= nb) continue;
-            const float2* p = base + (size_t)__ldg(rev + b * R) * stride;
+            const int r0 = __ldg(rev + b * R);
 #pragma unroll
-            for (int k = 0; k < R; ++k) v[u][k] = sld(p + (size_t)(k * fs) * stride);
+            for (int k = 0; k < R; ++k) v[u][k] = sld(rows(r0, k * fs));
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -158,9 +187,9 @@ __device__ __forceinline__ void sfirst_inv(const float2* __restrict__ base, size
 }
 
 // ---- last forward stage: smem positions b*R + k -> global rows rev(b*R) + m*(L/R) -----------------
-template <int R, int L, int NW, int TXP = 8>
-__device__ __forceinline__ void slast_fwd(float2* __restrict__ base, size_t stride, const float4* __restrict__ sm,
-                                          const int* __restrict__ rev, int cp, int w)
+template <int R, int L, int NW, int TXP = 8, class ROWS>
+__device__ __forceinline__ void slast_fwd(const ROWS& rows, const float4* __restrict__ sm, const int* __restrict__ rev,
+                                          int cp, int w)
 {
     constexpr int nb = L / R, fs = L / R;
     constexpr int ITER = (nb + NW - 1) / NW;
@@ -170,17 +199,17 @@ __device__ __forceinline__ void slast_fwd(float2* __restrict__ base, size_t stri
         if ((nb % NW) != 0 && b >= nb) break;
         p2 r[R], i[R];
         load_pairs<R>(sm, b * R * TXP + cp, TXP, r, i);
-        float2* p = base + (size_t)__ldg(rev + b * R) * stride;
+        const int r0 = __ldg(rev + b * R);
         Dft<R>::run(r, i);
 #pragma unroll
-        for (int m = 0; m < R; ++m) sst(p + (size_t)(m * fs) * stride, r[m], i[m]);
+        for (int m = 0; m < R; ++m) sst(rows(r0, m * fs), r[m], i[m]);
     }
 }
 
 // ---- last inverse stage: smem positions j + k*S -> global rows j + m*S -------------------------------
-template <int R, int L, int NW, int TXP = 8>
-__device__ __forceinline__ void slast_inv(float2* __restrict__ base, size_t stride, const float4* __restrict__ sm,
-                                          const float4* __restrict__ tw, int cp, int w)
+template <int R, int L, int NW, int TXP = 8, class ROWS>
+__device__ __forceinline__ void slast_inv(const ROWS& rows, const float4* __restrict__ sm, const float4* __restrict__ tw,
+                                          int cp, int w)
 {
     constexpr int S = L / R;
     constexpr int ITER = (S + NW - 1) / NW;
@@ -193,10 +222,29 @@ __device__ __forceinline__ void slast_inv(float2* __restrict__ base, size_t stri
 #pragma unroll
         for (int k = 1; k < R; ++k) cmulc(r[k], i[k], tw[j * k]);
         Dft<R>::run(i, r);
-        float2* p = base + (size_t)j * stride;
 #pragma unroll
-        for (int m = 0; m < R; ++m) sst(p + (size_t)(m * S) * stride, r[m], i[m]);
+        for (int m = 0; m < R; ++m) sst(rows(j, m * S), r[m], i[m]);
     }
+}
+
+// (base, stride) forms
+template <int R, int L, int NW, int U, int TXP = 8>
+__device__ __forceinline__ void sfirst_inv(const float2* __restrict__ base, size_t stride, float4* __restrict__ sm,
+                                           const int* __restrict__ rev, int cp, int w)
+{
+    sfirst_inv<R, L, NW, U, TXP>(RowsLinear{const_cast<float2*>(base), stride}, sm, rev, cp, w);
+}
+template <int R, int L, int NW, int TXP = 8>
+__device__ __forceinline__ void slast_fwd(float2* __restrict__ base, size_t stride, const float4* __restrict__ sm,
+                                          const int* __restrict__ rev, int cp, int w)
+{
+    slast_fwd<R, L, NW, TXP>(RowsLinear{base, stride}, sm, rev, cp, w);
+}
+template <int R, int L, int NW, int TXP = 8>
+__device__ __forceinline__ void slast_inv(float2* __restrict__ base, size_t stride, const float4* __restrict__ sm,
+                                          const float4* __restrict__ tw, int cp, int w)
+{
+    slast_inv<R, L, NW, TXP>(RowsLinear{base, stride}, sm, tw, cp, w);
 }
 
 // ---- fused middle: last forward stage, x H x c, first inverse stage (in registers) ---------------

@@ -9,7 +9,8 @@ namespace {
 
 
 // MODE 0 forward, 1 inverse, 2 fused forward x H x scale inverse (see fft_col_fast.cu)
-template <int MODE, class P, int THREADS, int U, bool MASKED, int TXP>
+// SPLIT: the strided side of the pass (output of modes 0 and 2, input of mode 1) uses the split / peer layout
+template <int MODE, class P, int THREADS, int U, bool MASKED, int TXP, bool SPLIT = false>
 __global__ void __launch_bounds__(THREADS) col_static_kernel(ColArgs a, int tilesPerGroup)
 {
     constexpr int L = P::L, NW = THREADS / TXP;
@@ -28,6 +29,9 @@ __global__ void __launch_bounds__(THREADS) col_static_kernel(ColArgs a, int tile
     const size_t off = (size_t)group * a.groupStride + col0 + 2 * cp;
     float2* base = a.data + off;
     const size_t stride = (size_t)a.stride;
+    const RowsSplit srows{a.splitPeers, a.split, a.splitBlock,
+                          (a.splitPeers ? a.splitPeerOffset : 0) + group * a.splitGroup + col0 + 2 * cp,
+                          a.splitRows, SPLIT ? 1.0f / (float)a.splitRows : 0.f, stride};
 
     load_twiddles(tw, a.P.tw, L);
     __syncthreads();
@@ -44,13 +48,18 @@ __global__ void __launch_bounds__(THREADS) col_static_kernel(ColArgs a, int tile
             __syncthreads();
         }
         if (MODE == 0) {
-            if (active) slast_fwd<P::RL, L, NW, TXP>(base, stride, sm, a.P.rev, cp, w);
+            if (!active) return;
+            if constexpr (SPLIT) slast_fwd<P::RL, L, NW, TXP>(srows, sm, a.P.rev, cp, w);
+            else slast_fwd<P::RL, L, NW, TXP>(base, stride, sm, a.P.rev, cp, w);
             return;
         }
         if (active) smid_fused<P::RL, L, NW, U, TXP>(a.H + off, stride, sm, a.P.rev, cp, w, a.scale);
         __syncthreads();
     } else {
-        if (active) sfirst_inv<P::RL, L, NW, U, TXP>(base, stride, sm, a.P.rev, cp, w);
+        if (active) {
+            if constexpr (SPLIT) sfirst_inv<P::RL, L, NW, U, TXP>(srows, sm, a.P.rev, cp, w);
+            else sfirst_inv<P::RL, L, NW, U, TXP>(base, stride, sm, a.P.rev, cp, w);
+        }
         __syncthreads();
     }
     if constexpr (P::ns >= 4) {
@@ -61,7 +70,9 @@ __global__ void __launch_bounds__(THREADS) col_static_kernel(ColArgs a, int tile
         if (active) sstage<P::R1, L, P::R1 * P::R2 * P::R3, NW, true, TXP>(sm, tw, cp, w);
         __syncthreads();
     }
-    if (active) slast_inv<P::R0, L, NW, TXP>(base, stride, sm, tw, cp, w);
+    if (!active) return;
+    if constexpr (SPLIT && MODE == 2) slast_inv<P::R0, L, NW, TXP>(srows, sm, tw, cp, w);
+    else slast_inv<P::R0, L, NW, TXP>(base, stride, sm, tw, cp, w);
 }
 
 
@@ -237,6 +248,14 @@ void launch(K kernel, long long grid, int threads, size_t smem, cudaStream_t st,
     FC_CUDA_KERNEL();
 }
 
+// split / peer layout variants are compiled for the power-of-two lengths only (slab mode targets those);
+// other lengths fall back to the generic kernel
+template <class P>
+constexpr bool split_capable()
+{
+    return (P::L & (P::L - 1)) == 0 && P::L >= 64;
+}
+
 // One static configuration: plan P, CTA size, load batch U, tile width TXP (column pairs per row).
 template <class P, int THREADS, int U, int TXP>
 void run_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
@@ -246,6 +265,14 @@ void run_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
     if (grid == 0) return;
     if (grid > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
     const size_t smem = (size_t)P::L * TXP * sizeof(float4) + (size_t)P::L * sizeof(float4);
+    if constexpr (split_capable<P>()) {
+        if (a.split || a.splitPeers) {
+            if (mode == 0) launch(col_static_kernel<0, P, THREADS, U, false, TXP, true>, grid, THREADS, smem, st, a, tpg);
+            else if (mode == 1) launch(col_static_kernel<1, P, THREADS, U, false, TXP, true>, grid, THREADS, smem, st, a, tpg);
+            else launch(col_static_kernel<2, P, THREADS, U, false, TXP, true>, grid, THREADS, smem, st, a, tpg);
+            return;
+        }
+    }
     if (mode == 0 && a.rowMask) launch(col_static_kernel<0, P, THREADS, U, true, TXP>, grid, THREADS, smem, st, a, tpg);
     else if (mode == 0) launch(col_static_kernel<0, P, THREADS, U, false, TXP>, grid, THREADS, smem, st, a, tpg);
     else if (mode == 1) launch(col_static_kernel<1, P, THREADS, U, false, TXP>, grid, THREADS, smem, st, a, tpg);
@@ -413,6 +440,7 @@ static int pipe_mode()
 bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
     if (!static_enabled() || a.txp != 8) return false;
+    if ((a.split || a.splitPeers) && ((a.P.L & (a.P.L - 1)) != 0 || a.P.L < 64 || a.rowMask || pipe_mode() > 0)) return false;
     // tuning knob for the longest pencils (profiles/): CTA shape / tile width of the L = 512 kernels
     static const int v512 = env_int("FCB200_V512", 0);
     if (plan_matches<P64>(a.P)) run_col<P64, 64, 1, 8>(a, mode, ngroups, st);

@@ -8,6 +8,11 @@ One process per GPU.  Rank g owns z planes [g*nz/P, (g+1)*nz/P) of the real volu
   all-to-all                 (ky slabs -> z slabs)
   y+x inverse                (fcb200_slab_yx_inverse; the y pass reads the receive buffer)
 
+`PeerSlabConvolver` is the B200-native form of the same schedule: no all-to-all at all.  The y pass and the
+last stage of the fused z pass store every output row straight into the owning rank's buffer over
+NVLink / NVSwitch peer memory (CUDA IPC mappings, fcb200_slab_xy_forward_peer / fcb200_slab_z_fused_peer), so
+the transfer overlaps the butterflies tile by tile; the phases are separated by a stream-ordered barrier only.
+
 The exchange is the only collective; it is pluggable so the same code runs with torch.distributed
 (NCCL, `DistExchange`) or with emulated ranks inside one process (`LocalExchange`, used by the
 single-GPU tests).  Result == the single-GPU convolution3DfftCUDAInPlace result up to fp32 round-off
@@ -25,7 +30,7 @@ def _ints(seq):
 
 
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t if isinstance(t, int) else t.data_ptr())
 
 
 class DistExchange:
@@ -131,3 +136,128 @@ def run_lockstep(convolvers, slabs, exchange):
     exchange.flush()
     for c, s in zip(convolvers, slabs):
         lib.fcb200_slab_yx_inverse(_p(c.buf_a), _p(c.zslab), _p(s), _ints(c.im_dim), c.nzl, c.nyl, c.dev, st)
+
+
+class _RawBuffer:
+    """cudaMalloc'ed device buffer (whole allocation => shareable through a CUDA IPC handle)"""
+
+    def __init__(self, lib, nbytes, dev):
+        self.lib, self.dev, self.nbytes = lib, dev, int(nbytes)
+        self.ptr = int(lib.fcb200_device_malloc(self.nbytes, dev))
+
+    def data_ptr(self):
+        return self.ptr
+
+    def ipc_handle(self):
+        h = ctypes.create_string_buffer(64)
+        self.lib.fcb200_ipc_get_handle(ctypes.c_void_p(self.ptr), h)
+        return h.raw
+
+    def free(self):
+        if self.ptr:
+            self.lib.fcb200_device_free(ctypes.c_void_p(self.ptr), self.dev)
+            self.ptr = 0
+
+
+class DistBarrier:
+    """stream-ordered barrier: a 1-element all-reduce on the current stream (NCCL orders it after the kernels
+    already queued on that stream and holds back the ones queued after it)"""
+
+    def __init__(self, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def __call__(self):
+        self.dist.all_reduce(self.flag, group=self.group)
+
+
+class PeerSlabConvolver(SlabConvolver):
+    """Slab convolution whose exchange is fused into the FFT kernels (peer stores over NVLink).
+
+    Buffers: `yslab` [d2][nyl][xcp] (written by every rank's y pass) and `recv` [P][nzl][nyl][xcp] (written by
+    every rank's fused z pass) are the two buffers the peers map.  Call `connect_ipc()` (one process per GPU) or
+    `connect_local()` (all ranks emulated in one process) before `convolve()`."""
+
+    def __init__(self, im_dim, kernel_dim, rank, world, dev, barrier=None, raw=True):
+        super().__init__(im_dim, kernel_dim, rank, world, dev, exchange=None)
+        torch = self.torch
+        nbytes = self.buf_a.numel() * 4
+        if raw:     # IPC needs whole cudaMalloc allocations, not slices of torch's caching allocator
+            self.buf_a = _RawBuffer(self._lib, nbytes, dev)
+            self.buf_b = _RawBuffer(self._lib, nbytes, dev)
+        self.barrier = barrier if barrier is not None else (lambda: None)
+        self.peer_yslab = self.peer_recv = None
+        self._mapped = []
+
+    def _table(self, ptrs):
+        torch = self.torch
+        return torch.tensor([int(p) for p in ptrs], dtype=torch.int64, device=self.H.device)
+
+    def connect_local(self, convolvers):
+        """all ranks live in this process (single-GPU emulation, or one process driving several GPUs with
+        peer access enabled)"""
+        self.peer_yslab = self._table([c.buf_b.data_ptr() for c in convolvers])
+        self.peer_recv = self._table([c.buf_a.data_ptr() for c in convolvers])
+
+    def connect_ipc(self, group=None):
+        """exchange CUDA IPC handles over torch.distributed and map every peer's two buffers"""
+        import torch.distributed as dist
+        mine = (self.buf_b.ipc_handle(), self.buf_a.ipc_handle())
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        ys, rv = [], []
+        for r, (hy, hr) in enumerate(handles):
+            if r == self.rank:
+                ys.append(self.buf_b.data_ptr())
+                rv.append(self.buf_a.data_ptr())
+                continue
+            py = int(self._lib.fcb200_ipc_open_handle(hy, self.dev))
+            pr = int(self._lib.fcb200_ipc_open_handle(hr, self.dev))
+            self._mapped += [py, pr]
+            ys.append(py)
+            rv.append(pr)
+        self.peer_yslab, self.peer_recv = self._table(ys), self._table(rv)
+
+    def close(self):
+        for p in self._mapped:
+            self._lib.fcb200_ipc_close_handle(ctypes.c_void_p(p), self.dev)
+        self._mapped = []
+        for b in (self.buf_a, self.buf_b):
+            if isinstance(b, _RawBuffer):
+                b.free()
+
+    # the three phases, separately callable so that emulated ranks can run them in lock-step
+    def phase_forward(self, real_slab, st):
+        self._lib.fcb200_slab_xy_forward_peer(_p(real_slab), _p(self.zslab), _p(self.peer_yslab), _ints(self.im_dim),
+                                              self.nzl, self.nyl, self.rank, self.dev, st)
+
+    def phase_z(self, st):
+        self._lib.fcb200_slab_z_fused_peer(_p(self.buf_b), _p(self.H), _p(self.peer_recv), _ints(self.im_dim), self.nzl,
+                                           self.nyl, self.rank, self.dev, st)
+
+    def phase_inverse(self, real_slab, st):
+        self._lib.fcb200_slab_yx_inverse(_p(self.buf_a), _p(self.zslab), _p(real_slab), _ints(self.im_dim), self.nzl,
+                                         self.nyl, self.dev, st)
+
+    def convolve(self, real_slab, stream=0):
+        st = ctypes.c_void_p(int(stream))
+        self.barrier()                 # every rank has finished reading the buffers of the previous call
+        self.phase_forward(real_slab, st)
+        self.barrier()                 # all y-pass rows have landed in my y slab
+        self.phase_z(st)
+        self.barrier()                 # all planes have landed in my receive buffer
+        self.phase_inverse(real_slab, st)
+
+
+def run_lockstep_peer(convolvers, slabs):
+    """Drive `world` emulated PeerSlabConvolvers through one convolution on a single GPU (same stream: the
+    phases are ordered by the stream itself)."""
+    st = ctypes.c_void_p(0)
+    for c, s in zip(convolvers, slabs):
+        c.phase_forward(s, st)
+    for c in convolvers:
+        c.phase_z(st)
+    for c, s in zip(convolvers, slabs):
+        c.phase_inverse(s, st)

@@ -75,6 +75,24 @@ FUNCTION_PREFIX void fcb200_slab_z_fused(float* yslab_spec, const float* H_yslab
                                         void* stream);
 FUNCTION_PREFIX void fcb200_slab_yx_inverse(const float* recv, float* zslab_spec, imageType* real_slab, const int* imDim,
                                            int nzl, int nyl, int devCUDA, void* stream);
+/* Fused compute + exchange over NVLink / NVSwitch peer memory (no NCCL on the data path):
+ * fcb200_slab_xy_forward_peer : like fcb200_slab_xy_forward, but the y pass stores every output row straight
+ *     into the y-slab buffer [d2][nyl][xcp] of the rank that owns it; peer_yslabs is a DEVICE array of P
+ *     pointers (entry p = rank p's y-slab buffer as mapped in this process, own entry included).
+ * fcb200_slab_z_fused_peer    : like fcb200_slab_z_fused, but the last inverse stage stores every output plane
+ *     straight into its owner's receive buffer [P][nzl][nyl][xcp] (block `rank`); peer_recv as above.
+ * The caller separates the phases with a stream-ordered barrier across ranks.
+ * fcb200_device_malloc / fcb200_ipc_*: plain cudaMalloc'ed buffers and CUDA IPC handles (64 bytes) so that
+ * one-process-per-GPU callers can map each other's exchange buffers. */
+FUNCTION_PREFIX void fcb200_slab_xy_forward_peer(const imageType* real_slab, float* zslab_spec, void* const* peer_yslabs,
+                                                const int* imDim, int nzl, int nyl, int rank, int devCUDA, void* stream);
+FUNCTION_PREFIX void fcb200_slab_z_fused_peer(float* yslab_spec, const float* H_yslab, void* const* peer_recv,
+                                             const int* imDim, int nzl, int nyl, int rank, int devCUDA, void* stream);
+FUNCTION_PREFIX void* fcb200_device_malloc(long long bytes, int devCUDA);
+FUNCTION_PREFIX void fcb200_device_free(void* p, int devCUDA);
+FUNCTION_PREFIX void fcb200_ipc_get_handle(void* dev_ptr, char* handle64);
+FUNCTION_PREFIX void* fcb200_ipc_open_handle(const char* handle64, int devCUDA);
+FUNCTION_PREFIX void fcb200_ipc_close_handle(void* mapped_ptr, int devCUDA);
 FUNCTION_PREFIX long long fcb200_slab_psf_scratch_elems(const int* imDim, const int* kernelDim, int devCUDA);
 FUNCTION_PREFIX void fcb200_slab_psf(const imageType* kernel_dev, const int* kernelDim, const int* imDim, int y0, int nyl,
                                     float* H_yslab, float* scratch, int devCUDA, void* stream);

@@ -30,7 +30,12 @@ dist.init_process_group("nccl", device_id=device)
 d0, d1, d2 = im_dim
 nzl = d2 // world
 psf = torch.from_numpy(bench.gaussian_psf(k_dim).reshape(-1)).to(device)
-conv = slab.SlabConvolver(im_dim, k_dim, rank, world, local, slab.DistExchange())
+mode = os.environ.get("SLAB_MODE", "nccl")      # nccl: all-to-all; peer: kernels store into the peers' buffers
+if mode == "peer":
+    conv = slab.PeerSlabConvolver(im_dim, k_dim, rank, world, local, barrier=slab.DistBarrier(device))
+    conv.connect_ipc()
+else:
+    conv = slab.SlabConvolver(im_dim, k_dim, rank, world, local, slab.DistExchange())
 conv.prepare_psf(psf)
 gen = torch.Generator(device=device)
 gen.manual_seed(1234 + rank)
@@ -65,9 +70,11 @@ torch.cuda.synchronize()
 ms = tiles.max_over_ranks(e0.elapsed_time(e1) / steps, device)
 if rank == 0:
     n = d0 * d1 * d2
-    out = {"dims": im_dim + k_dim, "world": world, "ms_step": round(ms, 3), "Mvox_s": round(n / ms / 1e3, 0)}
+    out = {"dims": im_dim + k_dim, "world": world, "mode": mode, "ms_step": round(ms, 3), "Mvox_s": round(n / ms / 1e3, 0)}
     if check:
         out.update({"max_rel_err_vs_single_gpu": err, "rel_l2_vs_single_gpu": l2})
     print(json.dumps(out))
 dist.barrier()
+if mode == "peer":
+    conv.close()
 dist.destroy_process_group()
