@@ -439,7 +439,12 @@ static int pipe_mode()
 
 bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
-    if (!static_enabled() || a.txp != 8) return false;
+    if (!static_enabled()) return false;
+    if (a.txp == 4 && plan_matches<P2048>(a.P) && !((a.split || a.splitPeers) && a.rowMask)) {
+        run_col<P2048, 512, 1, 4>(a, mode, ngroups, st);
+        return true;
+    }
+    if (a.txp != 8) return false;
     if ((a.split || a.splitPeers) && ((a.P.L & (a.P.L - 1)) != 0 || a.P.L < 64 || a.rowMask || pipe_mode() > 0)) return false;
     // tuning knob for the longest pencils (profiles/): CTA shape / tile width of the L = 512 kernels
     static const int v512 = env_int("FCB200_V512", 0);

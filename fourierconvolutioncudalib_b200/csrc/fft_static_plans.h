@@ -48,6 +48,7 @@ typedef SPlan<256, 16, 16> P256;
 typedef SPlan<384, 16, 8, 3> P384;
 typedef SPlan<512, 8, 8, 8> P512;
 typedef SPlan<1024, 16, 16, 4> P1024;
+typedef SPlan<2048, 16, 16, 8> P2048;   // 64-byte row segments (4 column pairs): a 128-byte tile would need 256 KB
 // planning style 1 (fused z axis): L = 256 as (8,8,4)
 typedef SPlan<256, 8, 8, 4> P256b;
 // 7-smooth extents of caller-padded volumes (BASELINE configs 2-4 padded: 270, 300, 420, 448, 560) and

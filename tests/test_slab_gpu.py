@@ -13,7 +13,8 @@ def gaussian_psf(kDim):
 
 
 @pytest.mark.parametrize("imDim,kDim,world", [((64, 64, 64), (7, 7, 7), 2), ((128, 96, 64), (9, 5, 7), 4),
-                                              ((70, 60, 48), (5, 5, 9), 2), ((256, 256, 64), (15, 15, 15), 8)])
+                                              ((70, 60, 48), (5, 5, 9), 2), ((256, 256, 64), (15, 15, 15), 8),
+                                              ((64, 2048, 64), (5, 7, 5), 2)])
 def test_emulated_ranks_match_single_gpu(fc, dev, imDim, kDim, world):
     import torch
     from fourierconvolutioncudalib_b200 import slab
@@ -40,7 +41,8 @@ def test_emulated_ranks_match_single_gpu(fc, dev, imDim, kDim, world):
 
 
 @pytest.mark.parametrize("imDim,kDim,world", [((64, 64, 64), (7, 7, 7), 2), ((128, 96, 64), (9, 5, 7), 4),
-                                              ((70, 60, 48), (5, 5, 9), 2), ((256, 256, 64), (15, 15, 15), 8)])
+                                              ((70, 60, 48), (5, 5, 9), 2), ((256, 256, 64), (15, 15, 15), 8),
+                                              ((64, 2048, 64), (5, 7, 5), 2)])
 @pytest.mark.parametrize("raw", [False, True])
 def test_peer_store_exchange_matches_alltoall(fc, dev, imDim, kDim, world, raw):
     """fused compute+exchange (kernels store into the peers' buffers through a pointer table) == the
