@@ -23,7 +23,7 @@ EXT_SYMBOLS = (
     "fcb200_debug_rfft3", "fcb200_debug_irfft3", "fcb200_debug_psf_spectrum",
     "fcb200_slab_xy_forward", "fcb200_slab_z_fused", "fcb200_slab_yx_inverse", "fcb200_slab_psf_scratch_elems",
     "fcb200_slab_psf", "fcb200_slab_xy_forward_peer", "fcb200_slab_z_fused_peer", "fcb200_device_malloc",
-    "fcb200_device_free", "fcb200_ipc_get_handle", "fcb200_ipc_open_handle", "fcb200_ipc_close_handle",
+    "fcb200_device_free", "fcb200_ipc_get_handle", "fcb200_ipc_open_handle", "fcb200_ipc_close_handle", "fcb200_convolve_batch",
     "fcb200_release", "fcb200_launch_count", "fcb200_profile_enable", "fcb200_profile_read",
 )
 
@@ -91,6 +91,7 @@ def load():
         "fcb200_ipc_get_handle": (None, [vp, ctypes.c_char_p]),
         "fcb200_ipc_open_handle": (vp, [ctypes.c_char_p, i]),
         "fcb200_ipc_close_handle": (None, [vp, i]),
+        "fcb200_convolve_batch": (None, [vp, i, ip, vp, ip, i]),
         "fcb200_release": (None, []),
         "fcb200_launch_count": (ctypes.c_longlong, []),
         "fcb200_profile_enable": (None, [i]),

@@ -75,6 +75,13 @@ def convolution3DfftCUDAInPlaceSaveMemory(im, imDim, kernel, kernelDim, devCUDA)
                                                       int(devCUDA))
 
 
+def convolve_batch(ims, imDim, kernel, kernelDim, devCUDA):
+    """extension (include/fcb200_ext.h: fcb200_convolve_batch): every array of `ims` (numpy / torch, host or
+    device, one kind) is convolved in place with the same PSF; transfers and convolutions are pipelined."""
+    ptrs = (ctypes.c_void_p * len(ims))(*[_ptr(im) for im in ims])
+    _load().fcb200_convolve_batch(ptrs, len(ims), _ints(imDim), _ptr(kernel), _ints(kernelDim), int(devCUDA))
+
+
 def convolution3DfftCUDA(im, imDim, kernel, kernelDim, devCUDA):
     """reference: src/convolution3Dfft.h:41-45 (legacy: imDim[2] fastest).  Returns a new array."""
     lib = _load()

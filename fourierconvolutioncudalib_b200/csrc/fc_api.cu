@@ -2,8 +2,11 @@
 // extensions of include/fcb200_ext.h.  Host orchestration only; all arithmetic is in fft_kernels.cu.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "convolution3Dfft.h"
@@ -68,21 +71,23 @@ struct DeviceGuard {
 // Core of the in-place convolution.
 //   nx,ny,nz : geometry of the real volume as consumed (nx fastest)
 //   pdims    : (k0,k1,k2,d0,d1,d2) handed to the PSF placement (reference fftShiftKernel arguments)
-void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const int* pdims, int dev,
-                   bool force_async, cudaStream_t user_stream, bool save_memory = false)
+bool env_flag(const char* name, bool dflt)
 {
-    DeviceGuard guard(dev);
-    for (int i = 0; i < 3; ++i)
-        if (pdims[i] > pdims[i + 3]) throw std::runtime_error("fcb200: kernel larger than image");
-    auto plan = get_plan(dev, nx, ny, nz);
-    std::lock_guard<std::mutex> lock(plan->mu);
-    ConvPlan& p = *plan;
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) != 0 : dflt;
+}
+
+// PSF taps (host or device pointer) -> PSF spectrum in plan.d_H (or the SaveMemory window buffers).
+// Host-pointer taps are remembered: when the next call brings the same bytes for the same shapes, d_H is
+// still their spectrum and the three PSF passes are skipped (FCB200_PSF_CACHE=0 turns
+// it off, bench.py does so to time the stateless path).  Returns true when the window (SaveMemory) path is set up.
+bool prepare_psf(ConvPlan& p, const float* kernel, bool k_dev, const int* pdims, bool save_memory, cudaStream_t st)
+{
+    static const bool cache_on = env_flag("FCB200_PSF_CACHE", true);
     const size_t ktaps = (size_t)pdims[0] * pdims[1] * pdims[2];
-
-    const bool im_dev = force_async || is_device_ptr(im, dev);
-    const bool k_dev = force_async || is_device_ptr(kernel, dev);
-    cudaStream_t st = force_async ? user_stream : (im_dev ? (cudaStream_t)0 : p.stream);
-
+    if (!k_dev && !save_memory && cache_on && p.h_valid && std::memcmp(p.h_dims, pdims, sizeof(int) * 6) == 0 &&
+        p.h_taps.size() == ktaps && std::memcmp(p.h_taps.data(), kernel, ktaps * sizeof(float)) == 0)
+        return false;
     const float* d_kernel = kernel;
     if (!k_dev) {
         if (ktaps > p.kernel_cap) {
@@ -96,21 +101,201 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
     }
     // SaveMemory: PSF spectrum derived on the fly inside the fused z kernel from <= 16 PSF planes (no
     // image-sized PSF buffer); falls back to the materialised spectrum when the PSF spans more planes
-    const bool window = save_memory && run_psf_window(p, d_kernel, pdims, st);
-    if (!window) run_psf_spectrum(p, d_kernel, pdims, st);
+    if (save_memory && run_psf_window(p, d_kernel, pdims, st)) return true;
+    run_psf_spectrum(p, d_kernel, pdims, st);
+    if (!k_dev && cache_on) {
+        p.h_taps.assign(kernel, kernel + ktaps);
+        std::memcpy(p.h_dims, pdims, sizeof(int) * 6);
+        p.h_valid = true;
+    }
+    return false;
+}
+
+void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const int* pdims, int dev,
+                   bool force_async, cudaStream_t user_stream, bool save_memory = false)
+{
+    DeviceGuard guard(dev);
+    for (int i = 0; i < 3; ++i)
+        if (pdims[i] > pdims[i + 3]) throw std::runtime_error("fcb200: kernel larger than image");
+    auto plan = get_plan(dev, nx, ny, nz);
+    std::lock_guard<std::mutex> lock(plan->mu);
+    ConvPlan& p = *plan;
+
+    const HostMem im_kind = force_async ? HostMem::Device : classify_pointer(im, dev);
+    const bool im_dev = im_kind == HostMem::Device;
+    const bool k_dev = force_async || is_device_ptr(kernel, dev);
+    cudaStream_t st = force_async ? user_stream : (im_dev ? (cudaStream_t)0 : p.stream);
+    // pageable buffers (what JNA hands over) go through pinned slots filled by the copy threads
+    static const bool staging_on = env_flag("FCB200_STAGING", true);
+    const bool staged = im_kind == HostMem::Pageable && staging_on;
+
+    const bool window = prepare_psf(p, kernel, k_dev, pdims, save_memory, st);
 
     float* d_im = im;
     if (!im_dev) {
         if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
-        FC_CUDA(cudaMemcpyAsync(p.d_real, im, p.real_bytes(), cudaMemcpyHostToDevice, st));
+        if (staged) p.stager.upload(p.d_real, im, p.real_bytes(), st);
+        else FC_CUDA(cudaMemcpyAsync(p.d_real, im, p.real_bytes(), cudaMemcpyHostToDevice, st));
         d_im = p.d_real;
     } else if ((reinterpret_cast<uintptr_t>(im) & 7) != 0) {
         throw std::runtime_error("fcb200: device image pointer must be 8-byte aligned");
     }
     if (window) run_convolve_window(p, d_im, st);
     else run_convolve(p, d_im, st);
-    if (!im_dev) FC_CUDA(cudaMemcpyAsync(im, p.d_real, p.real_bytes(), cudaMemcpyDeviceToHost, st));
+    if (!im_dev) {
+        if (staged) p.stager.download(im, p.d_real, p.real_bytes(), st);
+        else FC_CUDA(cudaMemcpyAsync(im, p.d_real, p.real_bytes(), cudaMemcpyDeviceToHost, st));
+    }
     if (!force_async) FC_CUDA(cudaStreamSynchronize(st));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batch of independent volumes of one shape with one PSF (BASELINE config 4: 64 blocks of 384^3).
+// The PSF spectrum is computed once; block b+1 is uploaded and block b-1 downloaded while block b is
+// convolved: three device image buffers, one copy stream per direction (PCIe is full duplex), one compute
+// stream.  Pinned / registered host buffers are DMA'd directly; pageable ones are staged chunk by chunk
+// (upload on a helper thread, download on the calling thread).
+// ------------------------------------------------------------------------------------------------
+void batch_resources(ConvPlan& p)
+{
+    if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+    p.d_ring[0] = p.d_real;
+    for (int i = 1; i < 3; ++i)
+        if (!p.d_ring[i]) FC_CUDA(cudaMalloc(&p.d_ring[i], p.real_bytes()));
+    if (!p.s_h2d) FC_CUDA(cudaStreamCreateWithFlags(&p.s_h2d, cudaStreamNonBlocking));
+    if (!p.s_d2h) FC_CUDA(cudaStreamCreateWithFlags(&p.s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) {
+        if (!p.ev_up[i]) FC_CUDA(cudaEventCreateWithFlags(&p.ev_up[i], cudaEventDisableTiming));
+        if (!p.ev_comp[i]) FC_CUDA(cudaEventCreateWithFlags(&p.ev_comp[i], cudaEventDisableTiming));
+        if (!p.ev_down[i]) FC_CUDA(cudaEventCreateWithFlags(&p.ev_down[i], cudaEventDisableTiming));
+    }
+}
+
+void batch_core(float* const* ims, int n, int nx, int ny, int nz, const float* kernel, const int* pdims, int dev,
+                bool save_memory)
+{
+    DeviceGuard guard(dev);
+    for (int i = 0; i < 3; ++i)
+        if (pdims[i] > pdims[i + 3]) throw std::runtime_error("fcb200: kernel larger than image");
+    if (n <= 0) return;
+    auto plan = get_plan(dev, nx, ny, nz);
+    std::lock_guard<std::mutex> lock(plan->mu);
+    ConvPlan& p = *plan;
+    const size_t bytes = p.real_bytes();
+    cudaStream_t st = p.stream;
+
+    bool any_pageable = false, any_device = false;
+    for (int b = 0; b < n; ++b) {
+        const HostMem k = classify_pointer(ims[b], dev);
+        any_pageable = any_pageable || k == HostMem::Pageable;
+        any_device = any_device || k == HostMem::Device;
+    }
+    const bool window = prepare_psf(p, kernel, is_device_ptr(kernel, dev), pdims, save_memory, st);
+    auto convolve = [&](float* d) {
+        if (window) run_convolve_window(p, d, st);
+        else run_convolve(p, d, st);
+    };
+    if (any_device) {   // device-resident blocks: nothing to overlap
+        for (int b = 0; b < n; ++b) {
+            if (classify_pointer(ims[b], dev) != HostMem::Device)
+                throw std::runtime_error("fcb200: a batch must be all host or all device pointers");
+            convolve(ims[b]);
+        }
+        FC_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    batch_resources(p);
+    static const bool staging_on = env_flag("FCB200_STAGING", true);
+
+    if (!any_pageable || !staging_on) {
+        // everything is enqueued up front; the three streams are ordered by events only
+        for (int b = 0; b < n; ++b) {
+            const int s = b % 3;
+            if (b >= 3) FC_CUDA(cudaStreamWaitEvent(p.s_h2d, p.ev_down[s], 0));   // buffer free again
+            FC_CUDA(cudaMemcpyAsync(p.d_ring[s], ims[b], bytes, cudaMemcpyHostToDevice, p.s_h2d));
+            FC_CUDA(cudaEventRecord(p.ev_up[s], p.s_h2d));
+            FC_CUDA(cudaStreamWaitEvent(st, p.ev_up[s], 0));
+            convolve(p.d_ring[s]);
+            FC_CUDA(cudaEventRecord(p.ev_comp[s], st));
+            FC_CUDA(cudaStreamWaitEvent(p.s_d2h, p.ev_comp[s], 0));
+            FC_CUDA(cudaMemcpyAsync(ims[b], p.d_ring[s], bytes, cudaMemcpyDeviceToHost, p.s_d2h));
+            FC_CUDA(cudaEventRecord(p.ev_down[s], p.s_d2h));
+        }
+        FC_CUDA(cudaStreamSynchronize(p.s_d2h));
+        FC_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+
+    // pageable blocks: an uploader thread stages block after block; this thread enqueues the convolutions and
+    // drains the results.  Host-side counters order the event records against the waits that use them.
+    p.stager.prepare();
+    std::mutex mu;
+    std::condition_variable cv;
+    int uploaded = 0, downloaded = 0;
+    std::string upload_error;
+    std::thread uploader([&] {
+        try {
+            FC_CUDA(cudaSetDevice(dev));
+            for (int b = 0; b < n; ++b) {
+                const int s = b % 3;
+                {
+                    std::unique_lock<std::mutex> l(mu);
+                    cv.wait(l, [&] { return downloaded >= b - 2; });   // ring slot drained
+                }
+                p.stager.upload(p.d_ring[s], ims[b], bytes, p.s_h2d);
+                FC_CUDA(cudaEventRecord(p.ev_up[s], p.s_h2d));
+                {
+                    std::lock_guard<std::mutex> l(mu);
+                    uploaded = b + 1;
+                }
+                cv.notify_all();
+            }
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> l(mu);
+            upload_error = e.what();
+            uploaded = n;
+            cv.notify_all();
+        }
+    });
+    std::string error;
+    try {
+        int next = 0;   // next block whose convolution has not been enqueued yet
+        for (int b = 0; b < n && error.empty(); ++b) {
+            for (;;) {
+                int up;
+                {
+                    std::unique_lock<std::mutex> l(mu);
+                    if (next <= b) cv.wait(l, [&] { return uploaded > next; });
+                    up = uploaded;
+                    if (!upload_error.empty()) throw std::runtime_error(upload_error);
+                }
+                if (next >= n || next >= up || next > b + 1) break;
+                const int s = next % 3;
+                FC_CUDA(cudaStreamWaitEvent(st, p.ev_up[s], 0));
+                convolve(p.d_ring[s]);
+                FC_CUDA(cudaEventRecord(p.ev_comp[s], st));
+                ++next;
+            }
+            const int s = b % 3;
+            FC_CUDA(cudaStreamWaitEvent(p.s_d2h, p.ev_comp[s], 0));
+            p.stager.download(ims[b], p.d_ring[s], bytes, p.s_d2h);
+            {
+                std::lock_guard<std::mutex> l(mu);
+                downloaded = b + 1;
+            }
+            cv.notify_all();
+        }
+    } catch (const std::exception& e) {
+        error = e.what();
+        std::lock_guard<std::mutex> l(mu);
+        downloaded = n + 3;   // release the uploader
+        cv.notify_all();
+    }
+    uploader.join();
+    cudaStreamSynchronize(p.s_h2d);
+    cudaStreamSynchronize(p.s_d2h);
+    cudaStreamSynchronize(st);
+    if (!error.empty()) throw std::runtime_error(error);
 }
 
 // host spectrum [nz][ny][xc] (what numpy.fft.rfftn returns)  <->  device layout [nz][ny][xcp]
@@ -153,6 +338,17 @@ void convolution3DfftCUDAInPlaceSaveMemory(imageType* im, int* imDim, imageType*
         check_dims(imDim, kernelDim);
         const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
         convolve_core(im, imDim[0], imDim[1], imDim[2], kernel, pdims, devCUDA, false, nullptr, true);
+    });
+}
+
+void fcb200_convolve_batch(imageType* const* ims, int n, const int* imDim, const imageType* kernel, const int* kernelDim,
+                           int devCUDA)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        if (!ims && n > 0) throw std::runtime_error("fcb200: ims is NULL");
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
+        batch_core(ims, n, imDim[0], imDim[1], imDim[2], kernel, pdims, devCUDA, false);
     });
 }
 
@@ -208,6 +404,7 @@ imageType* convolution3DfftCUDA_test(imageType* im, int* imDim, imageType* kerne
         // kernel is already image-sized and used as is (no shift), reference :253, :270
         FC_CUDA(cudaMemcpyAsync(p.d_real, kernel, n * sizeof(float), cudaMemcpyHostToDevice, st));
         ensure_full_workspace(p);
+        p.h_valid = false;
         run_forward(p, p.d_real, p.d_H, 3, st);
         FC_CUDA(cudaMemcpyAsync(p.d_real, im, n * sizeof(float), cudaMemcpyHostToDevice, st));
         run_convolve(p, p.d_real, st);

@@ -235,6 +235,14 @@ ConvPlan::~ConvPlan()
     free_axis(px);
     free_axis(py);
     free_axis(pz);
+    for (int i = 0; i < 3; ++i) {
+        if (i > 0) cudaFree(d_ring[i]);   // d_ring[0] aliases d_real
+        if (ev_up[i]) cudaEventDestroy(ev_up[i]);
+        if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
+        if (ev_down[i]) cudaEventDestroy(ev_down[i]);
+    }
+    if (s_h2d) cudaStreamDestroy(s_h2d);
+    if (s_d2h) cudaStreamDestroy(s_d2h);
     cudaFree(d_twx);
     cudaFree(d_spec);
     cudaFree(d_H);
@@ -560,6 +568,7 @@ void ensure_full_workspace(ConvPlan& p)
 
 void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
 {
+    p.h_valid = false;   // the caller re-validates the cache when it knows the taps (host-pointer calls)
     ensure_full_workspace(p);
     psf_lists(p, pdims, st);
     XArgs xa = x_args(p);

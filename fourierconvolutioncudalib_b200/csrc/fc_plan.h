@@ -1,5 +1,6 @@
 // Host-side planner and plan cache of the B200-native FFT convolution library.
 #pragma once
+#include "fc_hostpipe.h"
 #include <map>
 #include <memory>
 #include <mutex>
@@ -60,6 +61,17 @@ struct ConvPlan {
     size_t taps_cap = 0;
     unsigned char* d_plane_mask = nullptr;   // [nz] 1 = plane active
     cudaStream_t stream = nullptr;   // used for host-pointer calls
+    // host-pointer pipeline: pinned staging for pageable buffers, ring of device image buffers + copy
+    // streams for the batch entry point (ring[0] aliases d_real)
+    HostStager stager;
+    float* d_ring[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr}, ev_comp[3] = {nullptr, nullptr, nullptr},
+                ev_down[3] = {nullptr, nullptr, nullptr};
+    // PSF-spectrum cache across calls: d_H holds the spectrum of exactly these taps
+    bool h_valid = false;
+    int h_dims[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<float> h_taps;
     std::mutex mu;
     unsigned long long last_use = 0;
     size_t spec_bytes() const { return (size_t)g.nz * g.ny * g.xcp * sizeof(float2); }

@@ -45,3 +45,12 @@ def convolve_tiles(tiles, im_dim, kernel, kernel_dim, dev, stream=0):
     from . import api
     for t in tiles:
         api.convolve_device_async(t, im_dim, kernel, kernel_dim, dev, stream)
+
+
+def convolve_host_tiles(tiles, im_dim, kernel, kernel_dim, dev):
+    """Convolve this rank's HOST tiles (numpy arrays or pinned torch tensors) in place through the pipelined
+    batch entry point: one PSF spectrum, upload / convolution / download of neighbouring tiles overlap
+    (BASELINE config 4: 64 blocks of 384^3 dealt round-robin over the ranks, see assign_tiles)."""
+    from . import api
+    if tiles:
+        api.convolve_batch(tiles, im_dim, kernel, kernel_dim, dev)

@@ -75,6 +75,14 @@ FUNCTION_PREFIX void fcb200_slab_z_fused(float* yslab_spec, const float* H_yslab
                                         void* stream);
 FUNCTION_PREFIX void fcb200_slab_yx_inverse(const float* recv, float* zslab_spec, imageType* real_slab, const int* imDim,
                                            int nzl, int nyl, int devCUDA, void* stream);
+/* Batch of n independent volumes of one shape convolved in place with ONE PSF (the multi-view deconvolution /
+ * BASELINE config 4 pattern: reference callers loop over convolution3DfftCUDAInPlace, src/convolution3Dfft.h:56).
+ * ims[b]: host pointers (pinned, registered or pageable) or device pointers on devCUDA, all of one kind.
+ * The PSF spectrum is computed once; upload of block b+1, convolution of block b and download of block b-1
+ * overlap (three device buffers, one copy stream per direction).  Results are identical to n separate calls. */
+FUNCTION_PREFIX void fcb200_convolve_batch(imageType* const* ims, int n, const int* imDim, const imageType* kernel,
+                                          const int* kernelDim, int devCUDA);
+
 /* Fused compute + exchange over NVLink / NVSwitch peer memory (no NCCL on the data path):
  * fcb200_slab_xy_forward_peer : like fcb200_slab_xy_forward, but the y pass stores every output row straight
  *     into the y-slab buffer [d2][nyl][xcp] of the rank that owns it; peer_yslabs is a DEVICE array of P

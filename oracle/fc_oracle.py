@@ -28,20 +28,13 @@ sources under /root/reference) on the GPU box.
 import numpy as np
 
 
-def place_psf(kernel, kernel_dim, im_dim):
-    """Zero-padded, circularly shifted PSF exactly as the reference builds it.
-
-    kernel: flat float array of k0*k1*k2 values; kernel_dim=(k0,k1,k2); im_dim=(d0,d1,d2).
-    Returns the flat float64 array S of d0*d1*d2 values (src/convolution3Dfft.cu:139-165 with the
-    arguments of :454-461: (k0,k1,k2, d0,d1,d2) -- legacy convention, index 2 fastest -- while the
-    result is later consumed with d0 fastest, :474-486).
-    """
+def psf_tap_positions(kernel_dim, im_dim):
+    """Flat position (int64) in the padded volume of every PSF tap t = 0..K-1, exactly as the reference's
+    fftShiftKernel computes it (src/convolution3Dfft.cu:139-165 with the arguments of :454-461:
+    (k0,k1,k2, d0,d1,d2) -- legacy convention, index 2 fastest)."""
     k0, k1, k2 = (int(v) for v in kernel_dim)
     d0, d1, d2 = (int(v) for v in im_dim)
-    kernel = np.asarray(kernel).reshape(-1)
-    K = k0 * k1 * k2
-    assert kernel.size == K
-    t = np.arange(K, dtype=np.int64)
+    t = np.arange(k0 * k1 * k2, dtype=np.int64)
     c = t % k2
     aux = (t - c) // k2
     b = aux % k1
@@ -52,7 +45,20 @@ def place_psf(kernel, kernel_dim, im_dim):
     a = np.where(a < 0, a + d0, a)
     b = np.where(b < 0, b + d1, b)
     c = np.where(c < 0, c + d2, c)
-    pos = c + d2 * (b + d1 * a)
+    return c + d2 * (b + d1 * a)
+
+
+def place_psf(kernel, kernel_dim, im_dim):
+    """Zero-padded, circularly shifted PSF exactly as the reference builds it.
+
+    kernel: flat float array of k0*k1*k2 values; kernel_dim=(k0,k1,k2); im_dim=(d0,d1,d2).
+    Returns the flat float64 array S of d0*d1*d2 values; the result is later consumed with d0 fastest
+    (src/convolution3Dfft.cu:474-486) although the positions were computed with index 2 fastest.
+    """
+    d0, d1, d2 = (int(v) for v in im_dim)
+    kernel = np.asarray(kernel).reshape(-1)
+    pos = psf_tap_positions(kernel_dim, im_dim)
+    assert kernel.size == pos.size
     S = np.zeros(d0 * d1 * d2, dtype=np.float64)
     # the reference scatters with one thread per tap; positions are distinct when k_i <= d_i
     S[pos] = kernel.astype(np.float64)

@@ -127,6 +127,48 @@ def test_linearity_and_delta_at_full_config_size(fc, dev):
     check(ident, a)
 
 
+def test_config5_full_size_spot_check(fc, dev):
+    """BASELINE config 5 (2048x2048x1024 (x) 63x63x101, 2^32 voxels: the reference overflows its int sizes,
+    src/convolution3Dfft.cu:423-436) on one GPU, device resident.  No FFT oracle runs at this size, so random
+    output voxels are compared with the float64 direct sum over the PSF taps at the positions the reference's
+    placement formula gives them (oracle/fc_oracle.py: psf_tap_positions).  Tolerance 1e-4 of max|out|."""
+    import torch
+    if torch.cuda.get_device_properties(dev).total_memory < 100e9:
+        pytest.skip("needs ~70 GB of device memory")
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import fc_oracle
+    imDim, kDim = (2048, 2048, 1024), (63, 63, 101)
+    d0, d1, d2 = imDim
+    n = d0 * d1 * d2
+    device = torch.device(f"cuda:{dev}")
+    gen = torch.Generator(device=device)
+    gen.manual_seed(5)
+    src = torch.rand(n, device=device, generator=gen)
+    out = src.clone()
+    k = gaussian_psf(kDim).reshape(-1)
+    d_k = torch.from_numpy(k).to(device)
+    fc.convolve_device_async(out, imDim, d_k, kDim, dev, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    fc.release()                                    # drop the 32 GB plan workspace before the checks
+
+    pos = torch.from_numpy(fc_oracle.psf_tap_positions(kDim, imDim)).to(device)      # flat, d0 fastest
+    sx, sy, sz = pos % d0, (pos // d0) % d1, pos // (d0 * d1)
+    k64 = d_k.double()
+    rng = np.random.default_rng(55)
+    picks = [(0, 0, 0), (d2 - 1, d1 - 1, d0 - 1)] + [tuple(int(rng.integers(0, d)) for d in (d2, d1, d0)) for _ in range(30)]
+    scale = float(out.abs().max())
+    worst = 0.0
+    for z, y, x in picks:
+        idx = ((z - sz) % d2) * (d0 * d1) + ((y - sy) % d1) * d0 + ((x - sx) % d0)
+        want = float((src[idx].double() * k64).sum())
+        got = float(out[z * d0 * d1 + y * d0 + x])
+        worst = max(worst, abs(got - want))
+    assert worst <= 1e-4 * scale, (worst, scale)
+    # total mass is preserved by a unit-sum PSF (all 2^32 voxels take part)
+    assert abs(float(out.sum(dtype=torch.float64)) / float(src.sum(dtype=torch.float64)) - float(k.astype(np.float64).sum())) < 1e-5
+
+
 def test_device_queries_agree_with_reference(fc, dev, reflib):
     import ctypes
     assert fc.getNumDevicesCUDA() == reflib.getNumDevicesCUDA()
