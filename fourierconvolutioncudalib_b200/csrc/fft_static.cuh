@@ -40,7 +40,9 @@ __host__ __device__ constexpr int srev(int p)
 }
 
 // ---- shared -> shared stage ---------------------------------------------------------------------
-template <int R, int L, int Li, int NW, bool INV, int TXP = 8>
+// SWAPIN: exchange re and im of the inputs (with the same exchange on the outputs of the last stage, a
+// forward transform becomes the unnormalised inverse: IDFT(x) = swap(DFT(swap(x))))
+template <int R, int L, int Li, int NW, bool INV, int TXP = 8, bool SWAPIN = false>
 __device__ __forceinline__ void sstage(float4* __restrict__ buf, const float4* __restrict__ tw, int cp, int w)
 {
     constexpr int S = Li / R, nb = L / R, tstep = L / Li;
@@ -52,7 +54,8 @@ __device__ __forceinline__ void sstage(float4* __restrict__ buf, const float4* _
         const int beta = b / S, j = b % S;     // S is a constant: shifts / multiply-high
         const int idx0 = (beta * Li + j) * TXP + cp;
         p2 r[R], i[R];
-        load_pairs<R>(buf, idx0, S * TXP, r, i);
+        if (SWAPIN) load_pairs<R>(buf, idx0, S * TXP, i, r);
+        else load_pairs<R>(buf, idx0, S * TXP, r, i);
         if (INV) {
             if (S > 1) {
 #pragma unroll
@@ -117,7 +120,7 @@ struct RowsSplit {
 
 // ---- first forward stage: global rows j + k*S -> smem --------------------------------------------
 // U butterflies are loaded before any arithmetic (U*R float4 in flight per thread).
-template <int R, int L, int NW, int U, bool MASKED, int TXP = 8>
+template <int R, int L, int NW, int U, bool MASKED, int TXP = 8, bool SWAPIN = false>
 __device__ __forceinline__ void sfirst_fwd(const float2* __restrict__ base, size_t stride, float4* __restrict__ sm,
                                            const float4* __restrict__ tw, int cp, int w,
                                            const unsigned char* __restrict__ rowMask)
@@ -147,7 +150,8 @@ __device__ __forceinline__ void sfirst_fwd(const float2* __restrict__ base, size
             const int j = w + (it * U + u) * NW;
             if ((S % (NW * U)) != 0 && j >= S) continue;
             p2 r[R], i[R];
-            ssplit<R>(v[u], r, i);
+            if (SWAPIN) ssplit<R>(v[u], i, r);
+            else ssplit<R>(v[u], r, i);
             Dft<R>::run(r, i);
 #pragma unroll
             for (int m = 1; m < R; ++m) cmul(r[m], i[m], tw[j * m]);
@@ -187,7 +191,7 @@ __device__ __forceinline__ void sfirst_inv(const ROWS& rows, float4* __restrict_
 }
 
 // ---- last forward stage: smem positions b*R + k -> global rows rev(b*R) + m*(L/R) -----------------
-template <int R, int L, int NW, int TXP = 8, class ROWS>
+template <int R, int L, int NW, int TXP = 8, bool SWAPOUT = false, class ROWS>
 __device__ __forceinline__ void slast_fwd(const ROWS& rows, const float4* __restrict__ sm, const int* __restrict__ rev,
                                           int cp, int w)
 {
@@ -202,7 +206,10 @@ __device__ __forceinline__ void slast_fwd(const ROWS& rows, const float4* __rest
         const int r0 = __ldg(rev + b * R);
         Dft<R>::run(r, i);
 #pragma unroll
-        for (int m = 0; m < R; ++m) sst(rows(r0, m * fs), r[m], i[m]);
+        for (int m = 0; m < R; ++m) {
+            if (SWAPOUT) sst(rows(r0, m * fs), i[m], r[m]);
+            else sst(rows(r0, m * fs), r[m], i[m]);
+        }
     }
 }
 
@@ -234,11 +241,11 @@ __device__ __forceinline__ void sfirst_inv(const float2* __restrict__ base, size
 {
     sfirst_inv<R, L, NW, U, TXP>(RowsLinear{const_cast<float2*>(base), stride}, sm, rev, cp, w);
 }
-template <int R, int L, int NW, int TXP = 8>
+template <int R, int L, int NW, int TXP = 8, bool SWAPOUT = false>
 __device__ __forceinline__ void slast_fwd(float2* __restrict__ base, size_t stride, const float4* __restrict__ sm,
                                           const int* __restrict__ rev, int cp, int w)
 {
-    slast_fwd<R, L, NW, TXP>(RowsLinear{base, stride}, sm, rev, cp, w);
+    slast_fwd<R, L, NW, TXP, SWAPOUT>(RowsLinear{base, stride}, sm, rev, cp, w);
 }
 template <int R, int L, int NW, int TXP = 8>
 __device__ __forceinline__ void slast_inv(float2* __restrict__ base, size_t stride, const float4* __restrict__ sm,

@@ -36,8 +36,13 @@ __global__ void __launch_bounds__(THREADS) col_static_kernel(ColArgs a, int tile
     load_twiddles(tw, a.P.tw, L);
     __syncthreads();
 
-    if (MODE == 0 || MODE == 2) {
-        if (active) sfirst_fwd<P::R0, L, NW, U, MASKED, TXP>(base, stride, sm, tw, cp, w, a.rowMask);
+    // A plain inverse on the linear layout runs the FORWARD stage sequence with re/im exchanged on the way in
+    // and out (IDFT(x) = swap(DFT(swap(x)))): first stage straight from global, last stage straight to global,
+    // exactly the cost of the forward pass.  The mirrored decimation-in-time sequence below serves the fused
+    // pass (which continues from digit-reversed positions) and the split / peer input layout.
+    constexpr bool SWAP = (MODE == 1 && !SPLIT);
+    if (MODE == 0 || MODE == 2 || SWAP) {
+        if (active) sfirst_fwd<P::R0, L, NW, U, MASKED, TXP, SWAP>(base, stride, sm, tw, cp, w, a.rowMask);
         __syncthreads();
         if constexpr (P::ns >= 3) {
             if (active) sstage<P::R1, L, L / P::R0, NW, false, TXP>(sm, tw, cp, w);
@@ -47,10 +52,10 @@ __global__ void __launch_bounds__(THREADS) col_static_kernel(ColArgs a, int tile
             if (active) sstage<P::R2, L, L / (P::R0 * P::R1), NW, false, TXP>(sm, tw, cp, w);
             __syncthreads();
         }
-        if (MODE == 0) {
+        if (MODE == 0 || SWAP) {
             if (!active) return;
-            if constexpr (SPLIT) slast_fwd<P::RL, L, NW, TXP>(srows, sm, a.P.rev, cp, w);
-            else slast_fwd<P::RL, L, NW, TXP>(base, stride, sm, a.P.rev, cp, w);
+            if constexpr (SPLIT) slast_fwd<P::RL, L, NW, TXP, false>(srows, sm, a.P.rev, cp, w);
+            else slast_fwd<P::RL, L, NW, TXP, SWAP>(base, stride, sm, a.P.rev, cp, w);
             return;
         }
         if (active) smid_fused<P::RL, L, NW, U, TXP>(a.H + off, stride, sm, a.P.rev, cp, w, a.scale);
@@ -126,12 +131,17 @@ __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int til
     float4* tw = smem;
     float4* dbuf = tw + L;
     float4* hbuf = dbuf + (size_t)NBUF * TILE;   // MODE 2 only
+    int* pos_s = reinterpret_cast<int*>(hbuf + (MODE == 2 ? (size_t)NBUF * TILE : 0));   // [L] digit-reversal table
 
     const int t = threadIdx.x;
     const int cp = t & 7, w = t >> 3;
     const size_t stride = (size_t)a.stride;
 
     load_twiddles(tw, a.P.tw, L);
+    if (MODE == 2) {
+        for (int r = t; r < L; r += THREADS) pos_s[r] = __ldg(a.P.pos + r);
+        __syncthreads();
+    }
 
     auto decode = [&](int tile, size_t& off) -> bool {
         const int gi = tile / tilesPerGroup;
@@ -149,8 +159,8 @@ __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int til
             const float2* src = a.data + off;
 #pragma unroll 4
             for (int r = w; r < L; r += NW) {
-                const int p = (MODE == 0) ? r : __ldg(a.P.pos + r);   // inverse / H: row k sits at position pos[k]
-                const int pd = (MODE == 1) ? p : r;
+                const int p = (MODE == 2) ? pos_s[r] : r;   // H: row k is needed at position pos[k]
+                const int pd = r;
                 if (MASKED && a.rowMask[r] == 0) d[pd * 8] = make_float4(0.f, 0.f, 0.f, 0.f);
                 else cpa16(d + pd * 8, src + (size_t)r * stride);
                 if (MODE == 2) cpa16(hbuf + (size_t)slot * TILE + p * 8 + cp, a.H + off + (size_t)r * stride);
@@ -171,8 +181,9 @@ __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int til
         const bool active = decode(tile, off);
         float4* sm = dbuf + (size_t)slot * TILE;
         float2* base = a.data + off;
-        if (MODE == 0 || MODE == 2) {
-            if (active) sstage<P::R0, L, L, NW, false>(sm, tw, cp, w);
+        // MODE 1 (plain inverse) runs the FORWARD stage sequence with re/im exchanged on the way in and out
+        {
+            if (active) sstage<P::R0, L, L, NW, false, 8, MODE == 1>(sm, tw, cp, w);
             __syncthreads();
             if constexpr (P::ns >= 3) {
                 if (active) sstage<P::R1, L, L / P::R0, NW, false>(sm, tw, cp, w);
@@ -182,14 +193,11 @@ __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int til
                 if (active) sstage<P::R2, L, L / (P::R0 * P::R1), NW, false>(sm, tw, cp, w);
                 __syncthreads();
             }
-            if (MODE == 0) {
-                if (active) slast_fwd<P::RL, L, NW>(base, stride, sm, a.P.rev, cp, w);
+            if (MODE != 2) {
+                if (active) slast_fwd<P::RL, L, NW, 8, MODE == 1>(RowsLinear{base, stride}, sm, a.P.rev, cp, w);
                 continue;
             }
             if (active) smid_fused_sm<P::RL, L, NW>(hbuf + (size_t)slot * TILE, sm, cp, w, a.scale);
-            __syncthreads();
-        } else {
-            if (active) sstage<P::RL, L, P::RL, NW, true>(sm, tw, cp, w);
             __syncthreads();
         }
         if constexpr (P::ns >= 4) {
@@ -222,14 +230,17 @@ bool run_col_pipe(const ColArgs& a, int mode, long long ngroups, cudaStream_t st
     const int tpg = (a.rowLen + 15) / 16;
     const long long total = ngroups * tpg;
     if (total == 0) return true;
-    if ((size_t)P::L * sizeof(float4) + (size_t)NBUF * P::L * 8 * sizeof(float4) * (mode == 2 ? 2 : 1) > (size_t)kMaxDynSmem)
+    if ((size_t)P::L * (sizeof(float4) + sizeof(int)) + (size_t)NBUF * P::L * 8 * sizeof(float4) * (mode == 2 ? 2 : 1) >
+        (size_t)kMaxDynSmem)
         return false;
     if (total > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
     const size_t tile = (size_t)P::L * 8 * sizeof(float4);
-    const size_t smem = (size_t)P::L * sizeof(float4) + (size_t)NBUF * tile * (mode == 2 ? 2 : 1);
-    const int grid = (int)std::min<long long>(total, sm_count());
+    const size_t smem = (size_t)P::L * (sizeof(float4) + sizeof(int)) + (size_t)NBUF * tile * (mode == 2 ? 2 : 1);
     auto go = [&](auto kernel) {
         FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
+        const int grid = (int)std::min<long long>(total, (long long)sm_count() * std::max(1, per_sm));
         kernel<<<grid, THREADS, smem, st>>>(a, tpg, (int)total);
         FC_CUDA_KERNEL();
     };
@@ -436,6 +447,18 @@ static int pipe_mode()
     return v;
 }
 
+// Plain (non-fused) y / z passes of the long pencils run on the persistent multi-buffered kernel by default:
+// measured 0.117 ms against 0.127 ms per pass on C3 (profiles/r01_notes.md).  FCB200_PIPE_Y=0 turns it off.
+static bool try_pipe_plain(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
+{
+    static const int on = env_int("FCB200_PIPE_Y", 1);
+    if (!on || mode == 2 || a.split || a.splitPeers || a.rowMask || a.groupList) return false;
+    const long long total = ngroups * ((a.rowLen + 15) / 16);
+    if (total < 4LL * sm_count()) return false;   // too few tiles to fill the pipeline
+    if (plan_matches<P512>(a.P)) return run_col_pipe<P512, 512, 3>(a, mode, ngroups, st);
+    return false;
+}
+
 
 bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
@@ -445,6 +468,7 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
         return true;
     }
     if (a.txp != 8) return false;
+    if (pipe_mode() == 0 && try_pipe_plain(a, mode, ngroups, st)) return true;
     if ((a.split || a.splitPeers) && ((a.P.L & (a.P.L - 1)) != 0 || a.P.L < 64 || a.rowMask || pipe_mode() > 0)) return false;
     // tuning knob for the longest pencils (profiles/): CTA shape / tile width of the L = 512 kernels
     static const int v512 = env_int("FCB200_V512", 0);
