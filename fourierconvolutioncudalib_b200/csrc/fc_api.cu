@@ -131,6 +131,52 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
 
     const bool window = prepare_psf(p, kernel, k_dev, pdims, save_memory, st);
 
+    // Pinned host image: the volume travels in z chunks on its own copy streams; x+y forward of chunk c runs
+    // while chunk c+1 is still on the wire (and the PSF passes run under chunk 0), y+x inverse of chunk c+1
+    // runs while chunk c is already going home.  Only the fused z pass needs the whole volume.
+    static const int chunks_env = [] {
+        const char* e = std::getenv("FCB200_E2E_CHUNKS");
+        return e ? std::atoi(e) : 8;
+    }();
+    const int nch = (int)std::max<long long>(
+        1, std::min<long long>(std::min(8, chunks_env), std::min<long long>(nz, (long long)(p.real_bytes() >> 25))));
+    if (im_kind == HostMem::Pinned && nch > 1) {
+        if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+        if (!p.s_h2d) FC_CUDA(cudaStreamCreateWithFlags(&p.s_h2d, cudaStreamNonBlocking));
+        if (!p.s_d2h) FC_CUDA(cudaStreamCreateWithFlags(&p.s_d2h, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : p.ev_chunk)
+            if (!e) FC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        const size_t plane = (size_t)ny * nx;
+        const int per = (nz + nch - 1) / nch;
+        auto z0_of = [&](int c) { return std::min(nz, c * per); };
+        for (int c = 0; c < nch; ++c) {
+            const int z0 = z0_of(c), n = z0_of(c + 1) - z0;
+            if (n <= 0) continue;
+            FC_CUDA(cudaMemcpyAsync(p.d_real + z0 * plane, im + z0 * plane, n * plane * sizeof(float),
+                                    cudaMemcpyHostToDevice, p.s_h2d));
+            FC_CUDA(cudaEventRecord(p.ev_chunk[c], p.s_h2d));
+        }
+        for (int c = 0; c < nch; ++c) {
+            const int z0 = z0_of(c), n = z0_of(c + 1) - z0;
+            if (n <= 0) continue;
+            FC_CUDA(cudaStreamWaitEvent(st, p.ev_chunk[c], 0));
+            run_xy_forward_planes(p, p.d_real, z0, n, st);
+        }
+        run_z_fused(p, window, st);
+        for (int c = 0; c < nch; ++c) {
+            const int z0 = z0_of(c), n = z0_of(c + 1) - z0;
+            if (n <= 0) continue;
+            run_yx_inverse_planes(p, p.d_real, z0, n, st);
+            FC_CUDA(cudaEventRecord(p.ev_chunk[8 + c], st));
+            FC_CUDA(cudaStreamWaitEvent(p.s_d2h, p.ev_chunk[8 + c], 0));
+            FC_CUDA(cudaMemcpyAsync(im + z0 * plane, p.d_real + z0 * plane, n * plane * sizeof(float),
+                                    cudaMemcpyDeviceToHost, p.s_d2h));
+        }
+        FC_CUDA(cudaStreamSynchronize(p.s_d2h));
+        FC_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+
     float* d_im = im;
     if (!im_dev) {
         if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));

@@ -241,6 +241,8 @@ ConvPlan::~ConvPlan()
         if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
         if (ev_down[i]) cudaEventDestroy(ev_down[i]);
     }
+    for (cudaEvent_t e : ev_chunk)
+        if (e) cudaEventDestroy(e);
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_d2h) cudaStreamDestroy(s_d2h);
     cudaFree(d_twx);
@@ -653,38 +655,67 @@ bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaSt
     return true;
 }
 
-void run_convolve_window(ConvPlan& p, float* d_real, cudaStream_t st)
+// ---- the image path in three pieces; the x/y pieces work on any range of z planes so that the host-pointer
+// ---- entry can overlap them with the upload / download of the neighbouring planes
+void run_xy_forward_planes(ConvPlan& p, const float* d_real, int z0, int n, cudaStream_t st)
 {
+    const size_t rplane = (size_t)p.g.ny * p.g.nx, splane = (size_t)p.g.ny * p.g.xcp;
     XArgs xa = x_args(p);
-    xa.in_real = d_real;
-    xa.spec = p.d_spec;
+    xa.in_real = d_real + z0 * rplane;
+    xa.spec = p.d_spec + z0 * splane;
+    xa.nrows = (long long)p.g.ny * n;
     {
         PassTimer t(kPassXFwd, st);
         launch_x_fwd(xa, false, st);
     }
     {
         PassTimer t(kPassYFwd, st);
-        col_pass(y_args(p, p.d_spec), 0, p.g.nz, st);
+        col_pass(y_args(p, p.d_spec + z0 * splane), 0, n, st);
     }
+    count_launches(2);
+}
+
+void run_z_fused(ConvPlan& p, bool window, cudaStream_t st)
+{
     ColArgs za = z_args(p, p.d_spec);
-    za.H = p.d_Hwin;
-    za.winSlot = p.d_win_slot;
+    // reference: scale = 1.0f/(float)(size_img), src/convolution3Dfft.cu:531
     za.scale = 1.0f / (float)((size_t)p.g.nx * (size_t)p.g.ny * (size_t)p.g.nz);
-    {
-        PassTimer t(kPassZFused, st);
+    PassTimer t(kPassZFused, st);
+    if (window) {
+        za.H = p.d_Hwin;
+        za.winSlot = p.d_win_slot;
         if (!launch_col_otf(za, 1, p.psf_window_z0, st, false))
             throw std::runtime_error("fcb200: internal error, on-the-fly z pass unavailable");
+    } else {
+        za.H = p.d_H;
+        col_pass(za, 2, 1, st);
     }
+    count_launches(1);
+}
+
+void run_yx_inverse_planes(ConvPlan& p, float* d_real, int z0, int n, cudaStream_t st)
+{
+    const size_t rplane = (size_t)p.g.ny * p.g.nx, splane = (size_t)p.g.ny * p.g.xcp;
     {
         PassTimer t(kPassYInv, st);
-        col_pass(y_args(p, p.d_spec), 1, p.g.nz, st);
+        col_pass(y_args(p, p.d_spec + z0 * splane), 1, n, st);
     }
-    xa.out_real = d_real;
+    XArgs xa = x_args(p);
+    xa.spec = p.d_spec + z0 * splane;
+    xa.out_real = d_real + z0 * rplane;
+    xa.nrows = (long long)p.g.ny * n;
     {
         PassTimer t(kPassXInv, st);
         launch_x_inv(xa, st);
     }
-    count_launches(5);
+    count_launches(2);
+}
+
+void run_convolve_window(ConvPlan& p, float* d_real, cudaStream_t st)
+{
+    run_xy_forward_planes(p, d_real, 0, p.g.nz, st);
+    run_z_fused(p, true, st);
+    run_yx_inverse_planes(p, d_real, 0, p.g.nz, st);
 }
 
 void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st)
@@ -706,35 +737,9 @@ void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st)
 
 void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st)
 {
-    XArgs xa = x_args(p);
-    xa.in_real = d_real;
-    xa.spec = p.d_spec;
-    {
-        PassTimer t(kPassXFwd, st);
-        launch_x_fwd(xa, false, st);
-    }
-    {
-        PassTimer t(kPassYFwd, st);
-        col_pass(y_args(p, p.d_spec), 0, p.g.nz, st);
-    }
-    ColArgs za = z_args(p, p.d_spec);
-    za.H = p.d_H;
-    // reference: scale = 1.0f/(float)(size_img), src/convolution3Dfft.cu:531
-    za.scale = 1.0f / (float)((size_t)p.g.nx * (size_t)p.g.ny * (size_t)p.g.nz);
-    {
-        PassTimer t(kPassZFused, st);
-        col_pass(za, 2, 1, st);
-    }
-    {
-        PassTimer t(kPassYInv, st);
-        col_pass(y_args(p, p.d_spec), 1, p.g.nz, st);
-    }
-    xa.out_real = d_real;
-    {
-        PassTimer t(kPassXInv, st);
-        launch_x_inv(xa, st);
-    }
-    count_launches(5);
+    run_xy_forward_planes(p, d_real, 0, p.g.nz, st);
+    run_z_fused(p, false, st);
+    run_yx_inverse_planes(p, d_real, 0, p.g.nz, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -68,6 +68,7 @@ struct ConvPlan {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr}, ev_comp[3] = {nullptr, nullptr, nullptr},
                 ev_down[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_chunk[16] = {};   // single pinned call: per-chunk upload / compute events (8 + 8)
     // PSF-spectrum cache across calls: d_H holds the spectrum of exactly these taps
     bool h_valid = false;
     int h_dims[6] = {0, 0, 0, 0, 0, 0};
@@ -108,6 +109,10 @@ void ensure_full_workspace(ConvPlan& p);   // allocates the image-sized PSF spec
 void run_forward(ConvPlan& p, const float* d_real, float2* dst, int passes, cudaStream_t st);
 // Image path: d_real (device, dense) is convolved in place with the PSF spectrum in plan.d_H.
 void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st);
+// the same in three pieces (x+y forward / y+x inverse on z planes [z0, z0+n) of the volume at d_real)
+void run_xy_forward_planes(ConvPlan& p, const float* d_real, int z0, int n, cudaStream_t st);
+void run_z_fused(ConvPlan& p, bool window, cudaStream_t st);
+void run_yx_inverse_planes(ConvPlan& p, float* d_real, int z0, int n, cudaStream_t st);
 void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st);
 
 // ---- slab-decomposed single volume (multi-GPU): pass-level pieces on caller-owned device buffers ----

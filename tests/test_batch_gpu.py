@@ -103,3 +103,22 @@ def test_batch_rejects_mixed_pointer_kinds(fc, dev):
     b = torch.zeros(32 ** 3, device=f"cuda:{dev}")
     with pytest.raises(fc.api.FourierConvolutionError):
         fc.convolve_batch([a, b], imDim, k, kDim, dev)
+
+
+@pytest.mark.parametrize("imDim", [(256, 256, 261), (512, 512, 256)])
+def test_pinned_call_with_overlapped_chunks_matches_device_call(fc, dev, imDim):
+    """pinned host images >= 64 MB travel in z chunks whose x/y passes overlap the copies (fc_api.cu);
+    the numbers must not depend on the chunking (ragged last chunk included)"""
+    import torch
+    kDim = (9, 7, 11)
+    rng = np.random.default_rng(4)
+    im = (rng.random(int(np.prod(imDim)), dtype=np.float32) * 1000).astype(np.float32)
+    k = gaussian_psf(kDim).reshape(-1)
+    want = device_result(fc, dev, im, imDim, k, kDim)
+    h = torch.from_numpy(im).pin_memory()
+    fc.convolution3DfftCUDAInPlace(h, imDim, k, kDim, dev)
+    assert np.array_equal(h.numpy(), want)
+    h2 = torch.from_numpy(im).pin_memory()
+    fc.convolution3DfftCUDAInPlaceSaveMemory(h2, imDim, k, kDim, dev)
+    scale = np.abs(want).max()
+    assert np.abs(h2.numpy() - want).max() <= 1e-5 * scale
