@@ -129,7 +129,24 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
     static const bool staging_on = env_flag("FCB200_STAGING", true);
     const bool staged = im_kind == HostMem::Pageable && staging_on;
 
-    const bool window = prepare_psf(p, kernel, k_dev, pdims, save_memory, st);
+    // The PSF passes (three small, partly launch-bound kernels) run on a side stream next to the image's x/y
+    // passes and join before the fused z pass.  Off while per-pass profiling is on (events need serial passes).
+    static const bool overlap_on = env_flag("FCB200_PSF_OVERLAP", true);
+    const bool overlap = overlap_on && !profile_enabled();
+    cudaStream_t sp = st;
+    if (overlap) {
+        if (!p.s_psf) FC_CUDA(cudaStreamCreateWithFlags(&p.s_psf, cudaStreamNonBlocking));
+        if (!p.ev_psf_fork) FC_CUDA(cudaEventCreateWithFlags(&p.ev_psf_fork, cudaEventDisableTiming));
+        if (!p.ev_psf_done) FC_CUDA(cudaEventCreateWithFlags(&p.ev_psf_done, cudaEventDisableTiming));
+        sp = p.s_psf;
+        FC_CUDA(cudaEventRecord(p.ev_psf_fork, st));      // after whatever still reads the PSF buffers on st
+        FC_CUDA(cudaStreamWaitEvent(sp, p.ev_psf_fork, 0));
+    }
+    const bool window = prepare_psf(p, kernel, k_dev, pdims, save_memory, sp);
+    if (overlap) FC_CUDA(cudaEventRecord(p.ev_psf_done, sp));
+    auto join_psf = [&] {
+        if (overlap) FC_CUDA(cudaStreamWaitEvent(st, p.ev_psf_done, 0));
+    };
 
     // Pinned host image: the volume travels in z chunks on its own copy streams; x+y forward of chunk c runs
     // while chunk c+1 is still on the wire (and the PSF passes run under chunk 0), y+x inverse of chunk c+1
@@ -162,6 +179,7 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
             FC_CUDA(cudaStreamWaitEvent(st, p.ev_chunk[c], 0));
             run_xy_forward_planes(p, p.d_real, z0, n, st);
         }
+        join_psf();
         run_z_fused(p, window, st);
         for (int c = 0; c < nch; ++c) {
             const int z0 = z0_of(c), n = z0_of(c + 1) - z0;
@@ -186,8 +204,10 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
     } else if ((reinterpret_cast<uintptr_t>(im) & 7) != 0) {
         throw std::runtime_error("fcb200: device image pointer must be 8-byte aligned");
     }
-    if (window) run_convolve_window(p, d_im, st);
-    else run_convolve(p, d_im, st);
+    run_xy_forward_planes(p, d_im, 0, nz, st);
+    join_psf();
+    run_z_fused(p, window, st);
+    run_yx_inverse_planes(p, d_im, 0, nz, st);
     if (!im_dev) {
         if (staged) p.stager.download(im, p.d_real, p.real_bytes(), st);
         else FC_CUDA(cudaMemcpyAsync(im, p.d_real, p.real_bytes(), cudaMemcpyDeviceToHost, st));

@@ -152,6 +152,7 @@ static std::mutex g_prof_mu;
 static std::vector<PassEvent> g_prof_events;
 
 void profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+bool profile_enabled() { return g_profile.load() != 0; }
 
 int profile_read(float* ms_sum, long long* counts, int n)
 {
@@ -243,6 +244,9 @@ ConvPlan::~ConvPlan()
     }
     for (cudaEvent_t e : ev_chunk)
         if (e) cudaEventDestroy(e);
+    if (s_psf) cudaStreamDestroy(s_psf);
+    if (ev_psf_fork) cudaEventDestroy(ev_psf_fork);
+    if (ev_psf_done) cudaEventDestroy(ev_psf_done);
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_d2h) cudaStreamDestroy(s_d2h);
     cudaFree(d_twx);

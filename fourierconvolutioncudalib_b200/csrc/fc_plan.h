@@ -68,7 +68,10 @@ struct ConvPlan {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr}, ev_comp[3] = {nullptr, nullptr, nullptr},
                 ev_down[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_chunk[16] = {};   // single pinned call: per-chunk upload / compute events (8 + 8)
+    cudaEvent_t ev_chunk[16] = {};
+    // the PSF passes run on their own stream next to the image's x/y passes and join before the fused z pass
+    cudaStream_t s_psf = nullptr;
+    cudaEvent_t ev_psf_fork = nullptr, ev_psf_done = nullptr;   // single pinned call: per-chunk upload / compute events (8 + 8)
     // PSF-spectrum cache across calls: d_H holds the spectrum of exactly these taps
     bool h_valid = false;
     int h_dims[6] = {0, 0, 0, 0, 0, 0};
@@ -92,6 +95,7 @@ void count_launches(int n);
 enum PassId { kPassPsfClear = 0, kPassPsfX, kPassPsfY, kPassPsfZ, kPassXFwd, kPassYFwd, kPassZFused, kPassYInv,
               kPassXInv, kNumPassIds };
 void profile_enable(int on);
+bool profile_enabled();
 int profile_read(float* ms_sum, long long* counts, int n);
 
 // ---- pipeline pieces (all enqueue on `st`) -------------------------------------------------------
