@@ -32,6 +32,10 @@ def pass_of(name, grid):
         return "x_fwd"
     if "xrow_inv" in name or "xrowg_inv" in name or "x_inv_kernel" in name:
         return "x_inv"
+    if "col_pipe_kernel<0" in name:
+        return "y_fwd"
+    if "col_pipe_kernel<1" in name:
+        return "y_inv"
     if "col_static_kernel<2" in name or "col_otf" in name:
         return "z_fused"
     if "col_static_kernel<1" in name:
