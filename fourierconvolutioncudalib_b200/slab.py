@@ -45,10 +45,32 @@ class DistExchange:
         self.dist.all_to_all_single(recv, send, group=self.group)
 
 
+class CPasses:
+    """the pass-level C-ABI entry points (include/fcb200_ext.h: fcb200_slab_*) -- the product backend"""
+
+    def __init__(self):
+        self.lib = api._load()
+
+    def spectrum_pitch(self, d0):
+        return api.spectrum_pitch(d0)
+
+    def xy_forward(self, real_slab, zslab, send, im_dim, nzl, nyl, dev, st):
+        self.lib.fcb200_slab_xy_forward(_p(real_slab), _p(zslab), _p(send), _ints(im_dim), nzl, nyl, dev, st)
+
+    def z_fused(self, yslab, H, im_dim, nyl, dev, st):
+        self.lib.fcb200_slab_z_fused(_p(yslab), _p(H), _ints(im_dim), nyl, dev, st)
+
+    def yx_inverse(self, recv, zslab, real_slab, im_dim, nzl, nyl, dev, st):
+        self.lib.fcb200_slab_yx_inverse(_p(recv), _p(zslab), _p(real_slab), _ints(im_dim), nzl, nyl, dev, st)
+
+
 class SlabConvolver:
-    def __init__(self, im_dim, kernel_dim, rank, world, dev, exchange):
+    def __init__(self, im_dim, kernel_dim, rank, world, dev, exchange, passes=None, device=None):
+        """passes / device: the tests' CPU model of the pass-level entry points (tests/test_slab_gloo.py) runs the
+        same orchestration, buffers and exchange on CPU tensors; the product always uses CPasses on cuda:dev."""
         import torch
         self.torch = torch
+        self.passes = passes if passes is not None else CPasses()
         self.im_dim = tuple(int(v) for v in im_dim)
         self.k_dim = tuple(int(v) for v in kernel_dim)
         d0, d1, d2 = self.im_dim
@@ -56,16 +78,16 @@ class SlabConvolver:
             raise ValueError("slab mode needs imDim[1] and imDim[2] divisible by the number of ranks")
         self.rank, self.world, self.dev = rank, world, dev
         self.nzl, self.nyl = d2 // world, d1 // world
-        self.xcp = api.spectrum_pitch(d0)
+        self.xcp = self.passes.spectrum_pitch(d0)
         self.exchange = exchange
-        device = torch.device(f"cuda:{dev}")
+        device = torch.device(device if device is not None else f"cuda:{dev}")
         n_spec = self.nzl * d1 * self.xcp * 2            # floats of one slab-sized complex buffer
         self.zslab = torch.empty(n_spec, dtype=torch.float32, device=device)
         self.buf_a = torch.empty(n_spec, dtype=torch.float32, device=device)   # send, later receive
         self.buf_b = torch.empty(n_spec, dtype=torch.float32, device=device)   # y-slab spectrum
         self.H = torch.empty(n_spec, dtype=torch.float32, device=device)       # PSF spectrum, y slab
         self._psf_ready_for = None
-        self._lib = api._load()
+        self._lib = self.passes.lib if isinstance(self.passes, CPasses) else None
 
     def slab_of(self, volume_flat):
         """this rank's part of a full flat [d2][d1][d0] host/torch array (helper for tests/benchmarks)"""
@@ -88,14 +110,13 @@ class SlabConvolver:
 
     def convolve(self, real_slab, stream=0):
         """in-place convolution of this rank's z slab (flat torch CUDA tensor [nzl][d1][d0])"""
-        lib = self._lib
+        ps = self.passes
         st = ctypes.c_void_p(int(stream))
-        dims = _ints(self.im_dim)
-        lib.fcb200_slab_xy_forward(_p(real_slab), _p(self.zslab), _p(self.buf_a), dims, self.nzl, self.nyl, self.dev, st)
+        ps.xy_forward(real_slab, self.zslab, self.buf_a, self.im_dim, self.nzl, self.nyl, self.dev, st)
         self.exchange(self.buf_a, self.buf_b)          # buf_b = [d2][nyl][xcp]
-        lib.fcb200_slab_z_fused(_p(self.buf_b), _p(self.H), dims, self.nyl, self.dev, st)
+        ps.z_fused(self.buf_b, self.H, self.im_dim, self.nyl, self.dev, st)
         self.exchange(self.buf_b, self.buf_a)          # buf_a = [P][nzl][nyl][xcp]
-        lib.fcb200_slab_yx_inverse(_p(self.buf_a), _p(self.zslab), _p(real_slab), dims, self.nzl, self.nyl, self.dev, st)
+        ps.yx_inverse(self.buf_a, self.zslab, real_slab, self.im_dim, self.nzl, self.nyl, self.dev, st)
 
 
 class LocalExchange:
