@@ -218,7 +218,8 @@ def launch_count():
     return _load().fcb200_launch_count()
 
 
-PASS_NAMES = ("psf_clear", "psf_x", "psf_y", "psf_z", "x_fwd", "y_fwd", "z_fused", "y_inv", "x_inv")
+PASS_NAMES = ("psf_clear", "psf_x", "psf_y", "psf_z", "x_fwd", "y_fwd", "z_fused", "y_inv", "x_inv",
+              "xy_fwd", "yx_inv")
 
 
 def profile_enable(on=True):

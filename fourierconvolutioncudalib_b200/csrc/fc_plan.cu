@@ -4,6 +4,7 @@
 // (/root/reference/src/convolution3Dfft.cu:442-559).  Here a plan (twiddle / permutation tables,
 // spectrum workspace, stream) is built once per (device, shape) and cached, thread-safe.
 #include "fc_plan.h"
+#include "fft_xyfused.h"
 
 #include <algorithm>
 #include <atomic>
@@ -185,6 +186,14 @@ struct PassTimer {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
             cudaEventRecord(a, st);
+        }
+    }
+    void cancel()   // nothing was launched: drop the events
+    {
+        if (a) {
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+            a = b = nullptr;
         }
     }
     ~PassTimer()
@@ -664,6 +673,22 @@ bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaSt
 void run_xy_forward_planes(ConvPlan& p, const float* d_real, int z0, int n, cudaStream_t st)
 {
     const size_t rplane = (size_t)p.g.ny * p.g.nx, splane = (size_t)p.g.ny * p.g.xcp;
+    {   // one kernel for both passes where the cluster kernel covers the shape (fft_xyfused.cu)
+        XYArgs f{};
+        f.in_real = d_real + z0 * rplane;
+        f.spec = p.d_spec + z0 * splane;
+        f.g = p.g;
+        f.Px = p.px.dev;
+        f.Py = p.py.dev;
+        f.twx = p.d_twx;
+        f.nplanes = n;
+        PassTimer t(kPassXYFwd, st);
+        if (launch_xy_fwd_cluster(f, st)) {
+            count_launches(1);
+            return;
+        }
+        t.cancel();
+    }
     XArgs xa = x_args(p);
     xa.in_real = d_real + z0 * rplane;
     xa.spec = p.d_spec + z0 * splane;
@@ -700,6 +725,22 @@ void run_z_fused(ConvPlan& p, bool window, cudaStream_t st)
 void run_yx_inverse_planes(ConvPlan& p, float* d_real, int z0, int n, cudaStream_t st)
 {
     const size_t rplane = (size_t)p.g.ny * p.g.nx, splane = (size_t)p.g.ny * p.g.xcp;
+    {
+        XYArgs f{};
+        f.out_real = d_real + z0 * rplane;
+        f.spec = p.d_spec + z0 * splane;
+        f.g = p.g;
+        f.Px = p.px.dev;
+        f.Py = p.py.dev;
+        f.twx = p.d_twx;
+        f.nplanes = n;
+        PassTimer t(kPassYXInv, st);
+        if (launch_yx_inv_cluster(f, st)) {
+            count_launches(1);
+            return;
+        }
+        t.cancel();
+    }
     {
         PassTimer t(kPassYInv, st);
         col_pass(y_args(p, p.d_spec + z0 * splane), 1, n, st);

@@ -93,7 +93,7 @@ void count_launches(int n);
 
 // pass ids for the optional CUDA-event profile (fcb200_profile_*)
 enum PassId { kPassPsfClear = 0, kPassPsfX, kPassPsfY, kPassPsfZ, kPassXFwd, kPassYFwd, kPassZFused, kPassYInv,
-              kPassXInv, kNumPassIds };
+              kPassXInv, kPassXYFwd, kPassYXInv, kNumPassIds };
 void profile_enable(int on);
 bool profile_enabled();
 int profile_read(float* ms_sum, long long* counts, int n);
