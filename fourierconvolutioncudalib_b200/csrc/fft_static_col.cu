@@ -475,7 +475,11 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
     if (plan_matches<P64>(a.P)) run_col<P64, 64, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P128>(a.P)) run_col<P128, 64, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P256>(a.P)) run_col<P256, 128, 1, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P384>(a.P)) run_col<P384, 192, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P384>(a.P)) {
+        // fused pass: three PSF-spectrum batches in flight (384^3: 0.214 -> 0.169 ms)
+        if (mode == 2) run_col<P384, 192, 3, 8>(a, mode, ngroups, st);
+        else run_col<P384, 192, 1, 8>(a, mode, ngroups, st);
+    }
     else if (plan_matches<P512>(a.P) && pipe_mode() > 0 &&
              (pipe_mode() == 2   ? run_col_pipe<P512, 512, 2>(a, mode, ngroups, st)
               : pipe_mode() == 3 ? run_col_pipe<P512, 1024, 3>(a, mode, ngroups, st)
@@ -499,7 +503,11 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
                 else run_col<P512, 512, 1, 8>(a, mode, ngroups, st);
                 break;
         }
-    } else if (plan_matches<P256b>(a.P)) run_col<P256b, 128, 2, 8>(a, mode, ngroups, st);
+    } else if (plan_matches<P256b>(a.P)) {
+        // fused pass: all four PSF-spectrum batches of a thread in flight at once (0.1765 -> 0.1625 ms on C3)
+        if (mode == 2) run_col<P256b, 128, 4, 8>(a, mode, ngroups, st);
+        else run_col<P256b, 128, 2, 8>(a, mode, ngroups, st);
+    }
     else if (plan_matches<P560>(a.P)) run_col<P560, 320, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P448>(a.P)) run_col<P448, 512, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P420>(a.P)) run_col<P420, 384, 1, 8>(a, mode, ngroups, st);
