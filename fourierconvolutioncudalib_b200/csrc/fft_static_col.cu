@@ -268,26 +268,36 @@ constexpr bool split_capable()
 }
 
 // One static configuration: plan P, CTA size, load batch U, tile width TXP (column pairs per row).
-template <class P, int THREADS, int U, int TXP>
+// MODES: which modes this configuration is instantiated for (bit 0: forward, bit 1: inverse, bit 2: fused) --
+// a configuration used for one mode only does not compile the other kernels
+template <class P, int THREADS, int U, int TXP, int MODES = 7>
 void run_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
     const int tpg = (a.rowLen + 2 * TXP - 1) / (2 * TXP);
     const long long grid = ngroups * tpg;
     if (grid == 0) return;
     if (grid > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
+    if (!((MODES >> mode) & 1)) throw std::runtime_error("fcb200: internal error, column kernel mode not compiled");
     const size_t smem = (size_t)P::L * TXP * sizeof(float4) + (size_t)P::L * sizeof(float4);
     if constexpr (split_capable<P>()) {
         if (a.split || a.splitPeers) {
-            if (mode == 0) launch(col_static_kernel<0, P, THREADS, U, false, TXP, true>, grid, THREADS, smem, st, a, tpg);
-            else if (mode == 1) launch(col_static_kernel<1, P, THREADS, U, false, TXP, true>, grid, THREADS, smem, st, a, tpg);
-            else launch(col_static_kernel<2, P, THREADS, U, false, TXP, true>, grid, THREADS, smem, st, a, tpg);
+            if constexpr ((MODES & 1) != 0)
+                if (mode == 0) launch(col_static_kernel<0, P, THREADS, U, false, TXP, true>, grid, THREADS, smem, st, a, tpg);
+            if constexpr ((MODES & 2) != 0)
+                if (mode == 1) launch(col_static_kernel<1, P, THREADS, U, false, TXP, true>, grid, THREADS, smem, st, a, tpg);
+            if constexpr ((MODES & 4) != 0)
+                if (mode == 2) launch(col_static_kernel<2, P, THREADS, U, false, TXP, true>, grid, THREADS, smem, st, a, tpg);
             return;
         }
     }
-    if (mode == 0 && a.rowMask) launch(col_static_kernel<0, P, THREADS, U, true, TXP>, grid, THREADS, smem, st, a, tpg);
-    else if (mode == 0) launch(col_static_kernel<0, P, THREADS, U, false, TXP>, grid, THREADS, smem, st, a, tpg);
-    else if (mode == 1) launch(col_static_kernel<1, P, THREADS, U, false, TXP>, grid, THREADS, smem, st, a, tpg);
-    else launch(col_static_kernel<2, P, THREADS, U, false, TXP>, grid, THREADS, smem, st, a, tpg);
+    if constexpr ((MODES & 1) != 0) {
+        if (mode == 0 && a.rowMask) launch(col_static_kernel<0, P, THREADS, U, true, TXP>, grid, THREADS, smem, st, a, tpg);
+        else if (mode == 0) launch(col_static_kernel<0, P, THREADS, U, false, TXP>, grid, THREADS, smem, st, a, tpg);
+    }
+    if constexpr ((MODES & 2) != 0)
+        if (mode == 1) launch(col_static_kernel<1, P, THREADS, U, false, TXP>, grid, THREADS, smem, st, a, tpg);
+    if constexpr ((MODES & 4) != 0)
+        if (mode == 2) launch(col_static_kernel<2, P, THREADS, U, false, TXP>, grid, THREADS, smem, st, a, tpg);
 }
 
 
@@ -470,15 +480,13 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
     if (a.txp != 8) return false;
     if (pipe_mode() == 0 && try_pipe_plain(a, mode, ngroups, st)) return true;
     if ((a.split || a.splitPeers) && ((a.P.L & (a.P.L - 1)) != 0 || a.P.L < 64 || a.rowMask || pipe_mode() > 0)) return false;
-    // tuning knob for the longest pencils (profiles/): CTA shape / tile width of the L = 512 kernels
-    static const int v512 = env_int("FCB200_V512", 0);
     if (plan_matches<P64>(a.P)) run_col<P64, 64, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P128>(a.P)) run_col<P128, 64, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P256>(a.P)) run_col<P256, 128, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P384>(a.P)) {
         // fused pass: three PSF-spectrum batches in flight (384^3: 0.214 -> 0.169 ms)
-        if (mode == 2) run_col<P384, 192, 3, 8>(a, mode, ngroups, st);
-        else run_col<P384, 192, 1, 8>(a, mode, ngroups, st);
+        if (mode == 2) run_col<P384, 192, 3, 8, 4>(a, mode, ngroups, st);
+        else run_col<P384, 192, 1, 8, 3>(a, mode, ngroups, st);
     }
     else if (plan_matches<P512>(a.P) && pipe_mode() > 0 &&
              (pipe_mode() == 2   ? run_col_pipe<P512, 512, 2>(a, mode, ngroups, st)
@@ -489,24 +497,14 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
                 : pipe_mode() == 3 ? run_col_pipe<P256b, 512, 3>(a, mode, ngroups, st)
                                    : run_col_pipe<P256b, 256, 3>(a, mode, ngroups, st))) {
     } else if (plan_matches<P512>(a.P)) {
-        switch (v512) {
-            case 1: run_col<P512, 256, 1, 8>(a, mode, ngroups, st); break;
-            case 2: run_col<P512, 128, 2, 8>(a, mode, ngroups, st); break;
-            case 3: run_col<P512, 256, 2, 8>(a, mode, ngroups, st); break;
-            case 4: run_col<P512, 128, 2, 4>(a, mode, ngroups, st); break;
-            case 5: run_col<P512, 256, 1, 4>(a, mode, ngroups, st); break;
-            case 6: run_col<P512, 128, 1, 4>(a, mode, ngroups, st); break;
-            default:
-                // measured (profiles/r01_notes.md): plain passes like 512-thread CTAs (more warps), the fused
-                // pass is register-bound there and prefers 256 threads with two butterflies in flight
-                if (mode == 2) run_col<P512, 256, 2, 8>(a, mode, ngroups, st);
-                else run_col<P512, 512, 1, 8>(a, mode, ngroups, st);
-                break;
-        }
+        // measured (profiles/r01_notes.md, r01_sweep_col512_variants.jsonl): plain passes like 512-thread CTAs (more
+        // warps), the fused pass is register-bound there and prefers 256 threads with two butterflies in flight
+        if (mode == 2) run_col<P512, 256, 2, 8, 4>(a, mode, ngroups, st);
+        else run_col<P512, 512, 1, 8, 3>(a, mode, ngroups, st);
     } else if (plan_matches<P256b>(a.P)) {
         // fused pass: all four PSF-spectrum batches of a thread in flight at once (0.1765 -> 0.1625 ms on C3)
-        if (mode == 2) run_col<P256b, 128, 4, 8>(a, mode, ngroups, st);
-        else run_col<P256b, 128, 2, 8>(a, mode, ngroups, st);
+        if (mode == 2) run_col<P256b, 128, 4, 8, 4>(a, mode, ngroups, st);
+        else run_col<P256b, 128, 2, 8, 3>(a, mode, ngroups, st);
     }
     else if (plan_matches<P560>(a.P)) run_col<P560, 320, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P448>(a.P)) run_col<P448, 512, 1, 8>(a, mode, ngroups, st);
