@@ -43,6 +43,8 @@ std::vector<int> factorize(int L, bool* generic, int style)
         out = {8, 8, 4};
     } else if (style == 2 && L == 1024) {
         out = {16, 8, 8};   // x axis: the row-wise register kernel needs stage strides that are multiples of 8
+    } else if (style == 2 && L == 512) {
+        out = {16, 4, 8};   // x axis (nx = 1024): 32 lanes per row pair, warp-level synchronisation only
     } else {
         for (int i = 0; i < 4 && pow2_plan[e][i]; ++i) out.push_back(pow2_plan[e][i]);
     }

@@ -510,7 +510,11 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
     else if (plan_matches<P448>(a.P)) run_col<P448, 512, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P420>(a.P)) run_col<P420, 384, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P300>(a.P)) run_col<P300, 256, 1, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P1024>(a.P)) run_col<P1024, 512, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P1024>(a.P)) {
+        // plain passes: 64-byte row segments, two 256-thread CTAs per SM (1024x1024x256: 0.568 -> 0.529 ms)
+        if (mode == 2) run_col<P1024, 512, 1, 8, 4>(a, mode, ngroups, st);
+        else run_col<P1024, 256, 2, 4, 3>(a, mode, ngroups, st);
+    }
     else return false;
     return true;
 }

@@ -51,6 +51,8 @@ typedef SPlan<1024, 16, 16, 4> P1024;
 typedef SPlan<2048, 16, 16, 8> P2048;   // 64-byte row segments (4 column pairs): a 128-byte tile would need 256 KB
 // planning style 1 (fused z axis): L = 256 as (8,8,4)
 typedef SPlan<256, 8, 8, 4> P256b;
+// planning style 2 (x axis): half-length 512 of nx = 1024 rows as (16,4,8)
+typedef SPlan<512, 16, 4, 8> P512x;
 // 7-smooth extents of caller-padded volumes (BASELINE configs 2-4 padded: 270, 300, 420, 448, 560) and
 // the half-lengths of their x transforms
 typedef SPlan<560, 16, 5, 7> P560;

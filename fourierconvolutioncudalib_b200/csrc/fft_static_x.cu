@@ -102,7 +102,8 @@ static bool try_xrowg(const XArgs& a, bool inverse, cudaStream_t st)
 static bool try_xrowg_all(const XArgs& a, bool inverse, cudaStream_t st)
 {
     return try_xrowg<16, 8, 1, 64>(a, inverse, st) ||      // nx = 256
-           try_xrowg<8, 8, 8, 128>(a, inverse, st) ||      // nx = 1024
+           try_xrowg<16, 4, 8, 128>(a, inverse, st) ||     // nx = 1024 (x-axis planning style)
+           try_xrowg<8, 8, 8, 128>(a, inverse, st) ||
            try_xrowg<16, 8, 8, 128>(a, inverse, st);       // nx = 2048 (x-axis planning style)
 }
 
@@ -129,6 +130,7 @@ bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st)
            (xt256() == 128 && try_x_fwd<P256, 128>(a, psf, tiles, st)) ||
            (xt256() == 512 && try_x_fwd<P256, 512>(a, psf, tiles, st)) ||
            try_x_fwd<P256, 256>(a, psf, tiles, st) || try_x_fwd<P512, 256>(a, psf, tiles, st) ||
+           try_x_fwd<P512x, 256>(a, psf, tiles, st) ||
            try_x_fwd<P1024, 512>(a, psf, tiles, st) || try_x_fwd<P280, 256>(a, psf, tiles, st) ||
            try_x_fwd<P224, 256>(a, psf, tiles, st) || try_x_fwd<P210, 256>(a, psf, tiles, st) ||
            try_x_fwd<P150, 256>(a, psf, tiles, st) || try_x_fwd<P135, 256>(a, psf, tiles, st);
@@ -148,7 +150,7 @@ bool launch_x_inv_static(const XArgs& a, cudaStream_t st)
     return try_x_inv<P32, 64>(a, tiles, st) || try_x_inv<P64, 64>(a, tiles, st) || try_x_inv<P128, 128>(a, tiles, st) ||
            try_x_inv<P192, 192>(a, tiles, st) || (xt256() == 128 && try_x_inv<P256, 128>(a, tiles, st)) ||
            (xt256() == 512 && try_x_inv<P256, 512>(a, tiles, st)) || try_x_inv<P256, 256>(a, tiles, st) ||
-           try_x_inv<P512, 256>(a, tiles, st) || try_x_inv<P1024, 512>(a, tiles, st) ||
+           try_x_inv<P512, 256>(a, tiles, st) || try_x_inv<P512x, 256>(a, tiles, st) || try_x_inv<P1024, 512>(a, tiles, st) ||
            try_x_inv<P280, 256>(a, tiles, st) || try_x_inv<P224, 256>(a, tiles, st) || try_x_inv<P210, 256>(a, tiles, st) ||
            try_x_inv<P150, 256>(a, tiles, st) || try_x_inv<P135, 256>(a, tiles, st);
 }

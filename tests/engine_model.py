@@ -30,6 +30,8 @@ def factorize(L, style=0):
         out += [8, 8, 4]
     elif style == 2 and L == 1024:
         out += [16, 8, 8]
+    elif style == 2 and L == 512:
+        out += [16, 4, 8]
     else:
         out += _POW2_PLAN[e]
     for r in (3, 5, 7):
