@@ -25,6 +25,7 @@ EXT_SYMBOLS = (
     "fcb200_slab_psf", "fcb200_slab_xy_forward_peer", "fcb200_slab_z_fused_peer", "fcb200_device_malloc",
     "fcb200_device_free", "fcb200_ipc_get_handle", "fcb200_ipc_open_handle", "fcb200_ipc_close_handle", "fcb200_convolve_batch",
     "fcb200_release", "fcb200_launch_count", "fcb200_profile_enable", "fcb200_profile_read",
+    "fcb200_padded_extents", "fcb200_convolve_padded", "fcb200_convolve_padded_device_async",
 )
 
 
@@ -92,6 +93,9 @@ def load():
         "fcb200_ipc_open_handle": (vp, [ctypes.c_char_p, i]),
         "fcb200_ipc_close_handle": (None, [vp, i]),
         "fcb200_convolve_batch": (None, [vp, i, ip, vp, ip, i]),
+        "fcb200_padded_extents": (None, [ip, ip, i, ip]),
+        "fcb200_convolve_padded": (None, [vp, ip, vp, ip, i, i, i]),
+        "fcb200_convolve_padded_device_async": (None, [vp, ip, vp, ip, i, i, i, vp]),
         "fcb200_release": (None, []),
         "fcb200_launch_count": (ctypes.c_longlong, []),
         "fcb200_profile_enable": (None, [i]),

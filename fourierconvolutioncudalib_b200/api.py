@@ -147,6 +147,32 @@ def convolve_device_async_savememory(im_dev, imDim, kernel_dev, kernelDim, devCU
                                                         int(devCUDA), ctypes.c_void_p(int(stream)))
 
 
+PAD_ZERO, PAD_MIRROR = 0, 1            # mode
+PAD_EXACT, PAD_SMOOTH = 0, 1           # policy
+
+
+def padded_extents(imDim, kernelDim, policy=PAD_SMOOTH):
+    """extension (fcb200_padded_extents): grid the padded entry points convolve on.  policy 0 is the
+    reference's zero_padd (tests/padd_utils.h:12-24,99-108), 1 rounds up to 7-smooth sizes."""
+    out = (ctypes.c_int * 3)()
+    _load().fcb200_padded_extents(_ints(imDim), _ints(kernelDim), int(policy), out)
+    return tuple(out)
+
+
+def convolve_padded(im, imDim, kernel, kernelDim, devCUDA, mode=PAD_ZERO, policy=PAD_SMOOTH):
+    """extension (fcb200_convolve_padded): `im` is the UNPADDED volume (host or device), overwritten with the
+    cropped result of convolution3DfftCUDAInPlace on the padded grid (reference callers pad on the host:
+    tests/padd_utils.h:157-171)."""
+    _load().fcb200_convolve_padded(_ptr(im), _ints(imDim), _ptr(kernel), _ints(kernelDim), int(mode), int(policy),
+                                       int(devCUDA))
+
+
+def convolve_padded_device_async(im_dev, imDim, kernel_dev, kernelDim, devCUDA, mode=PAD_ZERO, policy=PAD_SMOOTH,
+                                 stream=0):
+    _load().fcb200_convolve_padded_device_async(_ptr(im_dev), _ints(imDim), _ptr(kernel_dev), _ints(kernelDim),
+                                                    int(mode), int(policy), int(devCUDA), ctypes.c_void_p(int(stream)))
+
+
 def plan_radices(L, style=0):
     r = (ctypes.c_int * 16)()
     g = ctypes.c_int(0)

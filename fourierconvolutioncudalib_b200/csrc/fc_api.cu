@@ -111,6 +111,29 @@ bool prepare_psf(ConvPlan& p, const float* kernel, bool k_dev, const int* pdims,
     return false;
 }
 
+// The PSF passes (three small, partly launch-bound kernels) run on a side stream next to the image's x/y
+// passes and join before the fused z pass.  Off while per-pass profiling is on (events need serial passes).
+struct PsfSide {
+    ConvPlan& p;
+    cudaStream_t st, sp;
+    bool overlap;
+    PsfSide(ConvPlan& plan, cudaStream_t main) : p(plan), st(main), sp(main)
+    {
+        static const bool overlap_on = env_flag("FCB200_PSF_OVERLAP", true);
+        overlap = overlap_on && !profile_enabled();
+        if (!overlap) return;
+        if (!p.s_psf) FC_CUDA(cudaStreamCreateWithFlags(&p.s_psf, cudaStreamNonBlocking));
+        if (!p.ev_psf_fork) FC_CUDA(cudaEventCreateWithFlags(&p.ev_psf_fork, cudaEventDisableTiming));
+        if (!p.ev_psf_done) FC_CUDA(cudaEventCreateWithFlags(&p.ev_psf_done, cudaEventDisableTiming));
+        sp = p.s_psf;
+        FC_CUDA(cudaEventRecord(p.ev_psf_fork, st));      // after whatever still reads the PSF buffers on st
+        FC_CUDA(cudaStreamWaitEvent(sp, p.ev_psf_fork, 0));
+    }
+    cudaStream_t stream() const { return sp; }
+    void done() { if (overlap) FC_CUDA(cudaEventRecord(p.ev_psf_done, sp)); }
+    void join() { if (overlap) FC_CUDA(cudaStreamWaitEvent(st, p.ev_psf_done, 0)); }
+};
+
 void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const int* pdims, int dev,
                    bool force_async, cudaStream_t user_stream, bool save_memory = false)
 {
@@ -129,24 +152,10 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
     static const bool staging_on = env_flag("FCB200_STAGING", true);
     const bool staged = im_kind == HostMem::Pageable && staging_on;
 
-    // The PSF passes (three small, partly launch-bound kernels) run on a side stream next to the image's x/y
-    // passes and join before the fused z pass.  Off while per-pass profiling is on (events need serial passes).
-    static const bool overlap_on = env_flag("FCB200_PSF_OVERLAP", true);
-    const bool overlap = overlap_on && !profile_enabled();
-    cudaStream_t sp = st;
-    if (overlap) {
-        if (!p.s_psf) FC_CUDA(cudaStreamCreateWithFlags(&p.s_psf, cudaStreamNonBlocking));
-        if (!p.ev_psf_fork) FC_CUDA(cudaEventCreateWithFlags(&p.ev_psf_fork, cudaEventDisableTiming));
-        if (!p.ev_psf_done) FC_CUDA(cudaEventCreateWithFlags(&p.ev_psf_done, cudaEventDisableTiming));
-        sp = p.s_psf;
-        FC_CUDA(cudaEventRecord(p.ev_psf_fork, st));      // after whatever still reads the PSF buffers on st
-        FC_CUDA(cudaStreamWaitEvent(sp, p.ev_psf_fork, 0));
-    }
-    const bool window = prepare_psf(p, kernel, k_dev, pdims, save_memory, sp);
-    if (overlap) FC_CUDA(cudaEventRecord(p.ev_psf_done, sp));
-    auto join_psf = [&] {
-        if (overlap) FC_CUDA(cudaStreamWaitEvent(st, p.ev_psf_done, 0));
-    };
+    PsfSide psf(p, st);
+    const bool window = prepare_psf(p, kernel, k_dev, pdims, save_memory, psf.stream());
+    psf.done();
+    auto join_psf = [&] { psf.join(); };
 
     // Pinned host image: the volume travels in z chunks on its own copy streams; x+y forward of chunk c runs
     // while chunk c+1 is still on the wire (and the PSF passes run under chunk 0), y+x inverse of chunk c+1
@@ -211,6 +220,138 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
     if (!im_dev) {
         if (staged) p.stager.download(im, p.d_real, p.real_bytes(), st);
         else FC_CUDA(cudaMemcpyAsync(im, p.d_real, p.real_bytes(), cudaMemcpyDeviceToHost, st));
+    }
+    if (!force_async) FC_CUDA(cudaStreamSynchronize(st));
+}
+
+// ------------------------------------------------------------------------------------------------
+// In-library padding (the step the reference leaves to its callers, src/convolution3Dfft.h:39,
+// :54, and that its tests do on the host: tests/padd_utils.h:99-171 + the sub-view read-back of
+// tests/test_fixtures.hpp:254-268).  The caller hands over the UNPADDED volume; it is embedded at offsets
+// kernelDim/2 in a padded grid (zeros or mirror), convolved there exactly like convolution3DfftCUDAInPlace
+// would convolve the caller-padded volume, and the interior is written back.  What the library gains from
+// knowing about the padding: only the unpadded bytes cross PCIe, zero z-halo planes are never transformed
+// forward (their spectrum planes are cleared instead), and no halo plane is transformed back.
+// ------------------------------------------------------------------------------------------------
+void padded_core(float* im, const int* imDim, const float* kernel, const int* kernelDim, int mode, int policy, int dev,
+                 bool force_async, cudaStream_t user_stream)
+{
+    if (mode != 0 && mode != 1) throw std::runtime_error("fcb200: padding mode must be 0 (zero) or 1 (mirror)");
+    if (policy != 0 && policy != 1) throw std::runtime_error("fcb200: padding policy must be 0 (exact) or 1 (7-smooth)");
+    int pd[3];
+    padded_extents(imDim, kernelDim, policy, pd);
+    const PadGeom g{imDim[0], imDim[1], imDim[2], pd[0], pd[1], pd[2],
+                    kernelDim[0] / 2, kernelDim[1] / 2, kernelDim[2] / 2, mode};
+    const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], pd[0], pd[1], pd[2]};
+    DeviceGuard guard(dev);
+    auto plan = get_plan(dev, pd[0], pd[1], pd[2]);
+    std::lock_guard<std::mutex> lock(plan->mu);
+    ConvPlan& p = *plan;
+
+    const HostMem im_kind = force_async ? HostMem::Device : classify_pointer(im, dev);
+    const bool im_dev = im_kind == HostMem::Device;
+    const bool k_dev = force_async || is_device_ptr(kernel, dev);
+    cudaStream_t st = force_async ? user_stream : (im_dev ? (cudaStream_t)0 : p.stream);
+    static const bool staging_on = env_flag("FCB200_STAGING", true);
+    const bool staged = im_kind == HostMem::Pageable && staging_on;
+
+    if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+    const size_t src_plane = (size_t)g.sy * g.sx, src_elems = src_plane * g.sz, src_bytes = src_elems * sizeof(float);
+    float* d_src = im;
+    if (!im_dev) {
+        if (src_elems > p.unpadded_cap) {
+            cudaFree(p.d_unpadded);
+            p.d_unpadded = nullptr;
+            p.unpadded_cap = 0;
+            FC_CUDA(cudaMalloc(&p.d_unpadded, src_bytes));
+            p.unpadded_cap = src_elems;
+        }
+        d_src = p.d_unpadded;
+    }
+
+    PsfSide psf(p, st);
+    prepare_psf(p, kernel, k_dev, pdims, false, psf.stream());
+    psf.done();
+
+    const size_t splane = (size_t)p.g.ny * p.g.xcp;
+    const int z_lo = g.oz, z_hi = g.oz + g.sz;          // source planes sit in padded planes [z_lo, z_hi)
+    // forward spectrum planes of the z halo: zero volume planes have a zero spectrum; mirrored ones are built
+    // from the (complete) source and transformed
+    auto halo_forward = [&] {
+        const int r0[2] = {0, z_hi}, rn[2] = {z_lo, g.pz - z_hi};
+        for (int i = 0; i < 2; ++i) {
+            if (rn[i] <= 0) continue;
+            if (mode == 0) {
+                FC_CUDA(cudaMemsetAsync(p.d_spec + r0[i] * splane, 0, rn[i] * splane * sizeof(float2), st));
+            } else {
+                run_pad_embed(d_src, p.d_real, g, r0[i], rn[i], st);
+                run_xy_forward_planes(p, p.d_real, r0[i], rn[i], st);
+            }
+        }
+    };
+
+    static const int chunks_env = [] {
+        const char* e = std::getenv("FCB200_E2E_CHUNKS");
+        return e ? std::atoi(e) : 8;
+    }();
+    const int nch = (int)std::max<long long>(
+        1, std::min<long long>(std::min(8, chunks_env), std::min<long long>(g.sz, (long long)(src_bytes >> 25))));
+    if (im_kind == HostMem::Pinned && nch > 1) {
+        // the unpadded volume travels in z chunks; embedding + x/y forward of chunk c run while chunk c+1 is on
+        // the wire, y/x inverse + crop of chunk c+1 run while chunk c goes home
+        if (!p.s_h2d) FC_CUDA(cudaStreamCreateWithFlags(&p.s_h2d, cudaStreamNonBlocking));
+        if (!p.s_d2h) FC_CUDA(cudaStreamCreateWithFlags(&p.s_d2h, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : p.ev_chunk)
+            if (!e) FC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        const int per = (g.sz + nch - 1) / nch;
+        auto z0_of = [&](int c) { return std::min(g.sz, c * per); };
+        for (int c = 0; c < nch; ++c) {
+            const int z0 = z0_of(c), n = z0_of(c + 1) - z0;
+            if (n <= 0) continue;
+            FC_CUDA(cudaMemcpyAsync(d_src + z0 * src_plane, im + z0 * src_plane, n * src_plane * sizeof(float),
+                                    cudaMemcpyHostToDevice, p.s_h2d));
+            FC_CUDA(cudaEventRecord(p.ev_chunk[c], p.s_h2d));
+        }
+        if (mode == 0) halo_forward();
+        for (int c = 0; c < nch; ++c) {
+            const int z0 = z0_of(c), n = z0_of(c + 1) - z0;
+            if (n <= 0) continue;
+            FC_CUDA(cudaStreamWaitEvent(st, p.ev_chunk[c], 0));
+            run_pad_embed(d_src, p.d_real, g, z_lo + z0, n, st);
+            run_xy_forward_planes(p, p.d_real, z_lo + z0, n, st);
+        }
+        if (mode != 0) halo_forward();
+        psf.join();
+        run_z_fused(p, false, st);
+        for (int c = 0; c < nch; ++c) {
+            const int z0 = z0_of(c), n = z0_of(c + 1) - z0;
+            if (n <= 0) continue;
+            run_yx_inverse_planes(p, p.d_real, z_lo + z0, n, st);
+            run_pad_crop(p.d_real, d_src, g, z0, n, st);
+            FC_CUDA(cudaEventRecord(p.ev_chunk[8 + c], st));
+            FC_CUDA(cudaStreamWaitEvent(p.s_d2h, p.ev_chunk[8 + c], 0));
+            FC_CUDA(cudaMemcpyAsync(im + z0 * src_plane, d_src + z0 * src_plane, n * src_plane * sizeof(float),
+                                    cudaMemcpyDeviceToHost, p.s_d2h));
+        }
+        FC_CUDA(cudaStreamSynchronize(p.s_d2h));
+        FC_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+
+    if (!im_dev) {
+        if (staged) p.stager.upload(d_src, im, src_bytes, st);
+        else FC_CUDA(cudaMemcpyAsync(d_src, im, src_bytes, cudaMemcpyHostToDevice, st));
+    }
+    run_pad_embed(d_src, p.d_real, g, z_lo, g.sz, st);
+    run_xy_forward_planes(p, p.d_real, z_lo, g.sz, st);
+    halo_forward();
+    psf.join();
+    run_z_fused(p, false, st);
+    run_yx_inverse_planes(p, p.d_real, z_lo, g.sz, st);
+    run_pad_crop(p.d_real, d_src, g, 0, g.sz, st);
+    if (!im_dev) {
+        if (staged) p.stager.download(im, d_src, src_bytes, st);
+        else FC_CUDA(cudaMemcpyAsync(im, d_src, src_bytes, cudaMemcpyDeviceToHost, st));
     }
     if (!force_async) FC_CUDA(cudaStreamSynchronize(st));
 }
@@ -415,6 +556,34 @@ void fcb200_convolve_batch(imageType* const* ims, int n, const int* imDim, const
         if (!ims && n > 0) throw std::runtime_error("fcb200: ims is NULL");
         const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
         batch_core(ims, n, imDim[0], imDim[1], imDim[2], kernel, pdims, devCUDA, false);
+    });
+}
+
+void fcb200_padded_extents(const int* imDim, const int* kernelDim, int policy, int* padDim)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        if (!padDim) throw std::runtime_error("fcb200: padDim is NULL");
+        if (policy != 0 && policy != 1) throw std::runtime_error("fcb200: padding policy must be 0 (exact) or 1 (7-smooth)");
+        padded_extents(imDim, kernelDim, policy, padDim);
+    });
+}
+
+void fcb200_convolve_padded(imageType* im, const int* imDim, const imageType* kernel, const int* kernelDim, int mode,
+                            int policy, int devCUDA)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        padded_core(im, imDim, kernel, kernelDim, mode, policy, devCUDA, false, nullptr);
+    });
+}
+
+void fcb200_convolve_padded_device_async(imageType* im_dev, const int* imDim, const imageType* kernel_dev,
+                                         const int* kernelDim, int mode, int policy, int devCUDA, void* stream)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        padded_core(im_dev, imDim, kernel_dev, kernelDim, mode, policy, devCUDA, true, (cudaStream_t)stream);
     });
 }
 

@@ -267,6 +267,7 @@ ConvPlan::~ConvPlan()
     cudaFree(d_win_slot);
     cudaFree(d_real);
     cudaFree(d_kernel);
+    cudaFree(d_unpadded);
     cudaFree(d_rows);
     cudaFree(d_planes);
     cudaFree(d_plane_mask);

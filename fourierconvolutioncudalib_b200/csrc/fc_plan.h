@@ -43,6 +43,8 @@ struct ConvPlan {
     float* d_real = nullptr;     // staging for host-pointer calls [nz][ny][nx]
     float* d_kernel = nullptr;   // PSF taps staging
     size_t kernel_cap = 0;
+    float* d_unpadded = nullptr; // padded entry points with host pointers: the caller's (unpadded) volume
+    size_t unpadded_cap = 0;     // floats
     // PSF pruning lists, cached per kernel shape / placement dims
     int psf_key[6] = {0, 0, 0, 0, 0, 0};
     int win_key[6] = {0, 0, 0, 0, 0, 0};
@@ -118,6 +120,22 @@ void run_xy_forward_planes(ConvPlan& p, const float* d_real, int z0, int n, cuda
 void run_z_fused(ConvPlan& p, bool window, cudaStream_t st);
 void run_yx_inverse_planes(ConvPlan& p, float* d_real, int z0, int n, cudaStream_t st);
 void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st);
+
+// ---- in-library padding (fc_pad.cu) ---------------------------------------------------------------
+// Source volume [sz][sy][sx] embedded at offsets (ox,oy,oz) in the padded volume [pz][py][px] (x fastest).
+// mode 0: zeros outside (reference tests/padd_utils.h:157-171); mode 1: mirror (numpy "reflect").
+struct PadGeom {
+    int sx, sy, sz;
+    int px, py, pz;
+    int ox, oy, oz;
+    int mode;
+};
+// padded planes [pz0, pz0+pn) of d_pad <- d_src (whole source volume on the device)
+void run_pad_embed(const float* d_src, float* d_pad, const PadGeom& g, int pz0, int pn, cudaStream_t st);
+// source planes [z0, z0+n) of d_dst <- interior of d_pad
+void run_pad_crop(const float* d_pad, float* d_dst, const PadGeom& g, int z0, int n, cudaStream_t st);
+// policy 0: image + 2*(kernel/2) per axis (the reference's zero_padd); 1: rounded up to a 7-smooth size
+void padded_extents(const int* imDim, const int* kernelDim, int policy, int* padDim);
 
 // ---- slab-decomposed single volume (multi-GPU): pass-level pieces on caller-owned device buffers ----
 // A rank owns nzl consecutive z planes of the real volume and, after the exchange, nyl consecutive ky

@@ -18,6 +18,25 @@ FUNCTION_PREFIX void fcb200_convolve_device_async_savememory(imageType* im_dev, 
                                                             const imageType* kernel_dev, const int* kernelDim,
                                                             int devCUDA, void* stream);
 
+/* In-library padding -- the step the reference leaves to its callers (TODO at src/convolution3Dfft.h:39, :54;
+ * done on the host by its tests: zero_padd::insert_at_offsets, tests/padd_utils.h:99-171, result read back through
+ * the same sub-view, tests/test_fixtures.hpp:254-268).
+ * `im` is the UNPADDED volume (imDim[0] fastest; host or device pointer), overwritten with the cropped result.
+ * It is embedded at offsets kernelDim[i]/2 in a grid of fcb200_padded_extents() voxels and convolved there exactly
+ * as convolution3DfftCUDAInPlace would convolve the caller-padded volume (same PSF placement on the padded grid).
+ *   mode   0: zeros outside (the reference's zero_padd)      1: mirror, numpy.pad(mode="reflect")
+ *   policy 0: padDim[i] = imDim[i] + 2*(kernelDim[i]/2) (tests/padd_utils.h:12-24)
+ *          1: that, rounded up to the next 7-smooth size (fastest extent even): every FFT stage is radix 2..16/3/5/7
+ * Only the unpadded bytes cross PCIe; zero halo planes are not transformed forward and no halo plane is
+ * transformed back. */
+FUNCTION_PREFIX void fcb200_padded_extents(const int* imDim, const int* kernelDim, int policy, int* padDim);
+FUNCTION_PREFIX void fcb200_convolve_padded(imageType* im, const int* imDim, const imageType* kernel, const int* kernelDim,
+                                           int mode, int policy, int devCUDA);
+/* device pointers, stream-ordered, no host synchronisation */
+FUNCTION_PREFIX void fcb200_convolve_padded_device_async(imageType* im_dev, const int* imDim, const imageType* kernel_dev,
+                                                        const int* kernelDim, int mode, int policy, int devCUDA,
+                                                        void* stream);
+
 /* Planner introspection (pure host code; callable without a GPU).
  * fcb200_plan_radices: writes the stage radices of a length-L transform (at most 16), returns the
  * number of stages; *generic is 1 when a radix outside {2,3,4,5,7,8} is needed. */

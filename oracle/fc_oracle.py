@@ -120,6 +120,57 @@ def crop(padded, off, shape):
     return padded[off[0]:off[0] + shape[0], off[1]:off[1] + shape[1], off[2]:off[2] + shape[2]]
 
 
+def smooth_extent(e, even=False):
+    """smallest 7-smooth integer >= e (even if asked): the padding policy 1 of the padded entry points"""
+    def smooth(v):
+        for f in (2, 3, 5, 7):
+            while v % f == 0:
+                v //= f
+        return v == 1
+    e = int(e)
+    while not smooth(e) or (even and e % 2):
+        e += 1
+    return e
+
+
+def padded_extents(im_dim, kernel_dim, policy):
+    """policy 0: zero_padd_extents (tests/padd_utils.h:12-24,99-108); 1: rounded up to 7-smooth, im_dim[0] even."""
+    ext = zero_padd_extents(im_dim, kernel_dim)
+    if policy == 1:
+        ext = tuple(smooth_extent(e, even=(i == 0)) for i, e in enumerate(ext))
+    return ext
+
+
+def convolve_padded_ref(im, im_dim, kernel, kernel_dim, mode=0, policy=0):
+    """What a reference caller does around convolution3DfftCUDAInPlace (tests/test_fixtures.hpp:254-268 with
+    tests/padd_utils.h:157-171): embed the volume at offsets kernel/2 in the padded grid (zeros, or
+    numpy "reflect" mirroring for mode 1), convolve on that grid, read the interior back.  Flat float64 result."""
+    d0, d1, d2 = (int(v) for v in im_dim)
+    p0, p1, p2 = padded_extents(im_dim, kernel_dim, policy)
+    o0, o1, o2 = zero_padd_offsets(kernel_dim)
+    I3 = np.asarray(im, dtype=np.float64).reshape(d2, d1, d0)
+    widths = ((o2, p2 - d2 - o2), (o1, p1 - d1 - o1), (o0, p0 - d0 - o0))
+    if mode == 0:
+        P3 = np.pad(I3, widths, mode="constant")
+    else:
+        # numpy's reflect folds repeatedly when the halo is wider than the axis, like the library's index fold
+        P3 = np.pad(I3, widths, mode="reflect") if min(I3.shape) > 1 else _reflect_pad_degenerate(I3, widths)
+    out = convolve_inplace_ref(P3.reshape(-1), (p0, p1, p2), kernel, kernel_dim).reshape(p2, p1, p0)
+    return crop(out, (o2, o1, o0), (d2, d1, d0)).reshape(-1)
+
+
+def _reflect_pad_degenerate(a, widths):
+    """reflect padding where an axis has a single sample (numpy refuses): that axis is replicated"""
+    for ax, (lo, hi) in enumerate(widths):
+        if a.shape[ax] == 1:
+            a = np.repeat(a, lo + hi + 1, axis=ax)
+        else:
+            w = [(0, 0)] * a.ndim
+            w[ax] = (lo, hi)
+            a = np.pad(a, w, mode="reflect")
+    return a
+
+
 def l2norm(reference, data):
     """tests/test_utils.hpp:75-88: sqrt(sum (a-b)^2) / N  (N, not sqrt(N))."""
     a = np.asarray(reference, dtype=np.float32).reshape(-1).astype(np.float64)

@@ -97,3 +97,39 @@ def test_center_tap_lands_on_origin():
         k[kd[0] // 2, kd[1] // 2, kd[2] // 2] = 1
         S = fo.place_psf(k.reshape(-1), kd, d)
         assert S[0] == 1 and S.sum() == 1
+
+
+# ---- padded entry point's oracle (fo.convolve_padded_ref): what a reference caller does around the ABI -------
+def test_padded_extents_follow_zero_padd_and_the_smooth_policy(fc):
+    # caller-padded flavours of the BASELINE configs
+    want = {((64, 64, 64), (3, 3, 3)): (70, 70, 70), ((256, 256, 256), (15, 15, 15)): (270, 270, 270),
+            ((512, 512, 256), (31, 31, 41)): (560, 560, 300), ((384, 384, 384), (25, 25, 61)): (420, 420, 448),
+            ((2048, 2048, 1024), (63, 63, 101)): (2160, 2160, 1125)}
+    for (im, k), smooth in want.items():
+        assert fo.padded_extents(im, k, 0) == fo.zero_padd_extents(im, k)
+        assert fo.padded_extents(im, k, 1) == smooth
+        for policy in (0, 1):                      # the library's planner agrees (pure host code, no GPU needed)
+            assert fc.padded_extents(im, k, policy) == fo.padded_extents(im, k, policy)
+    assert fo.padded_extents((17, 5, 9), (4, 3, 5), 1) == (24, 7, 14)     # fastest extent kept even
+
+
+def test_padded_oracle_zero_mode_is_the_reference_test_sequence():
+    """zero_padd + convolve + sub-view (tests/test_fixtures.hpp:254-268) == CPU convolve on the padded stack"""
+    rng = np.random.default_rng(2)
+    im3 = rng.random((10, 10, 10), dtype=np.float32)
+    k3 = rng.random((3, 3, 3), dtype=np.float32)
+    padded, off = fo.zero_padd(im3, k3.shape)
+    want = fo.crop(fo.direct_convolve(padded, k3, off), off, im3.shape).reshape(-1)
+    for policy in (0, 1):
+        got = fo.convolve_padded_ref(im3.reshape(-1), (10, 10, 10), k3.reshape(-1), (3, 3, 3), 0, policy)
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_padded_oracle_mirror_mode_keeps_a_constant_image_constant():
+    k = np.random.default_rng(4).random(5 * 3 * 7)
+    k /= k.sum()
+    im = np.full(12 * 9 * 8, 42.0)
+    got = fo.convolve_padded_ref(im, (12, 9, 8), k, (5, 3, 7), 1, 1)
+    assert np.allclose(got, 42.0, rtol=1e-12)
+    # zero mode darkens the border instead
+    assert fo.convolve_padded_ref(im, (12, 9, 8), k, (5, 3, 7), 0, 1).min() < 41.0
