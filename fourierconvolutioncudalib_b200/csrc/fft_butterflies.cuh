@@ -237,6 +237,69 @@ struct Dft<16> {
     }
 };
 
+// Radix 24 = 8 x 3 (x rows of 384 voxels: M = 192 = 24 * 8), internal twiddles w24^(b*c) as constants.
+//   n = 3a + b, k = c + 8d:  X[c + 8d] = sum_b w3^(b d) [ w24^(b c) sum_a x[3a + b] w8^(a c) ]
+template <>
+struct Dft<24> {
+    static __device__ __forceinline__ void run(p2* r, p2* i)
+    {
+        const float C1 = 0.96592582628906828675f;  // cos(pi/12)
+        const float S1 = 0.25881904510252076235f;  // sin(pi/12)
+        const float C2 = 0.86602540378443864676f;  // cos(pi/6)
+        const float C3 = 0.70710678118654752440f;  // cos(pi/4)
+        p2 tr[24], ti[24];   // t_b[c] at index 3c + b
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            p2 ar[8], ai[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                ar[a] = r[3 * a + b];
+                ai[a] = i[3 * a + b];
+            }
+            Dft<8>::run(ar, ai);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                tr[3 * c + b] = ar[c];
+                ti[3 * c + b] = ai[c];
+            }
+        }
+        // b = 1: w24^c, c = 1..7
+        Dft<16>::rot(tr[3 * 1 + 1], ti[3 * 1 + 1], C1, S1);        // w24^1
+        Dft<16>::rot(tr[3 * 2 + 1], ti[3 * 2 + 1], C2, 0.5f);      // w24^2
+        Dft<16>::rot(tr[3 * 3 + 1], ti[3 * 3 + 1], C3, C3);        // w24^3
+        Dft<16>::rot(tr[3 * 4 + 1], ti[3 * 4 + 1], 0.5f, C2);      // w24^4
+        Dft<16>::rot(tr[3 * 5 + 1], ti[3 * 5 + 1], S1, C1);        // w24^5
+        {                                                          // w24^6 = -i
+            const p2 t = tr[3 * 6 + 1];
+            tr[3 * 6 + 1] = ti[3 * 6 + 1];
+            ti[3 * 6 + 1] = pneg(t);
+        }
+        Dft<16>::rot(tr[3 * 7 + 1], ti[3 * 7 + 1], -S1, C1);       // w24^7
+        // b = 2: w24^(2c), c = 1..7
+        Dft<16>::rot(tr[3 * 1 + 2], ti[3 * 1 + 2], C2, 0.5f);      // w24^2
+        Dft<16>::rot(tr[3 * 2 + 2], ti[3 * 2 + 2], 0.5f, C2);      // w24^4
+        {                                                          // w24^6 = -i
+            const p2 t = tr[3 * 3 + 2];
+            tr[3 * 3 + 2] = ti[3 * 3 + 2];
+            ti[3 * 3 + 2] = pneg(t);
+        }
+        Dft<16>::rot(tr[3 * 4 + 2], ti[3 * 4 + 2], -0.5f, C2);     // w24^8
+        Dft<16>::rot(tr[3 * 5 + 2], ti[3 * 5 + 2], -C2, 0.5f);     // w24^10
+        tr[3 * 6 + 2] = pneg(tr[3 * 6 + 2]);                       // w24^12 = -1
+        ti[3 * 6 + 2] = pneg(ti[3 * 6 + 2]);
+        Dft<16>::rot(tr[3 * 7 + 2], ti[3 * 7 + 2], -C2, -0.5f);    // w24^14
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            Dft<3>::run(tr + 3 * c, ti + 3 * c);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                r[c + 8 * d] = tr[3 * c + d];
+                i[c + 8 * d] = ti[3 * c + d];
+            }
+        }
+    }
+};
+
 // Twiddles are kept in shared memory as float4 (c, c, s, s): both packed operands come out of one
 // 128-bit load as aligned register pairs.
 // (xr + i*xi) *= (c + i*s)

@@ -79,11 +79,11 @@ template <int R0, int R1, int R2, int THREADS>
 static bool try_xrowg(const XArgs& a, bool inverse, cudaStream_t st)
 {
     typedef XRowG<R0, R1, R2> G;
-    if (a.P.L != G::M || a.P.ns != G::NS || a.P.radix[0] != R0 || a.P.radix[1] != R1 ||
-        (G::NS == 3 && a.P.radix[2] != R2) || a.g.odd || a.rowList)
-        return false;
+    // three-stage plans read the planner's digit-reversal table, so the radices must be the planner's
+    if (a.P.L != G::M || a.g.odd || a.rowList) return false;
+    if (G::NS == 3 && (a.P.ns != 3 || a.P.radix[0] != R0 || a.P.radix[1] != R1 || a.P.radix[2] != R2)) return false;
     constexpr int RP = THREADS / G::TG;
-    static_assert(RP >= 1 && RP <= 15, "row pairs per CTA");
+    static_assert(RP >= 1 && (G::TG <= 32 || RP <= 15), "row pairs per CTA (named barriers 1..15)");
     const long long grid = (a.nrows + 2 * RP - 1) / (2 * RP);
     if (grid == 0) return true;
     if (grid > 0x7fffffffLL) return false;
@@ -101,6 +101,8 @@ static bool try_xrowg(const XArgs& a, bool inverse, cudaStream_t st)
 
 static bool try_xrowg_all(const XArgs& a, bool inverse, cudaStream_t st)
 {
+    static const bool x384 = env_int("FCB200_XROW384", 1) != 0;
+    if (x384 && try_xrowg<24, 8, 1, 128>(a, inverse, st)) return true;   // nx = 384
     return try_xrowg<16, 8, 1, 64>(a, inverse, st) ||      // nx = 256
            try_xrowg<16, 4, 8, 128>(a, inverse, st) ||     // nx = 1024 (x-axis planning style)
            try_xrowg<8, 8, 8, 128>(a, inverse, st) ||

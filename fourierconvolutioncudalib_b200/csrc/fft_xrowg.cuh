@@ -1,6 +1,8 @@
 // General register-resident row-wise x passes: plans (R0, R1) or (R0, R1, R2) of power-of-two radices
 // with R0 the largest radix, last radix RL in {8, 16} and every earlier stage stride a multiple of RL
-// (e.g. nx = 256 -> (16,8), nx = 1024 -> (8,8,8), nx = 2048 -> (16,8,8)).  Same idea as fft_xrow.cuh:
+// (e.g. nx = 256 -> (16,8), nx = 1024 -> (8,8,8), nx = 2048 -> (16,8,8)); also (24, 8) for nx = 384 (the
+// 384^3 blocks of BASELINE config 4): two-stage plans use no plan table besides the M roots, so the kernel
+// does not care which radices the planner chose for the other x kernels.  Same idea as fft_xrow.cuh:
 //   * a group of TG = M / R0 threads owns one pair of adjacent rows (packed fp32), lanes run along x,
 //     so global loads / stores are coalesced straight from / to registers;
 //   * stages are in-place DIF butterflies in registers; between stages the values make one trip through
@@ -156,7 +158,8 @@ __global__ void __launch_bounds__(THREADS) xrowg_fwd_kernel(XArgs a)
 #pragma unroll
         for (int it = 0; it < ITERL; ++it) {
             const int b = tl + it * TG;
-            const int k0 = __ldg(a.P.rev + b * RL);   // bins k0 + m * (M / RL)
+            // two stages: position b*RL + m holds bin b + m*R0, whatever radices the plan tables were built for
+            const int k0 = (NS == 2) ? b : __ldg(a.P.rev + b * RL);   // bins k0 + m * (M / RL)
 #pragma unroll
             for (int m = 0; m < RL; ++m) {
                 const int k = k0 + m * (M / RL);
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(THREADS) xrowg_fwd_kernel(XArgs a)
 #pragma unroll
     for (int q = 0; q < R0; ++q) {
         const int k = tl + TG * q;
-        const int k2 = (M - k) & (M - 1);
+        const int k2 = (M & (M - 1)) ? (k ? M - k : 0) : ((M - k) & (M - 1));
         const float4 va = x[k + k / R0], vb = x[k2 + k2 / R0];
         const p2 zr = make_float2(va.x, va.y), zi = make_float2(va.z, va.w);
         const p2 pr = make_float2(vb.x, vb.y), pi = make_float2(vb.z, vb.w);
@@ -267,11 +270,11 @@ __global__ void __launch_bounds__(THREADS) xrowg_inv_kernel(XArgs a)
 #pragma unroll
         for (int it = 0; it < ITERL; ++it) {
             const int b = tl + it * TG;
-            const int k0 = __ldg(a.P.rev + b * RL);
+            const int k0 = (NS == 2) ? b : __ldg(a.P.rev + b * RL);
 #pragma unroll
             for (int m = 0; m < RL; ++m) {
                 const int k = k0 + m * (M / RL);
-                const int k2 = (M - k) & (M - 1);
+                const int k2 = (M & (M - 1)) ? (k ? M - k : 0) : ((M - k) & (M - 1));
                 const float4 va = x[k + k / R0], vb = x[k2 + k2 / R0];
                 const p2 ar = make_float2(va.x, va.y), ai = make_float2(va.z, va.w);
                 const p2 br = make_float2(vb.x, vb.y), bi = make_float2(vb.z, vb.w);
