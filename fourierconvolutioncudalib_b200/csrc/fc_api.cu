@@ -255,7 +255,10 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
     static const bool staging_on = env_flag("FCB200_STAGING", true);
     const bool staged = im_kind == HostMem::Pageable && staging_on;
 
-    if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+    // Fused (default): the x passes assemble the padded rows while loading the unpadded volume and store only the
+    // interior back, so no padded real volume exists.  FCB200_PAD_FUSED=0: separate embed / crop kernels.
+    static const bool fused = env_flag("FCB200_PAD_FUSED", true);
+    if (!fused && !p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
     const size_t src_plane = (size_t)g.sy * g.sx, src_elems = src_plane * g.sz, src_bytes = src_elems * sizeof(float);
     float* d_src = im;
     if (!im_dev) {
@@ -275,6 +278,22 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
 
     const size_t splane = (size_t)p.g.ny * p.g.xcp;
     const int z_lo = g.oz, z_hi = g.oz + g.sz;          // source planes sit in padded planes [z_lo, z_hi)
+    auto forward_planes = [&](int pz0, int pn) {        // x+y forward of padded planes [pz0, pz0+pn)
+        if (fused) {
+            run_xy_forward_planes(p, d_src, pz0, pn, st, &g);
+        } else {
+            run_pad_embed(d_src, p.d_real, g, pz0, pn, st);
+            run_xy_forward_planes(p, p.d_real, pz0, pn, st);
+        }
+    };
+    auto inverse_planes = [&](int z0, int n) {          // y+x inverse of source planes [z0, z0+n), cropped into d_src
+        if (fused) {
+            run_yx_inverse_planes(p, d_src, z_lo + z0, n, st, &g);
+        } else {
+            run_yx_inverse_planes(p, p.d_real, z_lo + z0, n, st);
+            run_pad_crop(p.d_real, d_src, g, z0, n, st);
+        }
+    };
     // forward spectrum planes of the z halo: zero volume planes have a zero spectrum; mirrored ones are built
     // from the (complete) source and transformed
     auto halo_forward = [&] {
@@ -284,8 +303,7 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
             if (mode == 0) {
                 FC_CUDA(cudaMemsetAsync(p.d_spec + r0[i] * splane, 0, rn[i] * splane * sizeof(float2), st));
             } else {
-                run_pad_embed(d_src, p.d_real, g, r0[i], rn[i], st);
-                run_xy_forward_planes(p, p.d_real, r0[i], rn[i], st);
+                forward_planes(r0[i], rn[i]);
             }
         }
     };
@@ -317,8 +335,7 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
             const int z0 = z0_of(c), n = z0_of(c + 1) - z0;
             if (n <= 0) continue;
             FC_CUDA(cudaStreamWaitEvent(st, p.ev_chunk[c], 0));
-            run_pad_embed(d_src, p.d_real, g, z_lo + z0, n, st);
-            run_xy_forward_planes(p, p.d_real, z_lo + z0, n, st);
+            forward_planes(z_lo + z0, n);
         }
         if (mode != 0) halo_forward();
         psf.join();
@@ -326,8 +343,7 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
         for (int c = 0; c < nch; ++c) {
             const int z0 = z0_of(c), n = z0_of(c + 1) - z0;
             if (n <= 0) continue;
-            run_yx_inverse_planes(p, p.d_real, z_lo + z0, n, st);
-            run_pad_crop(p.d_real, d_src, g, z0, n, st);
+            inverse_planes(z0, n);
             FC_CUDA(cudaEventRecord(p.ev_chunk[8 + c], st));
             FC_CUDA(cudaStreamWaitEvent(p.s_d2h, p.ev_chunk[8 + c], 0));
             FC_CUDA(cudaMemcpyAsync(im + z0 * src_plane, d_src + z0 * src_plane, n * src_plane * sizeof(float),
@@ -342,13 +358,11 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
         if (staged) p.stager.upload(d_src, im, src_bytes, st);
         else FC_CUDA(cudaMemcpyAsync(d_src, im, src_bytes, cudaMemcpyHostToDevice, st));
     }
-    run_pad_embed(d_src, p.d_real, g, z_lo, g.sz, st);
-    run_xy_forward_planes(p, p.d_real, z_lo, g.sz, st);
+    forward_planes(z_lo, g.sz);
     halo_forward();
     psf.join();
     run_z_fused(p, false, st);
-    run_yx_inverse_planes(p, p.d_real, z_lo, g.sz, st);
-    run_pad_crop(p.d_real, d_src, g, 0, g.sz, st);
+    inverse_planes(0, g.sz);
     if (!im_dev) {
         if (staged) p.stager.download(im, d_src, src_bytes, st);
         else FC_CUDA(cudaMemcpyAsync(im, d_src, src_bytes, cudaMemcpyDeviceToHost, st));

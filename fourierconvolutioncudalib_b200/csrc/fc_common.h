@@ -47,6 +47,15 @@ struct PsfGather {
     int d0, d1, d2;
 };
 
+// In-library padding: source volume [sz][sy][sx] embedded at offsets (ox,oy,oz) in the padded volume
+// [pz][py][px] (x fastest).  mode 0: zeros outside (reference tests/padd_utils.h:157-171); 1: mirror.
+struct PadGeom {
+    int sx, sy, sz;
+    int px, py, pz;
+    int ox, oy, oz;
+    int mode;
+};
+
 inline void throw_cuda(cudaError_t err, const char* what, const char* file, int line)
 {
     if (err != cudaSuccess) {

@@ -673,10 +673,10 @@ bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaSt
 
 // ---- the image path in three pieces; the x/y pieces work on any range of z planes so that the host-pointer
 // ---- entry can overlap them with the upload / download of the neighbouring planes
-void run_xy_forward_planes(ConvPlan& p, const float* d_real, int z0, int n, cudaStream_t st)
+void run_xy_forward_planes(ConvPlan& p, const float* d_real, int z0, int n, cudaStream_t st, const PadGeom* pad)
 {
     const size_t rplane = (size_t)p.g.ny * p.g.nx, splane = (size_t)p.g.ny * p.g.xcp;
-    {   // one kernel for both passes where the cluster kernel covers the shape (fft_xyfused.cu)
+    if (pad == nullptr) {   // one kernel for both passes where the cluster kernel covers the shape (fft_xyfused.cu)
         XYArgs f{};
         f.in_real = d_real + z0 * rplane;
         f.spec = p.d_spec + z0 * splane;
@@ -696,6 +696,12 @@ void run_xy_forward_planes(ConvPlan& p, const float* d_real, int z0, int n, cuda
     xa.in_real = d_real + z0 * rplane;
     xa.spec = p.d_spec + z0 * splane;
     xa.nrows = (long long)p.g.ny * n;
+    if (pad != nullptr) {
+        xa.in_real = d_real;   // the unpadded volume; the loader picks the source row of every padded row
+        xa.padOn = 1;
+        xa.padZ0 = z0;
+        xa.pad = *pad;
+    }
     {
         PassTimer t(kPassXFwd, st);
         launch_x_fwd(xa, false, st);
@@ -725,10 +731,10 @@ void run_z_fused(ConvPlan& p, bool window, cudaStream_t st)
     count_launches(1);
 }
 
-void run_yx_inverse_planes(ConvPlan& p, float* d_real, int z0, int n, cudaStream_t st)
+void run_yx_inverse_planes(ConvPlan& p, float* d_real, int z0, int n, cudaStream_t st, const PadGeom* pad)
 {
     const size_t rplane = (size_t)p.g.ny * p.g.nx, splane = (size_t)p.g.ny * p.g.xcp;
-    {
+    if (pad == nullptr) {
         XYArgs f{};
         f.out_real = d_real + z0 * rplane;
         f.spec = p.d_spec + z0 * splane;
@@ -752,6 +758,12 @@ void run_yx_inverse_planes(ConvPlan& p, float* d_real, int z0, int n, cudaStream
     xa.spec = p.d_spec + z0 * splane;
     xa.out_real = d_real + z0 * rplane;
     xa.nrows = (long long)p.g.ny * n;
+    if (pad != nullptr) {
+        xa.out_real = d_real;   // the unpadded volume; only interior rows / columns are stored
+        xa.padOn = 1;
+        xa.padZ0 = z0;
+        xa.pad = *pad;
+    }
     {
         PassTimer t(kPassXInv, st);
         launch_x_inv(xa, st);

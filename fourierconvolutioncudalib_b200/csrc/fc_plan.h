@@ -116,20 +116,18 @@ void run_forward(ConvPlan& p, const float* d_real, float2* dst, int passes, cuda
 // Image path: d_real (device, dense) is convolved in place with the PSF spectrum in plan.d_H.
 void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st);
 // the same in three pieces (x+y forward / y+x inverse on z planes [z0, z0+n) of the volume at d_real)
-void run_xy_forward_planes(ConvPlan& p, const float* d_real, int z0, int n, cudaStream_t st);
+// pad != nullptr (in-library padding, fused): the volume of the plan is the PADDED grid, d_real is the caller's
+// UNPADDED volume; the x pass builds the padded rows of planes [z0, z0+n) while loading / writes only the
+// interior of the rows back (no padded real volume exists in memory)
+void run_xy_forward_planes(ConvPlan& p, const float* d_real, int z0, int n, cudaStream_t st,
+                           const PadGeom* pad = nullptr);
 void run_z_fused(ConvPlan& p, bool window, cudaStream_t st);
-void run_yx_inverse_planes(ConvPlan& p, float* d_real, int z0, int n, cudaStream_t st);
+void run_yx_inverse_planes(ConvPlan& p, float* d_real, int z0, int n, cudaStream_t st, const PadGeom* pad = nullptr);
 void run_inverse(ConvPlan& p, float2* spec, float* d_real, cudaStream_t st);
 
 // ---- in-library padding (fc_pad.cu) ---------------------------------------------------------------
 // Source volume [sz][sy][sx] embedded at offsets (ox,oy,oz) in the padded volume [pz][py][px] (x fastest).
 // mode 0: zeros outside (reference tests/padd_utils.h:157-171); mode 1: mirror (numpy "reflect").
-struct PadGeom {
-    int sx, sy, sz;
-    int px, py, pz;
-    int ox, oy, oz;
-    int mode;
-};
 // padded planes [pz0, pz0+pn) of d_pad <- d_src (whole source volume on the device)
 void run_pad_embed(const float* d_src, float* d_pad, const PadGeom& g, int pz0, int pn, cudaStream_t st);
 // source planes [z0, z0+n) of d_dst <- interior of d_pad

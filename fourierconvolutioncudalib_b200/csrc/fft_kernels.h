@@ -21,6 +21,13 @@ struct XArgs {
     const int* tapStart;
     const int* tapX;
     const int* tapIdx;
+    // In-library padding fused into the image x passes: the rows of this launch are rows of the PADDED grid
+    // (g = padded geometry, row 0 = padded plane padZ0); in_real / out_real point at the caller's UNPADDED
+    // volume.  Forward: each padded row is assembled from the source row (zeros / mirror) while loading.
+    // Inverse: only the interior part of interior rows is stored.
+    int padOn;
+    int padZ0;
+    PadGeom pad;
 };
 
 struct ColArgs {

@@ -121,7 +121,7 @@ bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st)
     if (!static_enabled()) return false;
     const long long tiles = (a.nrows + 15) / 16;
     if (tiles == 0) return true;
-    if (!psf && xrow_enabled()) {
+    if (!psf && xrow_enabled() && !a.padOn) {
         if (xrow_threads() == 64 && try_xrow<16, 64>(a, false, st)) return true;
         if (xrow_threads() == 256 && try_xrow<16, 256>(a, false, st)) return true;
         if (try_xrow<16, 128>(a, false, st) || try_xrow<8, 64>(a, false, st)) return true;
@@ -143,7 +143,7 @@ bool launch_x_inv_static(const XArgs& a, cudaStream_t st)
     if (!static_enabled()) return false;
     const long long tiles = (a.nrows + 15) / 16;
     if (tiles == 0) return true;
-    if (xrow_enabled()) {
+    if (xrow_enabled() && !a.padOn) {
         if (xrow_threads() == 64 && try_xrow<16, 64>(a, true, st)) return true;
         if (xrow_threads() == 256 && try_xrow<16, 256>(a, true, st)) return true;
         if (try_xrow<16, 128>(a, true, st) || try_xrow<8, 64>(a, true, st)) return true;

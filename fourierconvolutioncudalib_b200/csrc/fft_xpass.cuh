@@ -72,6 +72,40 @@ __device__ __forceinline__ float psf_tap(const PsfGather& g, long long flat)
     return __ldg(g.kernel + (c + g.k2 * (b + g.k1 * a)));
 }
 
+// numpy.pad(mode="reflect") index: even about 0, period 2(n-1)
+__device__ __forceinline__ int pad_fold(int s, int n)
+{
+    if (n == 1) return 0;
+    const int T = 2 * (n - 1);
+    s = s < 0 ? -s : s;
+    if (s >= T) s %= T;
+    return s < n ? s : T - s;
+}
+// source row feeding padded row (z, y); nullptr = the row is all zero
+__device__ __forceinline__ const float* pad_src_row(const PadGeom& pg, const float* src, int z, int y)
+{
+    int sz = z - pg.oz, sy = y - pg.oy;
+    if (pg.mode == 1) {
+        sz = pad_fold(sz, pg.sz);
+        sy = pad_fold(sy, pg.sy);
+    } else if (sz < 0 || sz >= pg.sz || sy < 0 || sy >= pg.sy) {
+        return nullptr;
+    }
+    return src + ((size_t)sz * pg.sy + sy) * pg.sx;
+}
+// source element feeding padded column x of that row; nullptr = zero
+__device__ __forceinline__ const float* pad_src_elem(const PadGeom& pg, const float* row, int x)
+{
+    const int s = x - pg.ox;
+    if (pg.mode == 1) return row + pad_fold(s, pg.sx);
+    return (row != nullptr && s >= 0 && s < pg.sx) ? row + s : nullptr;
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -213,6 +247,25 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kerne
         float2* dst = rowt + lrow * P;
         if (grow < 0) {
             for (int pos = lane; pos < L; pos += 32) dst[pos] = make_float2(0.f, 0.f);
+        } else if (LOADER == 0 && a.padOn) {
+            // padded row assembled from the caller's unpadded volume (lanes along x: coalesced source reads)
+            const float* srow = pad_src_row(a.pad, a.in_real, a.padZ0 + (int)(grow / g.ny), (int)(grow % g.ny));
+            // (4-byte cp.async: the source offset x - ox has no alignment; every load of the row is in flight at once)
+            float* dstf = reinterpret_cast<float*>(dst);
+            if (!g.odd) {
+                for (int x = lane; x < g.nx; x += 32) {
+                    const float* e = pad_src_elem(a.pad, srow, x);
+                    if (e) cp_async4(dstf + x, e);
+                    else dstf[x] = 0.f;
+                }
+            } else {
+                for (int pos = lane; pos < L; pos += 32) {
+                    const float* e = pad_src_elem(a.pad, srow, pos);
+                    if (e) cp_async4(dstf + 2 * pos, e);
+                    else dstf[2 * pos] = 0.f;
+                    dstf[2 * pos + 1] = 0.f;
+                }
+            }
         } else if (LOADER == 0 && !g.odd) {
             const float2* src = reinterpret_cast<const float2*>(a.in_real + grow * g.nx);
             for (int pos = lane; pos < L; pos += 32) cp_async8(dst + pos, src + pos);
@@ -450,6 +503,20 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
         const long long grow = row0 + lrow;
         if (grow >= a.nrows) continue;
         const float2* src = rowt + lrow * P;
+        if (a.padOn) {
+            // crop: only the interior part of interior rows goes back to the caller's unpadded volume
+            const PadGeom& pg = a.pad;
+            const int sz = a.padZ0 + (int)(grow / g.ny) - pg.oz, sy = (int)(grow % g.ny) - pg.oy;
+            if (sz < 0 || sz >= pg.sz || sy < 0 || sy >= pg.sy) continue;   // warp-uniform
+            float* dst = a.out_real + ((size_t)sz * pg.sy + sy) * pg.sx;
+            if (g.odd) {
+                for (int x = lane; x < pg.sx; x += 32) dst[x] = src[x + pg.ox].x;
+            } else {
+                const float* srcf = reinterpret_cast<const float*>(src);
+                for (int x = lane; x < pg.sx; x += 32) dst[x] = srcf[x + pg.ox];
+            }
+            continue;
+        }
         if (g.odd) {
             float* dst = a.out_real + grow * g.nx;
             for (int pos = lane; pos < L; pos += 32) dst[pos] = src[pos].x;

@@ -42,7 +42,11 @@ CASES = [  # imDim, kernelDim
     ((17, 5, 9), (4, 3, 5)),
     ((100, 36, 20), (9, 9, 5)),
     ((16, 16, 16), (15, 15, 15)),       # halo almost as wide as the volume
+    ((120, 20, 12), (9, 3, 3)),         # padded rows of 128: InPlace takes the row-wise x kernels, the fused
+    ((370, 12, 6), (15, 3, 3)),         # padded path the tiled ones (384 likewise) -> round-off, not bits
+    ((33, 9, 7), (5, 5, 5)),            # odd padded row length (37)
 ]
+ROW_WISE_NX = (128, 256, 384, 512, 1024, 2048)
 
 
 @pytest.mark.parametrize("mode", [0, 1], ids=["zero", "mirror"])
@@ -63,7 +67,10 @@ def test_padded_matches_oracle_and_host_padded_inplace(fc, dev, imDim, kDim, mod
     padded, pDim, off = host_pad(im, imDim, kDim, mode, policy)
     fc.convolution3DfftCUDAInPlace(padded, pDim, k.copy(), kDim, dev)
     want = fo.crop(padded.reshape(pDim[2], pDim[1], pDim[0]), off[::-1], imDim[::-1]).reshape(-1)
-    assert np.array_equal(got, want)
+    if pDim[0] in ROW_WISE_NX:
+        check(got, want, max_rel=2e-6, l2_rel=1e-6)
+    else:
+        assert np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("imDim,kDim", [((64, 64, 64), (3, 3, 3)), ((48, 40, 24), (5, 7, 9)), ((40, 40, 40), (9, 9, 9))],
