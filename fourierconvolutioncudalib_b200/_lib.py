@@ -80,12 +80,12 @@ def load():
         "fcb200_debug_rfft3": (None, [fp, ip, fp, i, i]),
         "fcb200_debug_irfft3": (None, [fp, ip, fp, i]),
         "fcb200_debug_psf_spectrum": (None, [fp, ip, ip, fp, i]),
-        "fcb200_slab_xy_forward": (None, [vp, vp, vp, ip, i, i, i, vp]),
+        "fcb200_slab_xy_forward": (None, [vp, vp, vp, ip, i, i, i, i, vp]),
         "fcb200_slab_z_fused": (None, [vp, vp, ip, i, i, vp]),
-        "fcb200_slab_yx_inverse": (None, [vp, vp, vp, ip, i, i, i, vp]),
+        "fcb200_slab_yx_inverse": (None, [vp, vp, vp, ip, i, i, i, i, vp]),
         "fcb200_slab_psf_scratch_elems": (ctypes.c_longlong, [ip, ip, i]),
         "fcb200_slab_psf": (None, [vp, ip, ip, i, i, vp, vp, i, vp]),
-        "fcb200_slab_xy_forward_peer": (None, [vp, vp, vp, ip, i, i, i, i, vp]),
+        "fcb200_slab_xy_forward_peer": (None, [vp, vp, vp, ip, i, i, i, i, i, vp]),
         "fcb200_slab_z_fused_peer": (None, [vp, vp, vp, ip, i, i, i, i, vp]),
         "fcb200_device_malloc": (vp, [ctypes.c_longlong, i]),
         "fcb200_device_free": (None, [vp, i]),

@@ -864,8 +864,8 @@ void fcb200_debug_psf_spectrum(const imageType* kernel, const int* kernelDim, co
 }
 
 // ---- slab-decomposed single volume ---------------------------------------------------------------
-void fcb200_slab_xy_forward(const imageType* real_slab, float* zslab_spec, float* send, const int* imDim, int nzl, int nyl,
-                            int devCUDA, void* stream)
+void fcb200_slab_xy_forward(const imageType* real_slab, float* zslab_spec, float* send, const int* imDim, int nzl, int nzp,
+                            int nyl, int devCUDA, void* stream)
 {
     guarded([&] {
         check_dims(imDim, nullptr);
@@ -873,7 +873,7 @@ void fcb200_slab_xy_forward(const imageType* real_slab, float* zslab_spec, float
         auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
         std::lock_guard<std::mutex> lock(plan->mu);
         run_slab_xy_forward(*plan, real_slab, reinterpret_cast<float2*>(zslab_spec), reinterpret_cast<float2*>(send), nzl,
-                            nyl, (cudaStream_t)stream);
+                            nyl, (cudaStream_t)stream, nullptr, 0, nzp);
     });
 }
 
@@ -889,8 +889,8 @@ void fcb200_slab_z_fused(float* yslab_spec, const float* H_yslab, const int* imD
     });
 }
 
-void fcb200_slab_yx_inverse(const float* recv, float* zslab_spec, imageType* real_slab, const int* imDim, int nzl, int nyl,
-                            int devCUDA, void* stream)
+void fcb200_slab_yx_inverse(const float* recv, float* zslab_spec, imageType* real_slab, const int* imDim, int nzl, int nzp,
+                            int nyl, int devCUDA, void* stream)
 {
     guarded([&] {
         check_dims(imDim, nullptr);
@@ -898,12 +898,12 @@ void fcb200_slab_yx_inverse(const float* recv, float* zslab_spec, imageType* rea
         auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
         std::lock_guard<std::mutex> lock(plan->mu);
         run_slab_yx_inverse(*plan, reinterpret_cast<const float2*>(recv), reinterpret_cast<float2*>(zslab_spec), real_slab,
-                            nzl, nyl, (cudaStream_t)stream);
+                            nzl, nyl, (cudaStream_t)stream, nzp);
     });
 }
 
 void fcb200_slab_xy_forward_peer(const imageType* real_slab, float* zslab_spec, void* const* peer_yslabs, const int* imDim,
-                                 int nzl, int nyl, int rank, int devCUDA, void* stream)
+                                 int nzl, int nzp, int nyl, int rank, int devCUDA, void* stream)
 {
     guarded([&] {
         check_dims(imDim, nullptr);
@@ -911,11 +911,11 @@ void fcb200_slab_xy_forward_peer(const imageType* real_slab, float* zslab_spec, 
         auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
         std::lock_guard<std::mutex> lock(plan->mu);
         run_slab_xy_forward(*plan, real_slab, reinterpret_cast<float2*>(zslab_spec), nullptr, nzl, nyl, (cudaStream_t)stream,
-                            reinterpret_cast<float2* const*>(peer_yslabs), rank);
+                            reinterpret_cast<float2* const*>(peer_yslabs), rank, nzp);
     });
 }
 
-void fcb200_slab_z_fused_peer(float* yslab_spec, const float* H_yslab, void* const* peer_recv, const int* imDim, int nzl,
+void fcb200_slab_z_fused_peer(float* yslab_spec, const float* H_yslab, void* const* peer_recv, const int* imDim, int nzp,
                               int nyl, int rank, int devCUDA, void* stream)
 {
     guarded([&] {
@@ -924,7 +924,7 @@ void fcb200_slab_z_fused_peer(float* yslab_spec, const float* H_yslab, void* con
         auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
         std::lock_guard<std::mutex> lock(plan->mu);
         run_slab_z_fused(*plan, reinterpret_cast<float2*>(yslab_spec), reinterpret_cast<const float2*>(H_yslab), nyl,
-                         (cudaStream_t)stream, reinterpret_cast<float2* const*>(peer_recv), rank, nzl);
+                         (cudaStream_t)stream, reinterpret_cast<float2* const*>(peer_recv), rank, nzp);
     });
 }
 
@@ -934,6 +934,7 @@ void* fcb200_device_malloc(long long bytes, int devCUDA)
         DeviceGuard guard(devCUDA);
         void* p = nullptr;
         FC_CUDA(cudaMalloc(&p, (size_t)bytes));
+        FC_CUDA(cudaMemset(p, 0, (size_t)bytes));   // ragged slabs leave the pad rows / planes of a block unwritten
         return p;
     });
 }

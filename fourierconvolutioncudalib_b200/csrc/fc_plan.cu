@@ -807,14 +807,16 @@ void run_convolve(ConvPlan& p, float* d_real, cudaStream_t st)
 // ------------------------------------------------------------------------------------------------
 static void check_slab(const ConvPlan& p, int nzl, int nyl)
 {
-    if (nzl <= 0 || nzl > p.g.nz || nyl <= 0 || p.g.ny % nyl != 0)
-        throw std::runtime_error("fcb200: slab extents must be positive and nyl must divide ny");
+    // ragged slabs: the last rank may own fewer than nyl rows / nzp planes; the block pitch stays nyl / nzp
+    if (nzl <= 0 || nzl > p.g.nz || nyl <= 0 || nyl > p.g.ny)
+        throw std::runtime_error("fcb200: slab extents must be positive and not larger than the volume");
 }
 
 void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2* send, int nzl, int nyl,
-                         cudaStream_t st, float2* const* peers, int rank)
+                         cudaStream_t st, float2* const* peers, int rank, int nzp)
 {
     check_slab(p, nzl, nyl);
+    if (nzp < nzl) throw std::runtime_error("fcb200: slab block pitch nzp must be >= the local plane count");
     XArgs xa = x_args(p);
     xa.in_real = d_real;
     xa.spec = zslab;
@@ -826,12 +828,12 @@ void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2
     ColArgs ya = y_args(p, zslab);
     ya.split = send;
     ya.splitRows = nyl;
-    ya.splitBlock = (long long)nzl * nyl * p.g.xcp;
+    ya.splitBlock = (long long)nzp * nyl * p.g.xcp;
     ya.splitGroup = (long long)nyl * p.g.xcp;
-    if (peers) {   // store straight into the peers' y-slab buffers [nz][nyl][xcp]: my planes start at rank*nzl
+    if (peers) {   // store straight into the peers' y-slab buffers [P*nzp][nyl][xcp]: my planes start at rank*nzp
         ya.split = nullptr;
         ya.splitPeers = peers;
-        ya.splitPeerOffset = (long long)rank * nzl * nyl * p.g.xcp;
+        ya.splitPeerOffset = (long long)rank * nzp * nyl * p.g.xcp;
     }
     {
         PassTimer t(kPassYFwd, st);
@@ -863,13 +865,14 @@ void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, 
 }
 
 void run_slab_yx_inverse(ConvPlan& p, const float2* recv, float2* zslab, float* d_real, int nzl, int nyl,
-                         cudaStream_t st)
+                         cudaStream_t st, int nzp)
 {
     check_slab(p, nzl, nyl);
+    if (nzp < nzl) throw std::runtime_error("fcb200: slab block pitch nzp must be >= the local plane count");
     ColArgs ya = y_args(p, zslab);
     ya.split = const_cast<float2*>(recv);
     ya.splitRows = nyl;
-    ya.splitBlock = (long long)nzl * nyl * p.g.xcp;
+    ya.splitBlock = (long long)nzp * nyl * p.g.xcp;
     ya.splitGroup = (long long)nyl * p.g.xcp;
     {
         PassTimer t(kPassYInv, st);
@@ -900,7 +903,8 @@ void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, 
                   float2* scratch, cudaStream_t st)
 {
     check_slab(p, 1, nyl);
-    if (y0 < 0 || y0 + nyl > p.g.ny) throw std::runtime_error("fcb200: PSF slab out of range");
+    if (y0 < 0 || y0 >= p.g.ny) throw std::runtime_error("fcb200: PSF slab out of range");
+    const int rows_here = std::min(nyl, p.g.ny - y0);   // ragged last slab: fewer valid rows, same pitch
     psf_lists(p, pdims, st);
     // x pass (gather loader) on every row of the planes that hold taps, written compactly
     XArgs xa = x_args(p);
@@ -927,7 +931,7 @@ void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, 
         col_pass(y_args(p, scratch), 0, p.n_planes, st);
     }
     // rows [y0, y0+nyl) of every active plane -> its place in the y-slab; the z pass skips other planes
-    const size_t row_bytes = (size_t)nyl * p.g.xcp * sizeof(float2);
+    const size_t row_bytes = (size_t)rows_here * p.g.xcp * sizeof(float2);
     for (int i = 0; i < p.n_planes; ++i) {
         const int z = p.h_planes[(size_t)i];
         FC_CUDA(cudaMemcpyAsync(Hslab + (size_t)z * nyl * p.g.xcp, scratch + ((size_t)i * p.g.ny + y0) * p.g.xcp,

@@ -1,6 +1,9 @@
 """Slab-decomposed 3D FFT convolution of ONE large volume over P GPUs (BASELINE config 5).
 
-One process per GPU.  Rank g owns z planes [g*nz/P, (g+1)*nz/P) of the real volume.  Per call:
+One process per GPU.  Rank g owns z planes [g*nzp, min(nz, (g+1)*nzp)) of the real volume, nzp = ceil(nz/P), and
+after the exchange the ky rows [g*nyl, min(ny, (g+1)*nyl)), nyl = ceil(ny/P): the extents need not be divisible
+by P (ragged slabs; exchange blocks keep the pitch nzp x nyl, the last rank's pad planes / rows are carried along
+and never read back).  Per call:
 
   x+y forward on the z slab  (C ABI: fcb200_slab_xy_forward; the y pass writes the send buffer)
   all-to-all                 (z slabs -> ky slabs)
@@ -54,14 +57,14 @@ class CPasses:
     def spectrum_pitch(self, d0):
         return api.spectrum_pitch(d0)
 
-    def xy_forward(self, real_slab, zslab, send, im_dim, nzl, nyl, dev, st):
-        self.lib.fcb200_slab_xy_forward(_p(real_slab), _p(zslab), _p(send), _ints(im_dim), nzl, nyl, dev, st)
+    def xy_forward(self, real_slab, zslab, send, im_dim, nzl, nzp, nyl, dev, st):
+        self.lib.fcb200_slab_xy_forward(_p(real_slab), _p(zslab), _p(send), _ints(im_dim), nzl, nzp, nyl, dev, st)
 
     def z_fused(self, yslab, H, im_dim, nyl, dev, st):
         self.lib.fcb200_slab_z_fused(_p(yslab), _p(H), _ints(im_dim), nyl, dev, st)
 
-    def yx_inverse(self, recv, zslab, real_slab, im_dim, nzl, nyl, dev, st):
-        self.lib.fcb200_slab_yx_inverse(_p(recv), _p(zslab), _p(real_slab), _ints(im_dim), nzl, nyl, dev, st)
+    def yx_inverse(self, recv, zslab, real_slab, im_dim, nzl, nzp, nyl, dev, st):
+        self.lib.fcb200_slab_yx_inverse(_p(recv), _p(zslab), _p(real_slab), _ints(im_dim), nzl, nzp, nyl, dev, st)
 
 
 class SlabConvolver:
@@ -74,26 +77,31 @@ class SlabConvolver:
         self.im_dim = tuple(int(v) for v in im_dim)
         self.k_dim = tuple(int(v) for v in kernel_dim)
         d0, d1, d2 = self.im_dim
-        if d2 % world or d1 % world:
-            raise ValueError("slab mode needs imDim[1] and imDim[2] divisible by the number of ranks")
         self.rank, self.world, self.dev = rank, world, dev
-        self.nzl, self.nyl = d2 // world, d1 // world
+        # block pitches (equal on all ranks) and what this rank really owns
+        self.nzp, self.nyl = -(-d2 // world), -(-d1 // world)
+        if (world - 1) * self.nzp >= d2 or (world - 1) * self.nyl >= d1:
+            raise ValueError("slab mode: every rank must own at least one z plane and one ky row "
+                             f"(imDim {self.im_dim} over {world} ranks)")
+        self.nzl = min(self.nzp, d2 - rank * self.nzp)
+        self.ny_here = min(self.nyl, d1 - rank * self.nyl)
         self.xcp = self.passes.spectrum_pitch(d0)
         self.exchange = exchange
         device = torch.device(device if device is not None else f"cuda:{dev}")
-        n_spec = self.nzl * d1 * self.xcp * 2            # floats of one slab-sized complex buffer
-        self.zslab = torch.empty(n_spec, dtype=torch.float32, device=device)
-        self.buf_a = torch.empty(n_spec, dtype=torch.float32, device=device)   # send, later receive
-        self.buf_b = torch.empty(n_spec, dtype=torch.float32, device=device)   # y-slab spectrum
-        self.H = torch.empty(n_spec, dtype=torch.float32, device=device)       # PSF spectrum, y slab
+        n_spec = world * self.nzp * self.nyl * self.xcp * 2     # floats of one exchange-sized complex buffer
+        self.zslab = torch.zeros(n_spec, dtype=torch.float32, device=device)
+        self.buf_a = torch.zeros(n_spec, dtype=torch.float32, device=device)   # send, later receive
+        self.buf_b = torch.zeros(n_spec, dtype=torch.float32, device=device)   # y-slab spectrum [P*nzp][nyl][xcp]
+        self.H = torch.zeros(n_spec, dtype=torch.float32, device=device)       # PSF spectrum, y slab
         self._psf_ready_for = None
         self._lib = self.passes.lib if isinstance(self.passes, CPasses) else None
 
     def slab_of(self, volume_flat):
         """this rank's part of a full flat [d2][d1][d0] host/torch array (helper for tests/benchmarks)"""
         d0, d1, d2 = self.im_dim
-        n = self.nzl * d1 * d0
-        return volume_flat[self.rank * n:(self.rank + 1) * n]
+        plane = d1 * d0
+        z0 = self.rank * self.nzp
+        return volume_flat[z0 * plane:(z0 + self.nzl) * plane]
 
     def prepare_psf(self, kernel_dev, stream=0):
         """PSF spectrum of this rank's ky slab (call again when the PSF changes)"""
@@ -112,11 +120,11 @@ class SlabConvolver:
         """in-place convolution of this rank's z slab (flat torch CUDA tensor [nzl][d1][d0])"""
         ps = self.passes
         st = ctypes.c_void_p(int(stream))
-        ps.xy_forward(real_slab, self.zslab, self.buf_a, self.im_dim, self.nzl, self.nyl, self.dev, st)
-        self.exchange(self.buf_a, self.buf_b)          # buf_b = [d2][nyl][xcp]
+        ps.xy_forward(real_slab, self.zslab, self.buf_a, self.im_dim, self.nzl, self.nzp, self.nyl, self.dev, st)
+        self.exchange(self.buf_a, self.buf_b)          # buf_b = [P*nzp][nyl][xcp], planes 0..d2-1 valid
         ps.z_fused(self.buf_b, self.H, self.im_dim, self.nyl, self.dev, st)
-        self.exchange(self.buf_b, self.buf_a)          # buf_a = [P][nzl][nyl][xcp]
-        ps.yx_inverse(self.buf_a, self.zslab, real_slab, self.im_dim, self.nzl, self.nyl, self.dev, st)
+        self.exchange(self.buf_b, self.buf_a)          # buf_a = [P][nzp][nyl][xcp]
+        ps.yx_inverse(self.buf_a, self.zslab, real_slab, self.im_dim, self.nzl, self.nzp, self.nyl, self.dev, st)
 
 
 class LocalExchange:
@@ -146,7 +154,7 @@ def run_lockstep(convolvers, slabs, exchange):
     st = ct.c_void_p(0)
     lib = convolvers[0]._lib
     for c, s in zip(convolvers, slabs):
-        lib.fcb200_slab_xy_forward(_p(s), _p(c.zslab), _p(c.buf_a), _ints(c.im_dim), c.nzl, c.nyl, c.dev, st)
+        lib.fcb200_slab_xy_forward(_p(s), _p(c.zslab), _p(c.buf_a), _ints(c.im_dim), c.nzl, c.nzp, c.nyl, c.dev, st)
     for c in convolvers:
         exchange(c.buf_a, c.buf_b)
     exchange.flush()
@@ -156,7 +164,7 @@ def run_lockstep(convolvers, slabs, exchange):
         exchange(c.buf_b, c.buf_a)
     exchange.flush()
     for c, s in zip(convolvers, slabs):
-        lib.fcb200_slab_yx_inverse(_p(c.buf_a), _p(c.zslab), _p(s), _ints(c.im_dim), c.nzl, c.nyl, c.dev, st)
+        lib.fcb200_slab_yx_inverse(_p(c.buf_a), _p(c.zslab), _p(s), _ints(c.im_dim), c.nzl, c.nzp, c.nyl, c.dev, st)
 
 
 class _RawBuffer:
@@ -197,7 +205,7 @@ class DistBarrier:
 class PeerSlabConvolver(SlabConvolver):
     """Slab convolution whose exchange is fused into the FFT kernels (peer stores over NVLink).
 
-    Buffers: `yslab` [d2][nyl][xcp] (written by every rank's y pass) and `recv` [P][nzl][nyl][xcp] (written by
+    Buffers: `yslab` [P*nzp][nyl][xcp] (written by every rank's y pass) and `recv` [P][nzp][nyl][xcp] (written by
     every rank's fused z pass) are the two buffers the peers map.  Call `connect_ipc()` (one process per GPU) or
     `connect_local()` (all ranks emulated in one process) before `convolve()`."""
 
@@ -252,15 +260,15 @@ class PeerSlabConvolver(SlabConvolver):
     # the three phases, separately callable so that emulated ranks can run them in lock-step
     def phase_forward(self, real_slab, st):
         self._lib.fcb200_slab_xy_forward_peer(_p(real_slab), _p(self.zslab), _p(self.peer_yslab), _ints(self.im_dim),
-                                              self.nzl, self.nyl, self.rank, self.dev, st)
+                                              self.nzl, self.nzp, self.nyl, self.rank, self.dev, st)
 
     def phase_z(self, st):
-        self._lib.fcb200_slab_z_fused_peer(_p(self.buf_b), _p(self.H), _p(self.peer_recv), _ints(self.im_dim), self.nzl,
+        self._lib.fcb200_slab_z_fused_peer(_p(self.buf_b), _p(self.H), _p(self.peer_recv), _ints(self.im_dim), self.nzp,
                                            self.nyl, self.rank, self.dev, st)
 
     def phase_inverse(self, real_slab, st):
         self._lib.fcb200_slab_yx_inverse(_p(self.buf_a), _p(self.zslab), _p(real_slab), _ints(self.im_dim), self.nzl,
-                                         self.nyl, self.dev, st)
+                                         self.nzp, self.nyl, self.dev, st)
 
     def convolve(self, real_slab, stream=0):
         st = ctypes.c_void_p(int(stream))

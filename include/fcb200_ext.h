@@ -76,24 +76,26 @@ FUNCTION_PREFIX int fcb200_profile_read(float* ms_sum, long long* counts, int n)
 
 /* ---- slab-decomposed single volume (one process per GPU; the transposes between the two
  * decompositions are done by the caller, e.g. NCCL all-to-all) -----------------------------------
- * A rank owns nzl consecutive z planes of the real volume [d2][d1][d0] and, after the exchange,
- * nyl consecutive ky rows of every plane (d1 % nyl == 0, P = d1 / nyl ranks).  All pointers are
- * DEVICE pointers; everything is enqueued on `stream` without host synchronisation.
+ * Rank g of P owns the z planes [g*nzp, g*nzp + nzl) of the real volume [d2][d1][d0] and, after the exchange,
+ * the ky rows [g*nyl, g*nyl + rows) of every plane, with the block pitches nzp = ceil(d2/P) and nyl = ceil(d1/P)
+ * equal on all ranks.  Extents need not be divisible by P (ragged slabs): the last rank then owns fewer planes
+ * (nzl < nzp) and fewer rows; the pad rows / planes of its blocks are carried along and never read back.
+ * All pointers are DEVICE pointers; everything is enqueued on `stream` without host synchronisation.
  *   real slab           [nzl][d1][d0]   float
  *   z-slab spectrum     [nzl][d1][xcp]  complex (xcp = fcb200_spectrum_pitch(d0)), scratch for the passes
- *   exchange buffer     [P][nzl][nyl][xcp] complex: block p goes to / comes from rank p
- *   y-slab spectrum     [d2][nyl][xcp]  complex
+ *   exchange buffer     [P][nzp][nyl][xcp] complex: block p goes to / comes from rank p
+ *   y-slab spectrum     [P*nzp][nyl][xcp] complex, planes 0..d2-1 valid
  * fcb200_slab_xy_forward : x + y forward passes; the y pass writes the exchange (send) buffer directly.
  * fcb200_slab_z_fused    : forward z, multiply by the PSF-spectrum slab and 1/N, inverse z, in place.
  * fcb200_slab_yx_inverse : y + x inverse passes; the y pass reads the exchange (receive) buffer directly.
- * fcb200_slab_psf        : the rank's y-slab [y0, y0+nyl) of the PSF spectrum (placement fused, pruned);
+ * fcb200_slab_psf        : the rank's y-slab [y0, min(y0+nyl, d1)) of the PSF spectrum, row pitch nyl (placement fused, pruned);
  *                          scratch must hold fcb200_slab_psf_scratch_elems() complex values. */
 FUNCTION_PREFIX void fcb200_slab_xy_forward(const imageType* real_slab, float* zslab_spec, float* send, const int* imDim,
-                                           int nzl, int nyl, int devCUDA, void* stream);
+                                           int nzl, int nzp, int nyl, int devCUDA, void* stream);
 FUNCTION_PREFIX void fcb200_slab_z_fused(float* yslab_spec, const float* H_yslab, const int* imDim, int nyl, int devCUDA,
                                         void* stream);
 FUNCTION_PREFIX void fcb200_slab_yx_inverse(const float* recv, float* zslab_spec, imageType* real_slab, const int* imDim,
-                                           int nzl, int nyl, int devCUDA, void* stream);
+                                           int nzl, int nzp, int nyl, int devCUDA, void* stream);
 /* Batch of n independent volumes of one shape convolved in place with ONE PSF (the multi-view deconvolution /
  * BASELINE config 4 pattern: reference callers loop over convolution3DfftCUDAInPlace, src/convolution3Dfft.h:56).
  * ims[b]: host pointers (pinned, registered or pageable) or device pointers on devCUDA, all of one kind.
@@ -104,17 +106,18 @@ FUNCTION_PREFIX void fcb200_convolve_batch(imageType* const* ims, int n, const i
 
 /* Fused compute + exchange over NVLink / NVSwitch peer memory (no NCCL on the data path):
  * fcb200_slab_xy_forward_peer : like fcb200_slab_xy_forward, but the y pass stores every output row straight
- *     into the y-slab buffer [d2][nyl][xcp] of the rank that owns it; peer_yslabs is a DEVICE array of P
+ *     into the y-slab buffer [P*nzp][nyl][xcp] of the rank that owns it; peer_yslabs is a DEVICE array of P
  *     pointers (entry p = rank p's y-slab buffer as mapped in this process, own entry included).
  * fcb200_slab_z_fused_peer    : like fcb200_slab_z_fused, but the last inverse stage stores every output plane
- *     straight into its owner's receive buffer [P][nzl][nyl][xcp] (block `rank`); peer_recv as above.
+ *     straight into its owner's receive buffer [P][nzp][nyl][xcp] (block `rank`); peer_recv as above.
  * The caller separates the phases with a stream-ordered barrier across ranks.
  * fcb200_device_malloc / fcb200_ipc_*: plain cudaMalloc'ed buffers and CUDA IPC handles (64 bytes) so that
  * one-process-per-GPU callers can map each other's exchange buffers. */
 FUNCTION_PREFIX void fcb200_slab_xy_forward_peer(const imageType* real_slab, float* zslab_spec, void* const* peer_yslabs,
-                                                const int* imDim, int nzl, int nyl, int rank, int devCUDA, void* stream);
+                                                const int* imDim, int nzl, int nzp, int nyl, int rank, int devCUDA,
+                                                void* stream);
 FUNCTION_PREFIX void fcb200_slab_z_fused_peer(float* yslab_spec, const float* H_yslab, void* const* peer_recv,
-                                             const int* imDim, int nzl, int nyl, int rank, int devCUDA, void* stream);
+                                             const int* imDim, int nzp, int nyl, int rank, int devCUDA, void* stream);
 FUNCTION_PREFIX void* fcb200_device_malloc(long long bytes, int devCUDA);
 FUNCTION_PREFIX void fcb200_device_free(void* p, int devCUDA);
 FUNCTION_PREFIX void fcb200_ipc_get_handle(void* dev_ptr, char* handle64);

@@ -37,28 +37,29 @@ class ModelPasses:
     def _c(self, buf, shape):
         return torch.view_as_complex(buf.view(*shape, 2))
 
-    def xy_forward(self, real_slab, zslab, send, im_dim, nzl, nyl, dev, st):
+    def xy_forward(self, real_slab, zslab, send, im_dim, nzl, nzp, nyl, dev, st):
         d0, d1, d2 = im_dim
-        xc, xcp, P = d0 // 2 + 1, self.spectrum_pitch(d0), d1 // nyl
+        xc, xcp, P = d0 // 2 + 1, self.spectrum_pitch(d0), -(-d1 // nyl)
         spec = torch.fft.fft(torch.fft.rfft(real_slab.view(nzl, d1, d0).double(), dim=2), dim=1)   # [nzl][d1][xc]
-        out = self._c(send, (P, nzl, nyl, xcp))
-        out.zero_()
+        out = self._c(send, (P, nzp, nyl, xcp))
+        out.fill_(float("nan"))          # pad planes / rows of ragged blocks must never reach the result
         for p in range(P):
-            out[p, :, :, :xc] = spec[:, p * nyl:(p + 1) * nyl, :].to(torch.complex64)
+            rows = min(nyl, d1 - p * nyl)
+            out[p, :nzl, :rows, :xc] = spec[:, p * nyl:p * nyl + rows, :].to(torch.complex64)
 
     def z_fused(self, yslab, H, im_dim, nyl, dev, st):
         d0, d1, d2 = im_dim
         xcp = self.spectrum_pitch(d0)
-        y = self._c(yslab, (d2, nyl, xcp))
-        h = self._c(H, (d2, nyl, xcp))
+        y = self._c(yslab[:d2 * nyl * xcp * 2], (d2, nyl, xcp))     # the buffer holds P*nzp >= d2 planes
+        h = self._c(H[:d2 * nyl * xcp * 2], (d2, nyl, xcp))
         z = torch.fft.fft(y.to(torch.complex128), dim=0) * h.to(torch.complex128) / float(d0 * d1 * d2)
         y.copy_((torch.fft.ifft(z, dim=0) * d2).to(torch.complex64))       # unnormalised inverse, like the kernels
 
-    def yx_inverse(self, recv, zslab, real_slab, im_dim, nzl, nyl, dev, st):
+    def yx_inverse(self, recv, zslab, real_slab, im_dim, nzl, nzp, nyl, dev, st):
         d0, d1, d2 = im_dim
-        xc, xcp, P = d0 // 2 + 1, self.spectrum_pitch(d0), d1 // nyl
-        blocks = self._c(recv, (P, nzl, nyl, xcp)).to(torch.complex128)
-        spec = torch.cat([blocks[p] for p in range(P)], dim=1)[:, :, :xc]                           # [nzl][d1][xc]
+        xc, xcp, P = d0 // 2 + 1, self.spectrum_pitch(d0), -(-d1 // nyl)
+        blocks = self._c(recv, (P, nzp, nyl, xcp)).to(torch.complex128)
+        spec = torch.cat([blocks[p, :nzl] for p in range(P)], dim=1)[:, :d1, :xc]                   # [nzl][d1][xc]
         out = torch.fft.irfft(torch.fft.ifft(spec, dim=1) * d1, n=d0, dim=2) * d0                   # unnormalised
         real_slab.copy_(out.reshape(-1).float())
 
@@ -81,16 +82,19 @@ def _worker(rank, world, port, im_dim, k_dim, out):
     S = fc_oracle.place_psf(k, k_dim, im_dim).reshape(d2, d1, d0)
     Hfull = torch.fft.fft(torch.fft.fft(torch.fft.rfft(torch.from_numpy(S), dim=2), dim=1), dim=0)
     xc = d0 // 2 + 1
-    h = torch.view_as_complex(conv.H.view(d2, conv.nyl, conv.xcp, 2))
+    h = torch.view_as_complex(conv.H[:d2 * conv.nyl * conv.xcp * 2].view(d2, conv.nyl, conv.xcp, 2))
     h.zero_()
-    h[:, :, :xc] = Hfull[:, rank * conv.nyl:(rank + 1) * conv.nyl, :].to(torch.complex64)
+    h[:, :conv.ny_here, :xc] = Hfull[:, rank * conv.nyl:rank * conv.nyl + conv.ny_here, :].to(torch.complex64)
     mine = torch.from_numpy(im.copy())
     my_slab = conv.slab_of(mine).clone()
+    assert my_slab.numel() == conv.nzl * d1 * d0
     conv.convolve(my_slab)
-    parts = [torch.empty_like(my_slab) for _ in range(world)]
-    dist.all_gather(parts, my_slab)
+    padded = torch.zeros(conv.nzp * d1 * d0)            # all_gather needs equal sizes: ragged slabs are padded
+    padded[:my_slab.numel()] = my_slab
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
     if rank == 0:
-        got = torch.cat(parts).numpy()
+        got = torch.cat(parts).numpy()[:d0 * d1 * d2]
         want = fc_oracle.convolve_inplace_ref(im, im_dim, k, k_dim)
         out.put((float(np.abs(got - want).max() / np.abs(want).max()),
                  float(np.linalg.norm(got - want) / np.linalg.norm(want))))
@@ -98,7 +102,8 @@ def _worker(rank, world, port, im_dim, k_dim, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("im_dim,k_dim", [((16, 12, 8), (3, 5, 3)), ((10, 8, 6), (3, 3, 3))])
+@pytest.mark.parametrize("im_dim,k_dim", [((16, 12, 8), (3, 5, 3)), ((10, 8, 6), (3, 3, 3)),
+                                          ((12, 9, 7), (3, 3, 3)), ((8, 5, 6), (3, 3, 1))])     # ragged: 9, 7, 5 over 2 ranks
 def test_two_rank_slab_schedule_matches_oracle(im_dim, k_dim):
     world = 2
     ctx = mp.get_context("spawn")
@@ -114,8 +119,16 @@ def test_two_rank_slab_schedule_matches_oracle(im_dim, k_dim):
     assert max_err <= 1e-4 and l2 <= 1e-5
 
 
-def test_slab_rejects_indivisible_extents():
+def test_slab_ownership_ragged_and_rejected_extents():
     sys.path.insert(0, ROOT)
     from fourierconvolutioncudalib_b200 import slab
-    with pytest.raises(ValueError):
-        slab.SlabConvolver((16, 9, 8), (3, 3, 3), 0, 2, 0, None, passes=ModelPasses(2), device="cpu")
+    # 1125 planes / 2160 rows over 8 ranks (BASELINE config 5, caller-padded): pitch 141 / 270, last rank 138 planes
+    convs = [slab.SlabConvolver((16, 2160, 1125), (3, 3, 3), r, 8, 0, None, passes=ModelPasses(8), device="meta")
+             for r in range(8)]
+    assert [c.nzp for c in convs] == [141] * 8 and [c.nzl for c in convs] == [141] * 7 + [138]
+    assert [c.nyl for c in convs] == [270] * 8 and sum(c.ny_here for c in convs) == 2160
+    assert sum(c.nzl for c in convs) == 1125
+    with pytest.raises(ValueError):      # 3 rows over 4 ranks: the last rank would own nothing
+        slab.SlabConvolver((16, 3, 8), (3, 3, 3), 0, 4, 0, None, passes=ModelPasses(4), device="cpu")
+    with pytest.raises(ValueError):      # 9 planes over 8 ranks: pitch 2 -> ranks 5..7 would own nothing
+        slab.SlabConvolver((16, 16, 9), (3, 3, 3), 0, 8, 0, None, passes=ModelPasses(8), device="cpu")

@@ -14,7 +14,11 @@ def gaussian_psf(kDim):
 
 @pytest.mark.parametrize("imDim,kDim,world", [((64, 64, 64), (7, 7, 7), 2), ((128, 96, 64), (9, 5, 7), 4),
                                               ((70, 60, 48), (5, 5, 9), 2), ((256, 256, 64), (15, 15, 15), 8),
-                                              ((64, 2048, 64), (5, 7, 5), 2)])
+                                              ((64, 2048, 64), (5, 7, 5), 2),
+                                              # ragged slabs: extents not divisible by the number of ranks
+                                              ((64, 70, 45), (5, 5, 5), 2), ((64, 90, 50), (5, 5, 9), 4),
+                                              ((128, 100, 75), (7, 5, 5), 8), ((64, 64, 75), (5, 5, 5), 8),
+                                              ((72, 135, 90), (5, 5, 5), 4)])
 def test_emulated_ranks_match_single_gpu(fc, dev, imDim, kDim, world):
     import torch
     from fourierconvolutioncudalib_b200 import slab
@@ -42,7 +46,11 @@ def test_emulated_ranks_match_single_gpu(fc, dev, imDim, kDim, world):
 
 @pytest.mark.parametrize("imDim,kDim,world", [((64, 64, 64), (7, 7, 7), 2), ((128, 96, 64), (9, 5, 7), 4),
                                               ((70, 60, 48), (5, 5, 9), 2), ((256, 256, 64), (15, 15, 15), 8),
-                                              ((64, 2048, 64), (5, 7, 5), 2)])
+                                              ((64, 2048, 64), (5, 7, 5), 2),
+                                              # ragged slabs: extents not divisible by the number of ranks
+                                              ((64, 70, 45), (5, 5, 5), 2), ((64, 90, 50), (5, 5, 9), 4),
+                                              ((128, 100, 75), (7, 5, 5), 8), ((64, 64, 75), (5, 5, 5), 8),
+                                              ((72, 135, 90), (5, 5, 5), 4)])
 @pytest.mark.parametrize("raw", [False, True])
 def test_peer_store_exchange_matches_alltoall(fc, dev, imDim, kDim, world, raw):
     """fused compute+exchange (kernels store into the peers' buffers through a pointer table) == the

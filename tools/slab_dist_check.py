@@ -28,7 +28,6 @@ device = torch.device(f"cuda:{local}")
 dist.init_process_group("nccl", device_id=device)
 
 d0, d1, d2 = im_dim
-nzl = d2 // world
 psf = torch.from_numpy(bench.gaussian_psf(k_dim).reshape(-1)).to(device)
 mode = os.environ.get("SLAB_MODE", "nccl")      # nccl: all-to-all; peer: kernels store into the peers' buffers
 if mode == "peer":
@@ -39,15 +38,18 @@ else:
 conv.prepare_psf(psf)
 gen = torch.Generator(device=device)
 gen.manual_seed(1234 + rank)
+nzl, nzp = conv.nzl, conv.nzp                   # ragged slabs: the last rank owns fewer planes than the pitch
 my = torch.rand(nzl * d1 * d0, device=device, generator=gen) * 1000
 err = None
 if check:
     # assemble the full volume on every rank, convolve it alone, compare this rank's slab
-    parts = [torch.empty_like(my) for _ in range(world)]
-    dist.all_gather(parts, my)
-    full = torch.cat(parts)
+    padded = torch.zeros(nzp * d1 * d0, device=device)
+    padded[:my.numel()] = my
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    full = torch.cat(parts)[:d0 * d1 * d2].contiguous()
     fc.convolution3DfftCUDAInPlace(full, im_dim, psf, k_dim, local)
-    want = full[rank * my.numel():(rank + 1) * my.numel()].clone()
+    want = full[rank * nzp * d1 * d0:rank * nzp * d1 * d0 + my.numel()].clone()
     got = my.clone()
     conv.convolve(got)
     torch.cuda.synchronize()
