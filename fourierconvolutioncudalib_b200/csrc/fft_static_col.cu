@@ -251,6 +251,31 @@ bool run_col_pipe(const ColArgs& a, int mode, long long ngroups, cudaStream_t st
     return true;
 }
 
+// modes 0 / 1 without row mask only (what try_pipe_plain needs): two kernels per configuration
+template <class P, int THREADS, int NBUF>
+bool run_col_pipe_plain(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
+{
+    const int tpg = (a.rowLen + 15) / 16;
+    const long long total = ngroups * tpg;
+    if (total == 0) return true;
+    if (mode > 1 || a.rowMask) return false;
+    const size_t tile = (size_t)P::L * 8 * sizeof(float4);
+    const size_t smem = (size_t)P::L * (sizeof(float4) + sizeof(int)) + (size_t)NBUF * tile;
+    if (smem > (size_t)kMaxDynSmem) return false;
+    if (total > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
+    auto go = [&](auto kernel) {
+        FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
+        const int grid = (int)std::min<long long>(total, (long long)sm_count() * std::max(1, per_sm));
+        kernel<<<grid, THREADS, smem, st>>>(a, tpg, (int)total);
+        FC_CUDA_KERNEL();
+    };
+    if (mode == 0) go(col_pipe_kernel<0, P, THREADS, NBUF, false>);
+    else go(col_pipe_kernel<1, P, THREADS, NBUF, false>);
+    return true;
+}
+
 template <typename K>
 void launch(K kernel, long long grid, int threads, size_t smem, cudaStream_t st, const ColArgs& a, int tpg)
 {
@@ -466,6 +491,15 @@ static bool try_pipe_plain(const ColArgs& a, int mode, long long ngroups, cudaSt
     const long long total = ngroups * ((a.rowLen + 15) / 16);
     if (total < 4LL * sm_count()) return false;   // too few tiles to fill the pipeline
     if (plan_matches<P512>(a.P)) return run_col_pipe<P512, 512, 3>(a, mode, ngroups, st);
+    // shorter pencils: TWO tile buffers and two (or three) CTAs per SM beat three buffers in one CTA
+    // (384^3 y passes 0.110 -> 0.097 ms, profiles/r01_sweep_pipe384.jsonl); FCB200_PIPE_SHORT=0 turns these off
+    static const int pshort = env_int("FCB200_PIPE_SHORT", 1);
+    if (pshort == 0) return false;
+    if (plan_matches<P384>(a.P)) return run_col_pipe_plain<P384, 192, 2>(a, mode, ngroups, st);
+    // measured on the caller-padded grids (profiles/r01_sweep_pipe_short.jsonl): 560: 0.181 -> 0.164 ms, 300: 0.068 -> 0.056 ms;
+    // 420 (0.164 -> 0.183) and 448 / 256 (unchanged) stay on the one-tile-per-CTA kernels
+    if (plan_matches<P560>(a.P)) return run_col_pipe_plain<P560, 320, 3>(a, mode, ngroups, st);
+    if (plan_matches<P300>(a.P)) return run_col_pipe_plain<P300, 256, 2>(a, mode, ngroups, st);
     return false;
 }
 

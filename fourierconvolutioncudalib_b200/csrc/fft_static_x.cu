@@ -101,8 +101,10 @@ static bool try_xrowg(const XArgs& a, bool inverse, cudaStream_t st)
 
 static bool try_xrowg_all(const XArgs& a, bool inverse, cudaStream_t st)
 {
-    static const bool x384 = env_int("FCB200_XROW384", 1) != 0;
-    if (x384 && try_xrowg<24, 8, 1, 128>(a, inverse, st)) return true;   // nx = 384
+    static const int x384 = env_int("FCB200_XROW384", 1);
+    if (x384 == 64 && try_xrowg<24, 8, 1, 64>(a, inverse, st)) return true;
+    if (x384 == 256 && try_xrowg<24, 8, 1, 256>(a, inverse, st)) return true;
+    if (x384 != 0 && try_xrowg<24, 8, 1, 128>(a, inverse, st)) return true;   // nx = 384
     return try_xrowg<16, 8, 1, 64>(a, inverse, st) ||      // nx = 256
            try_xrowg<16, 4, 8, 128>(a, inverse, st) ||     // nx = 1024 (x-axis planning style)
            try_xrowg<8, 8, 8, 128>(a, inverse, st) ||
