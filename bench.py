@@ -119,10 +119,17 @@ def ncu_traffic(pass_name):
     return None
 
 
+NUMA_BINDING = None
+
+
 def dist_setup(n_gpus):
     import torch
     from fourierconvolutioncudalib_b200 import tiles
     rank, local, world = tiles.rank_info()
+    # before any pinned allocation: host threads of this rank run next to its GPU (FCB200_BENCH_NUMA=0 turns it off)
+    global NUMA_BINDING
+    if os.environ.get("FCB200_BENCH_NUMA", "1") != "0":
+        NUMA_BINDING = tiles.bind_to_gpu_numa_node(local)
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -280,7 +287,8 @@ def run_ours(args):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, device) / e2e_steps
     e2e = {"value": world * n / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": 4 * n + 4 * psf.size, "d2h_bytes_per_step": 4 * n,
-           "api": "convolution3DfftCUDAInPlace(host pinned buffers)", "checksum": checksum}
+           "api": "convolution3DfftCUDAInPlace(host pinned buffers)", "checksum": checksum,
+           "numa_binding": ({"node": NUMA_BINDING[0], "cpus": NUMA_BINDING[1]} if NUMA_BINDING else None)}
 
     # ---- the same tiles as a pipelined batch (fcb200_convolve_batch: upload b+1 | convolve b | download b-1),
     # reported next to `e2e`, not instead of it: the reference ABI is one volume per call

@@ -123,10 +123,12 @@ __device__ __forceinline__ void smid_fused_sm(const float4* __restrict__ hs, flo
     }
 }
 
-template <int MODE, class P, int THREADS, int NBUF, bool MASKED>
+// TXP: column pairs per tile row (8 = 128-byte rows; 4 = 64-byte rows, half the tile size: more CTAs per SM)
+template <int MODE, class P, int THREADS, int NBUF, bool MASKED, int TXP = 8>
 __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int tilesPerGroup, int totalTiles)
 {
-    constexpr int L = P::L, NW = THREADS / 8, TILE = L * 8;
+    constexpr int L = P::L, NW = THREADS / TXP, TILE = L * TXP;
+    static_assert(MODE != 2 || TXP == 8, "the fused mode is written for 128-byte tile rows");
     extern __shared__ float4 smem[];
     float4* tw = smem;
     float4* dbuf = tw + L;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int til
     int* pos_s = reinterpret_cast<int*>(hbuf + (MODE == 2 ? (size_t)NBUF * TILE : 0));   // [L] digit-reversal table
 
     const int t = threadIdx.x;
-    const int cp = t & 7, w = t >> 3;
+    const int cp = t % TXP, w = t / TXP;
     const size_t stride = (size_t)a.stride;
 
     load_twiddles(tw, a.P.tw, L);
@@ -147,8 +149,8 @@ __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int til
         const int gi = tile / tilesPerGroup;
         const int tt = tile - gi * tilesPerGroup;
         const long long group = a.groupList ? (long long)a.groupList[gi] : (long long)gi;
-        const int col0 = tt * 16;
-        const int npairs = min(8, (a.rowLen - col0) >> 1);
+        const int col0 = tt * 2 * TXP;
+        const int npairs = min(TXP, (a.rowLen - col0) >> 1);
         off = (size_t)group * a.groupStride + col0 + 2 * cp;
         return cp < npairs;
     };
@@ -161,8 +163,8 @@ __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int til
             for (int r = w; r < L; r += NW) {
                 const int p = (MODE == 2) ? pos_s[r] : r;   // H: row k is needed at position pos[k]
                 const int pd = r;
-                if (MASKED && a.rowMask[r] == 0) d[pd * 8] = make_float4(0.f, 0.f, 0.f, 0.f);
-                else cpa16(d + pd * 8, src + (size_t)r * stride);
+                if (MASKED && a.rowMask[r] == 0) d[pd * TXP] = make_float4(0.f, 0.f, 0.f, 0.f);
+                else cpa16(d + pd * TXP, src + (size_t)r * stride);
                 if (MODE == 2) cpa16(hbuf + (size_t)slot * TILE + p * 8 + cp, a.H + off + (size_t)r * stride);
             }
         }
@@ -183,32 +185,36 @@ __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int til
         float2* base = a.data + off;
         // MODE 1 (plain inverse) runs the FORWARD stage sequence with re/im exchanged on the way in and out
         {
-            if (active) sstage<P::R0, L, L, NW, false, 8, MODE == 1>(sm, tw, cp, w);
+            if (active) sstage<P::R0, L, L, NW, false, TXP, MODE == 1>(sm, tw, cp, w);
             __syncthreads();
             if constexpr (P::ns >= 3) {
-                if (active) sstage<P::R1, L, L / P::R0, NW, false>(sm, tw, cp, w);
+                if (active) sstage<P::R1, L, L / P::R0, NW, false, TXP>(sm, tw, cp, w);
                 __syncthreads();
             }
             if constexpr (P::ns >= 4) {
-                if (active) sstage<P::R2, L, L / (P::R0 * P::R1), NW, false>(sm, tw, cp, w);
+                if (active) sstage<P::R2, L, L / (P::R0 * P::R1), NW, false, TXP>(sm, tw, cp, w);
                 __syncthreads();
             }
             if (MODE != 2) {
-                if (active) slast_fwd<P::RL, L, NW, 8, MODE == 1>(RowsLinear{base, stride}, sm, a.P.rev, cp, w);
+                if (active) slast_fwd<P::RL, L, NW, TXP, MODE == 1>(RowsLinear{base, stride}, sm, a.P.rev, cp, w);
                 continue;
             }
-            if (active) smid_fused_sm<P::RL, L, NW>(hbuf + (size_t)slot * TILE, sm, cp, w, a.scale);
-            __syncthreads();
+            if constexpr (MODE == 2) {
+                if (active) smid_fused_sm<P::RL, L, NW>(hbuf + (size_t)slot * TILE, sm, cp, w, a.scale);
+                __syncthreads();
+            }
         }
-        if constexpr (P::ns >= 4) {
-            if (active) sstage<P::R2, L, P::R2 * P::R3, NW, true>(sm, tw, cp, w);
-            __syncthreads();
+        if constexpr (MODE == 2) {
+            if constexpr (P::ns >= 4) {
+                if (active) sstage<P::R2, L, P::R2 * P::R3, NW, true>(sm, tw, cp, w);
+                __syncthreads();
+            }
+            if constexpr (P::ns >= 3) {
+                if (active) sstage<P::R1, L, P::R1 * P::R2 * P::R3, NW, true>(sm, tw, cp, w);
+                __syncthreads();
+            }
+            if (active) slast_inv<P::R0, L, NW>(base, stride, sm, tw, cp, w);
         }
-        if constexpr (P::ns >= 3) {
-            if (active) sstage<P::R1, L, P::R1 * P::R2 * P::R3, NW, true>(sm, tw, cp, w);
-            __syncthreads();
-        }
-        if (active) slast_inv<P::R0, L, NW>(base, stride, sm, tw, cp, w);
     }
     cpa_wait<0>();
 }
@@ -252,14 +258,14 @@ bool run_col_pipe(const ColArgs& a, int mode, long long ngroups, cudaStream_t st
 }
 
 // modes 0 / 1 without row mask only (what try_pipe_plain needs): two kernels per configuration
-template <class P, int THREADS, int NBUF>
+template <class P, int THREADS, int NBUF, int TXP = 8>
 bool run_col_pipe_plain(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
-    const int tpg = (a.rowLen + 15) / 16;
+    const int tpg = (a.rowLen + 2 * TXP - 1) / (2 * TXP);
     const long long total = ngroups * tpg;
     if (total == 0) return true;
     if (mode > 1 || a.rowMask) return false;
-    const size_t tile = (size_t)P::L * 8 * sizeof(float4);
+    const size_t tile = (size_t)P::L * TXP * sizeof(float4);
     const size_t smem = (size_t)P::L * (sizeof(float4) + sizeof(int)) + (size_t)NBUF * tile;
     if (smem > (size_t)kMaxDynSmem) return false;
     if (total > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
@@ -271,8 +277,8 @@ bool run_col_pipe_plain(const ColArgs& a, int mode, long long ngroups, cudaStrea
         kernel<<<grid, THREADS, smem, st>>>(a, tpg, (int)total);
         FC_CUDA_KERNEL();
     };
-    if (mode == 0) go(col_pipe_kernel<0, P, THREADS, NBUF, false>);
-    else go(col_pipe_kernel<1, P, THREADS, NBUF, false>);
+    if (mode == 0) go(col_pipe_kernel<0, P, THREADS, NBUF, false, TXP>);
+    else go(col_pipe_kernel<1, P, THREADS, NBUF, false, TXP>);
     return true;
 }
 
@@ -490,6 +496,12 @@ static bool try_pipe_plain(const ColArgs& a, int mode, long long ngroups, cudaSt
     if (!on || mode == 2 || a.split || a.splitPeers || a.rowMask || a.groupList) return false;
     const long long total = ngroups * ((a.rowLen + 15) / 16);
     if (total < 4LL * sm_count()) return false;   // too few tiles to fill the pipeline
+    static const int p512 = env_int("FCB200_PIPE512", 0);   // experiments: 64-byte tile rows, more CTAs per SM
+    if (plan_matches<P512>(a.P)) {
+        if (p512 == 1) return run_col_pipe_plain<P512, 256, 3, 4>(a, mode, ngroups, st);
+        if (p512 == 2) return run_col_pipe_plain<P512, 256, 2, 4>(a, mode, ngroups, st);
+        if (p512 == 3) return run_col_pipe_plain<P512, 512, 3, 4>(a, mode, ngroups, st);
+    }
     if (plan_matches<P512>(a.P)) return run_col_pipe<P512, 512, 3>(a, mode, ngroups, st);
     // shorter pencils: TWO tile buffers and two (or three) CTAs per SM beat three buffers in one CTA
     // (384^3 y passes 0.110 -> 0.097 ms, profiles/r01_sweep_pipe384.jsonl); FCB200_PIPE_SHORT=0 turns these off

@@ -18,6 +18,52 @@ def rank_info():
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
+def parse_cpulist(text):
+    """'0-3,8-11' (sysfs cpulist format) -> [0, 1, 2, 3, 8, 9, 10, 11]"""
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(pci_bus_id, sysfs="/sys"):
+    """NUMA node of the GPU with PCI address 'dddd:bb:dd.f' (sysfs), or None when the platform does not say"""
+    try:
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", pci_bus_id.lower(), "numa_node")).read())
+    except (OSError, ValueError):
+        return None
+    return node if node >= 0 else None
+
+
+def bind_to_gpu_numa_node(local_rank, sysfs="/sys"):
+    """One process per GPU: run this rank's host threads (and therefore first-touch its pinned staging buffers) on the
+    CPUs of the NUMA node its GPU hangs off, so that the 2 x volume bytes of every host-pointer call do not cross the
+    socket interconnect and the ranks spread over all memory controllers.  Returns (node, n_cpus) or None when
+    nothing was changed (no sysfs information, single node, affinity not permitted)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus_id = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+    except Exception:
+        return None
+    node = gpu_numa_node(bus_id, sysfs)
+    if node is None:
+        return None
+    try:
+        cpus = parse_cpulist(open(os.path.join(sysfs, f"devices/system/node/node{node}/cpulist")).read())
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+    except (OSError, ValueError, AttributeError):
+        return None
+    return node, len(cpus)
+
+
 def max_over_ranks(value, device=None):
     """max of a python float over all ranks (identity when torch.distributed is not initialised)"""
     import torch

@@ -66,3 +66,19 @@ def test_assign_tiles_single_rank_and_errors():
     assert tiles.assign_tiles(3, 8, 5) == []
     with pytest.raises(ValueError):
         tiles.assign_tiles(3, 2, 2)
+
+
+def test_numa_helpers(tmp_path):
+    """host-side pieces of tiles.bind_to_gpu_numa_node (sysfs parsing; no GPU, no affinity change)"""
+    sys.path.insert(0, ROOT)
+    from fourierconvolutioncudalib_b200 import tiles
+    assert tiles.parse_cpulist("0-3,8-11\n") == [0, 1, 2, 3, 8, 9, 10, 11]
+    assert tiles.parse_cpulist("5") == [5] and tiles.parse_cpulist("") == []
+    dev = tmp_path / "bus" / "pci" / "devices" / "0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    assert tiles.gpu_numa_node("0000:1B:00.0", str(tmp_path)) == 1
+    (dev / "numa_node").write_text("-1\n")
+    assert tiles.gpu_numa_node("0000:1b:00.0", str(tmp_path)) is None      # platform does not say
+    assert tiles.gpu_numa_node("0000:99:00.0", str(tmp_path)) is None
+    assert tiles.bind_to_gpu_numa_node(0, str(tmp_path)) is None           # no CUDA device here: nothing changes
