@@ -553,7 +553,13 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
         else run_col<P256b, 128, 2, 8, 3>(a, mode, ngroups, st);
     }
     else if (plan_matches<P560>(a.P)) run_col<P560, 320, 1, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P448>(a.P)) run_col<P448, 512, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P448>(a.P)) {
+        // fused pass: 256-thread CTAs, two PSF-spectrum batches in flight (420x420x448: 0.365 -> 0.219 ms,
+        // profiles/r01_sweep_z448.jsonl); the plain passes keep 512 threads
+        if (mode == 2) run_col<P448, 256, 2, 8, 4>(a, mode, ngroups, st);
+        else run_col<P448, 512, 1, 8, 3>(a, mode, ngroups, st);
+    }
+    // 420 and 300: other CTA sizes / load batches were measured and lost (profiles/r01_sweep_c420.jsonl, r01_sweep_z300.jsonl)
     else if (plan_matches<P420>(a.P)) run_col<P420, 384, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P300>(a.P)) run_col<P300, 256, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P1024>(a.P)) {
