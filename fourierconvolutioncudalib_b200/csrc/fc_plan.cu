@@ -48,12 +48,26 @@ std::vector<int> factorize(int L, bool* generic, int style)
     } else {
         for (int i = 0; i < 4 && pow2_plan[e][i]; ++i) out.push_back(pow2_plan[e][i]);
     }
-    static const int odd_fast[] = {3, 5, 7};
-    for (int r : odd_fast)
-        while (n > 1 && n % r == 0) {
-            out.push_back(r);
-            n /= r;
-        }
+    // odd 7-smooth part.  Up to four stages in total: one register stage per prime (3, 5, 7).  Lengths that would
+    // need FIVE or more shared-memory round trips (270 = 2*3*3*3*5, 1125, 2160 ...) pair their small primes into
+    // composite register stages instead (radix 15 = 3*5, 9 = 3*3; a single leftover 3 or 5 joins a trailing radix
+    // 2 / 4 -> 6, 12, 10): 270 = (2,15,9), 1125 = (15,15,5), 2160 = (16,15,9).  Measured (profiles/r01_notes.md):
+    // 270^3 0.438 -> 0.390 ms, whereas the four-stage lengths 300 / 420 lose with a radix-15 stage and keep primes.
+    int n3 = 0, n5 = 0, n7 = 0;
+    while (n % 3 == 0) { n /= 3; ++n3; }
+    while (n % 5 == 0) { n /= 5; ++n5; }
+    while (n % 7 == 0) { n /= 7; ++n7; }
+    if ((int)out.size() + n3 + n5 + n7 > 4) {
+        std::vector<int> comp;
+        while (n3 >= 1 && n5 >= 1) { comp.push_back(15); --n3; --n5; }
+        if ((n3 & 1) && !out.empty() && (out.back() == 2 || out.back() == 4)) { out.back() *= 3; --n3; }
+        while (n3 >= 2) { comp.push_back(9); n3 -= 2; }
+        if (n5 >= 1 && !out.empty() && out.back() == 2) { out.back() = 10; --n5; }
+        out.insert(out.end(), comp.begin(), comp.end());
+    }
+    out.insert(out.end(), (size_t)n3, 3);
+    out.insert(out.end(), (size_t)n5, 5);
+    out.insert(out.end(), (size_t)n7, 7);
     for (int p = 11; n > 1; p += 2) {
         if ((long long)p * p > n) p = n;  // remaining cofactor is prime
         while (n % p == 0) {

@@ -300,6 +300,93 @@ struct Dft<24> {
     }
 };
 
+// ---- composite radices 6, 9, 10, 12, 15 ------------------------------------------------------------------
+// The 7-smooth extents callers pad to (270, 300, 420, 1080, 1125, 2160 ...) have many small odd factors; one
+// register stage per prime would mean four or five shared-memory round trips.  A composite radix A*B runs as
+// Cooley-Tukey inside the registers of one thread: A-point DFTs, constant twiddles w_N^(b c), B-point DFTs.
+//   n = B a + b, k = c + A d:  X[c + A d] = sum_b w_B^(b d) [ w_N^(b c) sum_a x[B a + b] w_A^(a c) ]
+// The roots are compile-time constants (Taylor series evaluated in double by the compiler).
+namespace ctrig {
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double ccos(double x)
+{
+    double t = 1.0, s = 1.0;
+    for (int k = 1; k <= 16; ++k) {
+        t *= -x * x / ((2.0 * k - 1.0) * (2.0 * k));
+        s += t;
+    }
+    return s;
+}
+constexpr double csin(double x)
+{
+    double t = x, s = x;
+    for (int k = 1; k <= 16; ++k) {
+        t *= -x * x / ((2.0 * k) * (2.0 * k + 1.0));
+        s += t;
+    }
+    return s;
+}
+// c[m] - i s[m] = exp(-2 pi i m / N), angle reduced to (-pi, pi]
+template <int N>
+struct Roots {
+    float c[N], s[N];
+    constexpr Roots() : c{}, s{}
+    {
+        for (int m = 0; m < N; ++m) {
+            const int mm = (2 * m > N) ? m - N : m;
+            const double a = 2.0 * kPi * mm / N;
+            c[m] = (float)ccos(a);
+            s[m] = (float)csin(a);
+        }
+    }
+};
+}  // namespace ctrig
+
+template <int A, int B>
+struct DftCT {
+    static constexpr int N = A * B;
+    static __device__ __forceinline__ void run(p2* r, p2* i)
+    {
+        constexpr ctrig::Roots<N> W{};
+        p2 tr[N], ti[N];   // t_b[c] at index B c + b
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            p2 ar[A], ai[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                ar[a] = r[B * a + b];
+                ai[a] = i[B * a + b];
+            }
+            Dft<A>::run(ar, ai);
+#pragma unroll
+            for (int c = 0; c < A; ++c) {
+                if (b * c != 0) {   // (t_r + i t_i) *= (C - i S)
+                    const float C = W.c[(b * c) % N], S = W.s[(b * c) % N];
+                    const p2 nr = pfmas(ai[c], S, pmuls(ar[c], C));
+                    ai[c] = pfmas(ar[c], -S, pmuls(ai[c], C));
+                    ar[c] = nr;
+                }
+                tr[B * c + b] = ar[c];
+                ti[B * c + b] = ai[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < A; ++c) {
+            Dft<B>::run(tr + B * c, ti + B * c);
+#pragma unroll
+            for (int d = 0; d < B; ++d) {
+                r[c + A * d] = tr[B * c + d];
+                i[c + A * d] = ti[B * c + d];
+            }
+        }
+    }
+};
+template <> struct Dft<6> : DftCT<2, 3> {};
+template <> struct Dft<9> : DftCT<3, 3> {};
+template <> struct Dft<10> : DftCT<2, 5> {};
+template <> struct Dft<12> : DftCT<4, 3> {};
+template <> struct Dft<15> : DftCT<3, 5> {};
+
 // Twiddles are kept in shared memory as float4 (c, c, s, s): both packed operands come out of one
 // 128-bit load as aligned register pairs.
 // (xr + i*xi) *= (c + i*s)

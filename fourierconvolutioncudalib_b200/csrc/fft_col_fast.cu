@@ -199,7 +199,12 @@ __device__ __forceinline__ void mid_fused(const float2* __restrict__ hbase, long
         case 3: { constexpr int RR = 3; CALL; } break; \
         case 4: { constexpr int RR = 4; CALL; } break; \
         case 5: { constexpr int RR = 5; CALL; } break; \
+        case 6: { constexpr int RR = 6; CALL; } break; \
         case 7: { constexpr int RR = 7; CALL; } break; \
+        case 9: { constexpr int RR = 9; CALL; } break; \
+        case 10: { constexpr int RR = 10; CALL; } break; \
+        case 12: { constexpr int RR = 12; CALL; } break; \
+        case 15: { constexpr int RR = 15; CALL; } break; \
         case 16: { constexpr int RR = 16; CALL; } break; \
         default: { constexpr int RR = 8; CALL; } break; \
     }

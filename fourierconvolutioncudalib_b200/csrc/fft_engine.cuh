@@ -13,7 +13,7 @@
 // reversal).  Inverse (DIT, stages mirrored) takes that order back to natural order.  Callers map
 // positions to global rows, so natural order in global memory costs nothing for the strided axes.
 //
-// Radices 2,3,4,5,7,8,16 run in registers.  Any other prime factor p runs as a direct O(p) sum per
+// Radices 2,3,4,5,6,7,8,9,10,12,15,16 run in registers (6..15: composite, fft_butterflies.cuh).  Any other prime factor p runs as a direct O(p) sum per
 // output between two tile buffers (ping-pong), so every length the C ABI can receive is supported
 // (the reference's own tests use 79, 109, 173, 37, 23, 53, ... -- SURVEY.md section 4).
 //
@@ -128,7 +128,8 @@ __device__ __forceinline__ void stage_generic(const float4* __restrict__ src, fl
 
 __device__ __forceinline__ bool is_fast_radix(int R)
 {
-    return R == 1 || R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8 || R == 16;
+    return R == 1 || R == 2 || R == 3 || R == 4 || R == 5 || R == 6 || R == 7 || R == 8 || R == 9 || R == 10 || R == 12 ||
+           R == 15 || R == 16;
 }
 
 template <bool INV>
@@ -142,8 +143,13 @@ __device__ __forceinline__ void stage_dispatch(int R, float4*& cur, float4*& oth
             case 3: stage_smem<3, INV>(cur, tw, L, Li, cp, w, W, txp); break;
             case 4: stage_smem<4, INV>(cur, tw, L, Li, cp, w, W, txp); break;
             case 5: stage_smem<5, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 6: stage_smem<6, INV>(cur, tw, L, Li, cp, w, W, txp); break;
             case 7: stage_smem<7, INV>(cur, tw, L, Li, cp, w, W, txp); break;
             case 8: stage_smem<8, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 9: stage_smem<9, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 10: stage_smem<10, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 12: stage_smem<12, INV>(cur, tw, L, Li, cp, w, W, txp); break;
+            case 15: stage_smem<15, INV>(cur, tw, L, Li, cp, w, W, txp); break;
             case 16: stage_smem<16, INV>(cur, tw, L, Li, cp, w, W, txp); break;
             default: stage_generic<INV>(cur, oth, tw, L, Li, R, cp, w, W, txp); break;
         }

@@ -560,6 +560,7 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
         else run_col<P448, 512, 1, 8, 3>(a, mode, ngroups, st);
     }
     // 420 and 300: other CTA sizes / load batches were measured and lost (profiles/r01_sweep_c420.jsonl, r01_sweep_z300.jsonl)
+    else if (plan_matches<P270>(a.P) && env_int("FCB200_S270", 1) != 0) run_col<P270, 256, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P420>(a.P)) run_col<P420, 384, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P300>(a.P)) run_col<P300, 256, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P1024>(a.P)) {

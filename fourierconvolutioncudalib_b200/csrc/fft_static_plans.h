@@ -59,6 +59,7 @@ typedef SPlan<560, 16, 5, 7> P560;
 typedef SPlan<448, 8, 8, 7> P448;
 typedef SPlan<420, 4, 3, 5, 7> P420;
 typedef SPlan<300, 4, 3, 5, 5> P300;
+typedef SPlan<270, 2, 15, 9> P270;      // composite register radices (15 = 3*5, 9 = 3*3): three stages instead of five
 typedef SPlan<280, 8, 5, 7> P280;
 typedef SPlan<224, 8, 4, 7> P224;
 typedef SPlan<210, 2, 3, 5, 7> P210;

@@ -16,7 +16,8 @@ _POW2_PLAN = {0: [], 1: [2], 2: [4], 3: [8], 4: [16], 5: [8, 4], 6: [8, 8], 7: [
 
 def factorize(L, style=0):
     """Same result as the C planner (fc_plan.cu: factorize): fewest stages for the power-of-two part
-    with radices <= 16, then 3, 5, 7, then the remaining primes (generic stages)."""
+    with radices <= 16, then the odd 7-smooth part (composite radices 15 / 9 / 6 / 12 / 10 where factors pair up), then
+    the remaining primes (generic stages)."""
     out = []
     n = L
     e = 0
@@ -34,10 +35,29 @@ def factorize(L, style=0):
         out += [16, 4, 8]
     else:
         out += _POW2_PLAN[e]
+    # odd 7-smooth part: composite register stages (15, 9) and a leftover 3 / 5 joining a trailing 2 / 4
+    cnt = {}
     for r in (3, 5, 7):
+        cnt[r] = 0
         while n % r == 0 and n > 1:
-            out.append(r)
+            cnt[r] += 1
             n //= r
+    comp = []
+    if len(out) + cnt[3] + cnt[5] + cnt[7] > 4:      # only lengths that would need five or more stages
+        while cnt[3] >= 1 and cnt[5] >= 1:
+            comp.append(15)
+            cnt[3] -= 1
+            cnt[5] -= 1
+        if cnt[3] % 2 == 1 and out and out[-1] in (2, 4):
+            out[-1] *= 3
+            cnt[3] -= 1
+        while cnt[3] >= 2:
+            comp.append(9)
+            cnt[3] -= 2
+        if cnt[5] >= 1 and out and out[-1] == 2:
+            out[-1] = 10
+            cnt[5] -= 1
+    out += comp + [3] * cnt[3] + [5] * cnt[5] + [7] * cnt[7]
     p = 11
     while n > 1:
         while n % p == 0:

@@ -5,10 +5,19 @@ import pytest
 import engine_model as em
 
 LENGTHS = [1024, 2048, 4096, 8192, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 19, 21, 30, 35, 46, 64, 66, 106, 130, 132, 148, 158, 168,
-           218, 256, 286, 300, 346, 384, 512, 560]
+           218, 256, 286, 300, 346, 384, 512, 560, 18, 36, 45, 75, 90, 96, 135, 150, 210, 270, 420, 448, 1080, 1125, 2160]
 
 
-@pytest.mark.parametrize("L", [2, 3, 4, 5, 7, 8, 12, 30, 35, 64, 66, 130, 158, 300])
+def test_composite_radix_plans():
+    want = {270: [2, 15, 9], 1125: [15, 15, 5], 2160: [16, 15, 9], 1080: [8, 15, 9], 810: [6, 15, 9], 540: [4, 15, 9],
+            # up to four stages: one register stage per prime, as measured
+            300: [4, 3, 5, 5], 420: [4, 3, 5, 7], 150: [2, 3, 5, 5], 135: [3, 3, 3, 5], 210: [2, 3, 5, 7], 96: [8, 4, 3],
+            384: [16, 8, 3], 192: [8, 8, 3], 560: [16, 5, 7], 448: [8, 8, 7], 280: [8, 5, 7], 224: [8, 4, 7]}
+    for L, r in want.items():
+        assert em.factorize(L) == r, L
+
+
+@pytest.mark.parametrize("L", [2, 3, 4, 5, 7, 8, 12, 30, 35, 64, 66, 130, 158, 300, 270, 420, 1125, 90])
 def test_inplace_dif_and_mirror_inverse(L):
     rng = np.random.default_rng(L)
     r = em.factorize(L)
@@ -42,7 +51,7 @@ def test_c_planner_matches_model(fc, L, style):
     radices, generic = fc.plan_radices(L, style)
     assert radices == em.factorize(L, style)
     assert int(np.prod(radices)) == L
-    assert generic == any(r not in (1, 2, 3, 4, 5, 7, 8, 16) for r in radices)
+    assert generic == any(r not in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16) for r in radices)
     rev, pos, tw = fc.plan_tables(L, style)
     assert np.array_equal(rev, em.rev_positions(L, radices))
     assert np.array_equal(pos[rev], np.arange(L))

@@ -13,6 +13,9 @@ SHAPES = [  # imDim = (d0 fastest, d1, d2)
     (256, 256, 16), (512, 32, 8), (270, 30, 20), (300, 40, 28), (2, 2, 2), (4, 1, 1), (6, 2, 1),
     (560, 300, 8), (448, 420, 4), (420, 560, 3), (270, 448, 2), (32, 6, 300), (32, 4, 448), (300, 4, 560),
     (1024, 16, 4), (2048, 8, 6), (128, 34, 3), (256, 5, 3), (384, 12, 4), (32, 1024, 2), (16, 4, 1024),
+    # composite register radices 6, 9, 10, 12, 15 (fft_butterflies.cuh: DftCT) on every axis
+    (12, 6, 9), (30, 18, 12), (20, 10, 15), (90, 45, 36), (150, 135, 10), (24, 96, 75), (2160, 4, 2),
+    (4, 1080, 2), (6, 4, 1125), (540, 12, 6), (36, 540, 3), (10, 6, 810),
 ]
 
 
