@@ -511,7 +511,9 @@ static bool try_pipe_plain(const ColArgs& a, int mode, long long ngroups, cudaSt
     // measured on the caller-padded grids (profiles/r01_sweep_pipe_short.jsonl): 560: 0.181 -> 0.164 ms, 300: 0.068 -> 0.056 ms;
     // 420 (0.164 -> 0.183) and 448 / 256 (unchanged) stay on the one-tile-per-CTA kernels
     if (plan_matches<P560>(a.P)) return run_col_pipe_plain<P560, 320, 3>(a, mode, ngroups, st);
-    if (plan_matches<P300>(a.P)) return run_col_pipe_plain<P300, 256, 2>(a, mode, ngroups, st);
+    // L = 256 plain passes (256^3: 0.0307 / 0.0293 -> 0.0271 / 0.0255 ms, profiles/r01_sweep256.jsonl); three buffers or
+    // 256-thread CTAs are slower, and L = 270 does not move
+    if (plan_matches<P256>(a.P)) return run_col_pipe_plain<P256, 128, 2>(a, mode, ngroups, st);
     return false;
 }
 
