@@ -64,7 +64,38 @@ inline void throw_cuda(cudaError_t err, const char* what, const char* file, int 
         throw std::runtime_error(msg.str());
     }
 }
+// ---- programmatic dependent launch (PDL, sm_90+) ------------------------------------------------------------
+// Consecutive passes on one stream are launched with cudaLaunchAttributeProgrammaticStreamSerialization: every
+// kernel calls pdl_launch_dependents() first and pdl_wait() after its prologue (twiddle tables into shared memory:
+// plan constants, never produced by the previous pass), so the next pass's CTAs are scheduled and run their prologue
+// while the last wave of the previous pass drains; griddepcontrol.wait then blocks until the previous grid has
+// completed and its writes are visible.  Both instructions are no-ops in a normally launched kernel.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled();   // FCB200_PDL (default 1); fc_plan.cu
+
 #define FC_CUDA(expr) ::fcb200::throw_cuda((expr), #expr, __FILE__, __LINE__)
 #define FC_CUDA_KERNEL() ::fcb200::throw_cuda(cudaPeekAtLastError(), "kernel launch", __FILE__, __LINE__)
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(bool allow, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = allow ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    throw_cuda(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...), "kernel launch", __FILE__, __LINE__);
+}
+#endif
 
 }  // namespace fcb200

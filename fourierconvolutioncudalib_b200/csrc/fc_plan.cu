@@ -159,6 +159,20 @@ static std::atomic<long long> g_launches{0};
 long long launch_count() { return g_launches.load(); }
 void count_launches(int n) { g_launches.fetch_add(n); }
 
+// PDL pays in the launch-bound regime (64^3: -6 %, 256^3: -3 %); on large volumes the early-resident CTAs of the next
+// pass take SMs away from the PSF passes running on the side stream (C3: +6 %, profiles/r01_sweep_pdl.jsonl), so
+// it is used for plans whose spectrum fits the L2 only
+static int plan_pdl(const ConvPlan& p) { return (pdl_enabled() && p.spec_bytes() <= (size_t)96 << 20) ? 1 : 0; }
+
+bool pdl_enabled()
+{
+    static const bool on = [] {
+        const char* e = std::getenv("FCB200_PDL");
+        return !(e && std::atoi(e) == 0);
+    }();
+    return on;
+}
+
 // ---- optional per-pass timing with CUDA events on the launching stream (bench.py roofline) ----
 static std::atomic<int> g_profile{0};
 struct PassEvent {
@@ -399,6 +413,7 @@ static ColArgs y_args(ConvPlan& p, float2* data)
     a.data = data;
     a.H = nullptr;
     a.P = p.py.dev;
+    a.pdl = plan_pdl(p);
     a.stride = p.g.xcp;
     a.groupStride = (long long)p.g.ny * p.g.xcp;
     a.txp = p.txp_y;
@@ -435,6 +450,7 @@ static ColArgs z_args(ConvPlan& p, float2* data)
     a.data = data;
     a.H = nullptr;
     a.P = p.pz.dev;
+    a.pdl = plan_pdl(p);
     a.stride = C;
     a.groupStride = 0;
     a.txp = p.txp_z;
@@ -457,6 +473,7 @@ static XArgs x_args(ConvPlan& p)
     XArgs a{};
     a.g = p.g;
     a.P = p.px.dev;
+    a.pdl = plan_pdl(p);
     a.twx = p.d_twx;
     a.nrows = (long long)p.g.ny * p.g.nz;
     a.rowList = nullptr;

@@ -28,6 +28,7 @@ struct XArgs {
     int padOn;
     int padZ0;
     PadGeom pad;
+    int pdl;                // launch with programmatic stream serialization (fc_common.h: launch_pdl)
 };
 
 struct ColArgs {
@@ -56,6 +57,7 @@ struct ColArgs {
     // Mode 0 and mode 2 (fused z) write their output rows there; mode 1 reads from the plain split buffer.
     float2* const* splitPeers;
     long long splitPeerOffset;
+    int pdl;                // launch with programmatic stream serialization (fc_common.h: launch_pdl)
 };
 
 bool x_pass_supported(const Geometry& g, const AxisPlanDev& P);

@@ -33,7 +33,9 @@ __global__ void __launch_bounds__(THREADS) col_static_kernel(ColArgs a, int tile
                           (a.splitPeers ? a.splitPeerOffset : 0) + group * a.splitGroup + col0 + 2 * cp,
                           a.splitRows, SPLIT ? 1.0f / (float)a.splitRows : 0.f, stride};
 
+    pdl_launch_dependents();
     load_twiddles(tw, a.P.tw, L);
+    pdl_wait();
     __syncthreads();
 
     // A plain inverse on the linear layout runs the FORWARD stage sequence with re/im exchanged on the way in
@@ -139,11 +141,13 @@ __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int til
     const int cp = t % TXP, w = t / TXP;
     const size_t stride = (size_t)a.stride;
 
+    pdl_launch_dependents();
     load_twiddles(tw, a.P.tw, L);
     if (MODE == 2) {
         for (int r = t; r < L; r += THREADS) pos_s[r] = __ldg(a.P.pos + r);
         __syncthreads();
     }
+    pdl_wait();
 
     auto decode = [&](int tile, size_t& off) -> bool {
         const int gi = tile / tilesPerGroup;
@@ -247,7 +251,7 @@ bool run_col_pipe(const ColArgs& a, int mode, long long ngroups, cudaStream_t st
         int per_sm = 1;
         FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
         const int grid = (int)std::min<long long>(total, (long long)sm_count() * std::max(1, per_sm));
-        kernel<<<grid, THREADS, smem, st>>>(a, tpg, (int)total);
+        launch_pdl(a.pdl != 0, kernel, dim3(grid), dim3(THREADS), smem, st, a, tpg, (int)total);
         FC_CUDA_KERNEL();
     };
     if (mode == 0 && a.rowMask) go(col_pipe_kernel<0, P, THREADS, NBUF, true>);
@@ -274,7 +278,7 @@ bool run_col_pipe_plain(const ColArgs& a, int mode, long long ngroups, cudaStrea
         int per_sm = 1;
         FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
         const int grid = (int)std::min<long long>(total, (long long)sm_count() * std::max(1, per_sm));
-        kernel<<<grid, THREADS, smem, st>>>(a, tpg, (int)total);
+        launch_pdl(a.pdl != 0, kernel, dim3(grid), dim3(THREADS), smem, st, a, tpg, (int)total);
         FC_CUDA_KERNEL();
     };
     if (mode == 0) go(col_pipe_kernel<0, P, THREADS, NBUF, false, TXP>);
@@ -286,7 +290,7 @@ template <typename K>
 void launch(K kernel, long long grid, int threads, size_t smem, cudaStream_t st, const ColArgs& a, int tpg)
 {
     if (smem > 48 * 1024) FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<(unsigned)grid, threads, smem, st>>>(a, tpg);
+    launch_pdl(a.pdl != 0, kernel, dim3((unsigned)grid), dim3(threads), smem, st, a, tpg);
     FC_CUDA_KERNEL();
 }
 
@@ -394,7 +398,9 @@ __global__ void __launch_bounds__(THREADS) col_otf_kernel(ColArgs a, int tilesPe
     float2* base = a.data + off;
     const size_t stride = (size_t)a.stride;
 
+    pdl_launch_dependents();
     load_twiddles(tw, a.P.tw, L);
+    pdl_wait();
     // window rows: issued now, consumed after the first stage so that their latency overlaps with the
     // first-stage loads (q & 7 == cp because THREADS % 8 == 0)
     constexpr int NWIN = (128 + THREADS - 1) / THREADS;
@@ -477,7 +483,7 @@ bool try_col_otf(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, b
     if (grid > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
     auto kernel = col_otf_kernel<P, THREADS, U>;
     if (smem > 48 * 1024) FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<(unsigned)grid, THREADS, smem, st>>>(a, tpg, z0);
+    launch_pdl(a.pdl != 0, kernel, dim3((unsigned)grid), dim3(THREADS), smem, st, a, tpg, z0);
     FC_CUDA_KERNEL();
     return true;
 }

@@ -18,7 +18,7 @@ bool try_x_fwd(const XArgs& a, bool psf, long long tiles, cudaStream_t st)
     auto go = [&](auto kernel) {
         if (smem > 48 * 1024)
             FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<(unsigned)tiles, THREADS, smem, st>>>(a);
+        launch_pdl(a.pdl != 0, kernel, dim3((unsigned)tiles), dim3(THREADS), smem, st, a);
         FC_CUDA_KERNEL();
     };
     if (psf) go(x_fwd_kernel<1, P, THREADS>);
@@ -34,7 +34,7 @@ bool try_x_inv(const XArgs& a, long long tiles, cudaStream_t st)
     if (smem > (size_t)kMaxDynSmem) return false;
     auto kernel = x_inv_kernel<P, THREADS>;
     if (smem > 48 * 1024) FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<(unsigned)tiles, THREADS, smem, st>>>(a);
+    launch_pdl(a.pdl != 0, kernel, dim3((unsigned)tiles), dim3(THREADS), smem, st, a);
     FC_CUDA_KERNEL();
     return true;
 }
@@ -67,7 +67,7 @@ static bool try_xrow(const XArgs& a, bool inverse, cudaStream_t st)
     auto go = [&](auto kernel) {
         if (smem > 48 * 1024)
             FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<(unsigned)grid, THREADS, smem, st>>>(a);
+        launch_pdl(a.pdl != 0, kernel, dim3((unsigned)grid), dim3(THREADS), smem, st, a);
         FC_CUDA_KERNEL();
     };
     if (inverse) go(xrow_inv_kernel<R, THREADS>);
@@ -91,7 +91,7 @@ static bool try_xrowg(const XArgs& a, bool inverse, cudaStream_t st)
     auto go = [&](auto kernel) {
         if (smem > 48 * 1024)
             FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<(unsigned)grid, THREADS, smem, st>>>(a);
+        launch_pdl(a.pdl != 0, kernel, dim3((unsigned)grid), dim3(THREADS), smem, st, a);
         FC_CUDA_KERNEL();
     };
     if (inverse) go(xrowg_inv_kernel<R0, R1, R2, THREADS>);

@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kerne
     const int lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
     const long long row0 = (long long)blockIdx.x * NROWS;
 
+    pdl_launch_dependents();
     load_twiddles(sm.tw, a.P.tw, L);
+    pdl_wait();
 
     // ---- global rows -> row tile (one warp per row at a time, lanes along x)
     for (int lrow = warp; lrow < NROWS; lrow += nwarps) {
@@ -404,7 +406,9 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
     const int lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
     const long long row0 = (long long)blockIdx.x * NROWS;
 
+    pdl_launch_dependents();
     load_twiddles(sm.tw, a.P.tw, L);
+    pdl_wait();
 
     // ---- spectrum rows (pair-planar) -> row tile (interleaved); loads are issued XLB at a time
     for (int lrow = warp; lrow < NROWS; lrow += nwarps) {

@@ -39,11 +39,13 @@ __global__ void __launch_bounds__(THREADS) xrow_fwd_kernel(XArgs a)
     const Geometry g = a.g;
     const int t = threadIdx.x, lane = t & 31;
     const int grp = t / R, j = t % R;
+    pdl_launch_dependents();
     for (int idx = t; idx < R * R; idx += THREADS) {
         const int m = idx / R, jj = idx % R;
         const float2 w = __ldg(a.P.tw + jj * m);
         twt[idx] = make_float4(w.x, w.x, w.y, w.y);
     }
+    pdl_wait();
     __syncthreads();
 
     const long long rowA = ((long long)blockIdx.x * RP + grp) * 2;
@@ -134,11 +136,13 @@ __global__ void __launch_bounds__(THREADS) xrow_inv_kernel(XArgs a)
     const Geometry g = a.g;
     const int t = threadIdx.x, lane = t & 31;
     const int grp = t / R, j = t % R;
+    pdl_launch_dependents();
     for (int idx = t; idx < R * R; idx += THREADS) {
         const int m = idx / R, jj = idx % R;
         const float2 w = __ldg(a.P.tw + jj * m);
         twt[idx] = make_float4(w.x, w.x, w.y, w.y);
     }
+    pdl_wait();
     __syncthreads();
 
     const long long rowA = ((long long)blockIdx.x * RP + grp) * 2;

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(THREADS) xrowg_fwd_kernel(XArgs a)
     const Geometry g = a.g;
     const int t = threadIdx.x, lane = t & 31;
     const int grp = t / TG, tl = t % TG;
+    pdl_launch_dependents();
     {
         constexpr int S1 = M / R0;
         for (int idx = t; idx < M; idx += THREADS) {
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(THREADS) xrowg_fwd_kernel(XArgs a)
             }
         }
     }
+    pdl_wait();
     __syncthreads();
 
     const long long rowA = ((long long)blockIdx.x * RP + grp) * 2;
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(THREADS) xrowg_inv_kernel(XArgs a)
     const Geometry g = a.g;
     const int t = threadIdx.x, lane = t & 31;
     const int grp = t / TG, tl = t % TG;
+    pdl_launch_dependents();
     {
         constexpr int S1 = M / R0;
         for (int idx = t; idx < M; idx += THREADS) {
@@ -237,6 +240,7 @@ __global__ void __launch_bounds__(THREADS) xrowg_inv_kernel(XArgs a)
             }
         }
     }
+    pdl_wait();
     __syncthreads();
 
     const long long rowA = ((long long)blockIdx.x * RP + grp) * 2;
