@@ -26,6 +26,7 @@ EXT_SYMBOLS = (
     "fcb200_device_free", "fcb200_ipc_get_handle", "fcb200_ipc_open_handle", "fcb200_ipc_close_handle", "fcb200_convolve_batch",
     "fcb200_release", "fcb200_launch_count", "fcb200_profile_enable", "fcb200_profile_read",
     "fcb200_padded_extents", "fcb200_convolve_padded", "fcb200_convolve_padded_device_async",
+    "fcb200_convolve_batch_padded",
 )
 
 
@@ -95,6 +96,7 @@ def load():
         "fcb200_convolve_batch": (None, [vp, i, ip, vp, ip, i]),
         "fcb200_padded_extents": (None, [ip, ip, i, ip]),
         "fcb200_convolve_padded": (None, [vp, ip, vp, ip, i, i, i]),
+        "fcb200_convolve_batch_padded": (None, [vp, i, ip, vp, ip, i, i, i]),
         "fcb200_convolve_padded_device_async": (None, [vp, ip, vp, ip, i, i, i, vp]),
         "fcb200_release": (None, []),
         "fcb200_launch_count": (ctypes.c_longlong, []),

@@ -167,6 +167,13 @@ def convolve_padded(im, imDim, kernel, kernelDim, devCUDA, mode=PAD_ZERO, policy
                                        int(devCUDA))
 
 
+def convolve_batch_padded(ims, imDim, kernel, kernelDim, devCUDA, mode=PAD_ZERO, policy=PAD_SMOOTH):
+    """extension (fcb200_convolve_batch_padded): convolve_batch with the padding done in the library"""
+    ptrs = (ctypes.c_void_p * len(ims))(*[_ptr(im) for im in ims])
+    _load().fcb200_convolve_batch_padded(ptrs, len(ims), _ints(imDim), _ptr(kernel), _ints(kernelDim), int(mode),
+                                             int(policy), int(devCUDA))
+
+
 def convolve_padded_device_async(im_dev, imDim, kernel_dev, kernelDim, devCUDA, mode=PAD_ZERO, policy=PAD_SMOOTH,
                                  stream=0):
     _load().fcb200_convolve_padded_device_async(_ptr(im_dev), _ints(imDim), _ptr(kernel_dev), _ints(kernelDim),

@@ -233,15 +233,39 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
 // knowing about the padding: only the unpadded bytes cross PCIe, zero z-halo planes are never transformed
 // forward (their spectrum planes are cleared instead), and no halo plane is transformed back.
 // ------------------------------------------------------------------------------------------------
-void padded_core(float* im, const int* imDim, const float* kernel, const int* kernelDim, int mode, int policy, int dev,
-                 bool force_async, cudaStream_t user_stream)
+// Device-resident unpadded volume d_src convolved on the padded grid of plan p, fused form (the x passes pad and
+// crop, see fft_xpass.cuh); before_z() runs between the forward passes and the fused z pass (PSF join).
+template <typename F>
+void padded_convolve_device(ConvPlan& p, float* d_src, const PadGeom& g, cudaStream_t st, F&& before_z)
+{
+    const size_t splane = (size_t)p.g.ny * p.g.xcp;
+    const int z_lo = g.oz, z_hi = g.oz + g.sz;
+    run_xy_forward_planes(p, d_src, z_lo, g.sz, st, &g);
+    const int r0[2] = {0, z_hi}, rn[2] = {z_lo, g.pz - z_hi};
+    for (int i = 0; i < 2; ++i) {
+        if (rn[i] <= 0) continue;
+        if (g.mode == 0) FC_CUDA(cudaMemsetAsync(p.d_spec + r0[i] * splane, 0, rn[i] * splane * sizeof(float2), st));
+        else run_xy_forward_planes(p, d_src, r0[i], rn[i], st, &g);
+    }
+    before_z();
+    run_z_fused(p, false, st);
+    run_yx_inverse_planes(p, d_src, z_lo, g.sz, st, &g);
+}
+
+PadGeom make_pad_geom(const int* imDim, const int* kernelDim, int mode, int policy, int* pd)
 {
     if (mode != 0 && mode != 1) throw std::runtime_error("fcb200: padding mode must be 0 (zero) or 1 (mirror)");
     if (policy != 0 && policy != 1) throw std::runtime_error("fcb200: padding policy must be 0 (exact) or 1 (7-smooth)");
-    int pd[3];
     padded_extents(imDim, kernelDim, policy, pd);
-    const PadGeom g{imDim[0], imDim[1], imDim[2], pd[0], pd[1], pd[2],
-                    kernelDim[0] / 2, kernelDim[1] / 2, kernelDim[2] / 2, mode};
+    return PadGeom{imDim[0], imDim[1], imDim[2], pd[0], pd[1], pd[2],
+                   kernelDim[0] / 2, kernelDim[1] / 2, kernelDim[2] / 2, mode};
+}
+
+void padded_core(float* im, const int* imDim, const float* kernel, const int* kernelDim, int mode, int policy, int dev,
+                 bool force_async, cudaStream_t user_stream)
+{
+    int pd[3];
+    const PadGeom g = make_pad_geom(imDim, kernelDim, mode, policy, pd);
     const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], pd[0], pd[1], pd[2]};
     DeviceGuard guard(dev);
     auto plan = get_plan(dev, pd[0], pd[1], pd[2]);
@@ -393,7 +417,7 @@ void batch_resources(ConvPlan& p)
 }
 
 void batch_core(float* const* ims, int n, int nx, int ny, int nz, const float* kernel, const int* pdims, int dev,
-                bool save_memory)
+                bool save_memory, const PadGeom* pad = nullptr)
 {
     DeviceGuard guard(dev);
     for (int i = 0; i < 3; ++i)
@@ -402,7 +426,8 @@ void batch_core(float* const* ims, int n, int nx, int ny, int nz, const float* k
     auto plan = get_plan(dev, nx, ny, nz);
     std::lock_guard<std::mutex> lock(plan->mu);
     ConvPlan& p = *plan;
-    const size_t bytes = p.real_bytes();
+    // padded batches: (nx, ny, nz) is the padded grid of the plan, the blocks and the ring buffers hold UNPADDED volumes
+    const size_t bytes = pad ? (size_t)pad->sx * pad->sy * pad->sz * sizeof(float) : p.real_bytes();
     cudaStream_t st = p.stream;
 
     bool any_pageable = false, any_device = false;
@@ -413,7 +438,8 @@ void batch_core(float* const* ims, int n, int nx, int ny, int nz, const float* k
     }
     const bool window = prepare_psf(p, kernel, is_device_ptr(kernel, dev), pdims, save_memory, st);
     auto convolve = [&](float* d) {
-        if (window) run_convolve_window(p, d, st);
+        if (pad) padded_convolve_device(p, d, *pad, st, [] {});
+        else if (window) run_convolve_window(p, d, st);
         else run_convolve(p, d, st);
     };
     if (any_device) {   // device-resident blocks: nothing to overlap
@@ -589,6 +615,19 @@ void fcb200_convolve_padded(imageType* im, const int* imDim, const imageType* ke
     guarded([&] {
         check_dims(imDim, kernelDim);
         padded_core(im, imDim, kernel, kernelDim, mode, policy, devCUDA, false, nullptr);
+    });
+}
+
+void fcb200_convolve_batch_padded(imageType* const* ims, int n, const int* imDim, const imageType* kernel,
+                                  const int* kernelDim, int mode, int policy, int devCUDA)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        if (!ims && n > 0) throw std::runtime_error("fcb200: ims is NULL");
+        int pd[3];
+        const PadGeom g = make_pad_geom(imDim, kernelDim, mode, policy, pd);
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], pd[0], pd[1], pd[2]};
+        batch_core(ims, n, pd[0], pd[1], pd[2], kernel, pdims, devCUDA, false, &g);
     });
 }
 

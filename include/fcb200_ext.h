@@ -32,6 +32,10 @@ FUNCTION_PREFIX void fcb200_convolve_device_async_savememory(imageType* im_dev, 
 FUNCTION_PREFIX void fcb200_padded_extents(const int* imDim, const int* kernelDim, int policy, int* padDim);
 FUNCTION_PREFIX void fcb200_convolve_padded(imageType* im, const int* imDim, const imageType* kernel, const int* kernelDim,
                                            int mode, int policy, int devCUDA);
+/* n unpadded blocks of one shape, one PSF: fcb200_convolve_batch (below) with the padding done in the library --
+ * the multi-view deconvolution pattern (blocks + halo) in one call; transfers of neighbouring blocks overlap. */
+FUNCTION_PREFIX void fcb200_convolve_batch_padded(imageType* const* ims, int n, const int* imDim, const imageType* kernel,
+                                                 const int* kernelDim, int mode, int policy, int devCUDA);
 /* device pointers, stream-ordered, no host synchronisation */
 FUNCTION_PREFIX void fcb200_convolve_padded_device_async(imageType* im_dev, const int* imDim, const imageType* kernel_dev,
                                                         const int* kernelDim, int mode, int policy, int devCUDA,

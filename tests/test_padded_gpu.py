@@ -141,3 +141,31 @@ def test_padded_rejects_bad_arguments(fc, dev):
         fc.convolve_padded(im, (8, 8, 8), k, (3, 3, 3), dev, policy=5)
     with pytest.raises(fc.api.FourierConvolutionError):
         fc.convolve_padded(im, (8, 0, 8), k, (3, 3, 3), dev)
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["zero", "mirror"])
+def test_padded_batch_equals_separate_padded_calls(fc, dev, mode):
+    """fcb200_convolve_batch_padded (blocks + halo in one call, transfers pipelined) == n separate padded calls"""
+    import torch
+    imDim, kDim, nblocks = (96, 80, 72), (9, 7, 11), 5
+    rng = np.random.default_rng(21)
+    k = rng.random(int(np.prod(kDim)), dtype=np.float32)
+    k /= k.sum()
+    blocks = [(rng.random(int(np.prod(imDim)), dtype=np.float32) * 100).astype(np.float32) for _ in range(nblocks)]
+    want = []
+    for b in blocks:
+        w = b.copy()
+        fc.convolve_padded(w, imDim, k.copy(), kDim, dev, mode=mode, policy=1)
+        want.append(w)
+    check(want[0], fo.convolve_padded_ref(blocks[0], imDim, k, kDim, mode, 1))
+    pageable = [b.copy() for b in blocks]
+    fc.convolve_batch_padded(pageable, imDim, k.copy(), kDim, dev, mode=mode, policy=1)
+    pinned = [torch.from_numpy(b.copy()).pin_memory() for b in blocks]
+    fc.convolve_batch_padded(pinned, imDim, k.copy(), kDim, dev, mode=mode, policy=1)
+    device = [torch.from_numpy(b).to(f"cuda:{dev}") for b in blocks]
+    fc.convolve_batch_padded(device, imDim, k.copy(), kDim, dev, mode=mode, policy=1)
+    for i in range(nblocks):
+        assert np.array_equal(pageable[i], want[i])
+        assert np.array_equal(pinned[i].numpy(), want[i])
+        assert np.array_equal(device[i].cpu().numpy(), want[i])
+    fc.convolve_batch_padded([], imDim, k.copy(), kDim, dev)        # empty batch: nothing to do
