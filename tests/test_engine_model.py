@@ -70,3 +70,23 @@ def test_psf_active_rows_match_oracle_placement(fc):
         S = fo.place_psf(np.ones(int(np.prod(kDim)), np.float32), kDim, imDim)
         rows = np.unique(np.nonzero(S)[0] // imDim[0])
         assert np.array_equal(rows, fc.psf_active_rows(imDim, kDim))
+
+
+def test_c_planner_matches_model_exhaustively_up_to_1200(fc):
+    """every length a caller can pass on an axis (up to 1200, plus the padded config-5 extents): same radix
+    sequence as the numpy model, product == L, stages bounded, digit reversal a permutation"""
+    fast = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16)
+    for L in list(range(1, 1201)) + [1125, 2048, 2160, 4096]:
+        for style in (0, 1, 2):
+            radices, generic = fc.plan_radices(L, style)
+            assert radices == em.factorize(L, style), (L, style)
+            assert int(np.prod(radices)) == L
+            assert generic == any(r not in fast for r in radices)
+        r0 = em.factorize(L)
+        smooth = [r for r in r0 if r in fast]
+        if len(smooth) == len(r0) and L > 1:
+            # 7-smooth lengths never need more than four shared-memory round trips up to 1200 ... except the few with
+            # many repeated small primes that even composite radices cannot pack into four stages
+            assert len(r0) <= 5, (L, r0)
+    rev, pos, _ = fc.plan_tables(270)
+    assert sorted(rev.tolist()) == list(range(270)) and np.array_equal(pos[rev], np.arange(270))
