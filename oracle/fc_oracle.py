@@ -171,6 +171,32 @@ def _reflect_pad_degenerate(a, widths):
     return a
 
 
+def modulate_subsampled_ref(im, im_dim, kernel, kernel_dim):
+    """numpy restatement of modulateAndNormalizeSubsampled_kernel (src/convolution3Dfft.cu:65-125), the only piece of the
+    legacy "SaveMemory" idea that survives in the reference snapshot (no host function calls it; the declaration at
+    src/convolution3Dfft.h:58-64 is commented out).  Host flow as the header comment describes it: FFT of the image at
+    image size, FFT of the RAW (unpadded, unshifted) PSF at PSF size, this kernel, inverse FFT.  Legacy convention:
+    index 2 is the fastest axis (:80-84).  Returns the flat float64 result.
+
+    Kept in the oracle ONLY to document why the product does not offer these semantics: the result is a
+    nearest-neighbour resampling of the PSF spectrum with a 0/pi phase stand-in (:106-117) and is several per cent away
+    from the convolution (tests/test_oracle.py::test_legacy_subsampled_multiply_is_not_a_convolution)."""
+    d0, d1, d2 = (int(v) for v in im_dim)
+    k0, k1, k2 = (int(v) for v in kernel_dim)
+    F = np.fft.rfftn(np.asarray(im, np.float64).reshape(d0, d1, d2))                 # [d0][d1][d2/2+1]
+    K = np.fft.rfftn(np.asarray(kernel, np.float64).reshape(k0, k1, k2)).reshape(-1)   # [k0][k1][k2/2+1], flat
+    r0, r1, r2 = (np.float32(k0) / np.float32(d0), np.float32(k1) / np.float32(d1), np.float32(k2) / np.float32(d2))
+    i0, i1, i2 = np.meshgrid(np.arange(d0), np.arange(d1), np.arange(d2 // 2 + 1), indexing="ij")     # :80-84
+    q2 = (r2 * i2.astype(np.float32) + np.float32(0.5)).astype(np.int64) % k2                         # :106
+    q1 = (r1 * i1.astype(np.float32) + np.float32(0.5)).astype(np.int64) % k1                         # :107
+    q0 = (r0 * i0.astype(np.float32) + np.float32(0.5)).astype(np.int64) % k0                         # :108
+    flat = q2 + (1 + k2 // 2) * (q1 + k1 * q0)                                                        # :110-111
+    a = K[np.minimum(flat, K.size - 1)]            # odd k2: q2 may be k2/2+1, one past the row (clamped at the very end)
+    a = np.where((q0 + q1 + q2) % 2 == 1, -a, a)                                                      # :113-117
+    out = np.fft.irfftn(a * F, s=(d0, d1, d2), axes=(0, 1, 2))     # c = 1/N (:118-121) is numpy's inverse normalisation
+    return out.reshape(-1)
+
+
 def l2norm(reference, data):
     """tests/test_utils.hpp:75-88: sqrt(sum (a-b)^2) / N  (N, not sqrt(N))."""
     a = np.asarray(reference, dtype=np.float32).reshape(-1).astype(np.float64)

@@ -133,3 +133,22 @@ def test_padded_oracle_mirror_mode_keeps_a_constant_image_constant():
     assert np.allclose(got, 42.0, rtol=1e-12)
     # zero mode darkens the border instead
     assert fo.convolve_padded_ref(im, (12, 9, 8), k, (5, 3, 7), 0, 1).min() < 41.0
+
+
+def test_legacy_subsampled_multiply_is_not_a_convolution():
+    """the only surviving piece of the legacy "SaveMemory" idea
+    (modulateAndNormalizeSubsampled_kernel, src/convolution3Dfft.cu:65-125; no host caller in the snapshot, so there is
+    nothing to pin it against) is 2-8 % away from the convolution the entry point's header promises
+    (src/convolution3Dfft.h:58-64: "like InPlace").  That is why convolution3DfftCUDAInPlaceSaveMemory here returns the
+    InPlace result instead (tests/test_parity_gpu.py::test_savememory_entry_point holds it to 1e-4 / 1e-5)."""
+    rng = np.random.default_rng(0)
+    for d, k in (((32, 32, 32), (7, 7, 7)), ((48, 48, 48), (15, 15, 15))):
+        im = rng.random(int(np.prod(d)))
+        ax = [np.exp(-0.5 * ((np.arange(n) - n // 2) / (n / 6.0)) ** 2) for n in k]
+        psf = ax[0][:, None, None] * ax[1][None, :, None] * ax[2][None, None, :]
+        psf /= psf.sum()
+        got = fo.modulate_subsampled_ref(im, d, psf.reshape(-1), k)
+        # cubic volume: the reference InPlace placement is the plain centred PSF, in either axis convention
+        want = fo.convolve_inplace_ref(im, d, psf.reshape(-1), k)
+        err = np.linalg.norm(got - want) / np.linalg.norm(want)
+        assert 1e-2 < err < 1e-1, err            # three orders of magnitude above the parity tolerance (1e-5)
