@@ -106,8 +106,8 @@ def test_zero_padded_cubic_equals_direct_convolution(fc, dev):
 def test_padded_device_pointers_and_pinned_chunks(fc, dev):
     """device-resident call (stream-ordered) and the z-chunked pinned path give the pageable-path result"""
     import torch
-    imDim, kDim = (160, 144, 136), (9, 7, 11)      # 12.5 MB: below the chunking threshold
-    big, kbig = (384, 320, 96), (9, 9, 7)          # 47 MB unpadded -> pinned calls travel in chunks
+    imDim, kDim = (160, 144, 136), (9, 7, 11)      # 12.5 MB: below the chunking threshold (one chunk per 32 MiB, >= 2)
+    big, kbig = (448, 320, 168), (9, 9, 7)         # 92 MB unpadded -> pinned calls travel in 2 z chunks
     rng = np.random.default_rng(5)
     for (idim, kdim) in ((imDim, kDim), (big, kbig)):
         im = rng.random(int(np.prod(idim)), dtype=np.float32)
