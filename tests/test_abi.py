@@ -64,3 +64,20 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU fallback", ""), f
+
+
+def test_cpp_caller_catches_runtime_error_across_the_c_boundary(fc, tmp_path):
+    """the reference's C++ callers rely on std::runtime_error crossing the C ABI (tests/test_gpu_convolve.cpp:237-247);
+    tests/cpp/abi_exceptions.cpp is such a caller, restricted to the entry points that need no GPU"""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "abi_exceptions")
+    libdir = os.path.dirname(fc._lib.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "abi_exceptions.cpp"), "-o", exe,
+                           "-L", libdir, "-lFourierConvolutionCUDALib", "-Wl,-rpath," + libdir])
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "0 failure(s)" in res.stdout
