@@ -48,3 +48,22 @@ def test_numerical_stability(fc, dev, case):
     name, stack, kernel, factor, expected, thr = case
     got = refcases.run_case(make_convolve(fc, dev), stack, kernel, factor)
     assert fo.l2norm(expected, got) < thr
+
+
+def test_cpp_port_of_reference_cases_links_and_passes(fc, dev, tmp_path):
+    """tests/cpp/reference_cases.cpp: the reference's asymmetric-volume and 8^3 identity cases as a C++ program linked
+    against the drop-in library like the reference's own test executables (tests/CMakeLists.txt:23-27)"""
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "reference_cases")
+    libdir = os.path.dirname(fc._lib.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "reference_cases.cpp"), "-o", exe,
+                           "-L", libdir, "-lFourierConvolutionCUDALib", "-Wl,-rpath," + libdir])
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "0 failure(s)" in res.stdout
