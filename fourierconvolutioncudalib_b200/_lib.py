@@ -27,6 +27,8 @@ EXT_SYMBOLS = (
     "fcb200_release", "fcb200_launch_count", "fcb200_profile_enable", "fcb200_profile_read",
     "fcb200_padded_extents", "fcb200_convolve_padded", "fcb200_convolve_padded_device_async",
     "fcb200_convolve_batch_padded",
+    "fcb200_convolve_slab", "fcb200_convolve_slab_device", "fcb200_slab_last_timing", "fcb200_slab_devices",
+    "fcb200_convolve_batch_multi",
 )
 
 
@@ -98,6 +100,11 @@ def load():
         "fcb200_convolve_padded": (None, [vp, ip, vp, ip, i, i, i]),
         "fcb200_convolve_batch_padded": (None, [vp, i, ip, vp, ip, i, i, i]),
         "fcb200_convolve_padded_device_async": (None, [vp, ip, vp, ip, i, i, i, vp]),
+        "fcb200_convolve_slab": (None, [vp, ip, vp, ip, ip, i]),
+        "fcb200_convolve_slab_device": (None, [vp, ip, vp, ip, ip, i]),
+        "fcb200_slab_last_timing": (i, [ip, ip, i, fp, i]),
+        "fcb200_slab_devices": (i, [ip, i, ip, i]),
+        "fcb200_convolve_batch_multi": (None, [vp, i, ip, vp, ip, ip, i, ip]),
         "fcb200_release": (None, []),
         "fcb200_launch_count": (ctypes.c_longlong, []),
         "fcb200_profile_enable": (None, [i]),

@@ -82,6 +82,47 @@ def convolve_batch(ims, imDim, kernel, kernelDim, devCUDA):
     _load().fcb200_convolve_batch(ptrs, len(ims), _ints(imDim), _ptr(kernel), _ints(kernelDim), int(devCUDA))
 
 
+def convolve_batch_multi(ims, imDim, kernel, kernelDim, devs):
+    """extension (fcb200_convolve_batch_multi): host blocks dealt over several devices from one shared queue;
+    returns how many blocks each device took"""
+    ptrs = (ctypes.c_void_p * len(ims))(*[_ptr(im) for im in ims])
+    taken = (ctypes.c_int * len(devs))()
+    _load().fcb200_convolve_batch_multi(ptrs, len(ims), _ints(imDim), _ptr(kernel), _ints(kernelDim), _ints(devs),
+                                            len(devs), taken)
+    return list(taken)
+
+
+def convolve_slab(im, imDim, kernel, kernelDim, devs):
+    """extension (fcb200_convolve_slab): ONE host volume convolved in place, cut in z slabs over `devs`"""
+    _load().fcb200_convolve_slab(_ptr(im), _ints(imDim), _ptr(kernel), _ints(kernelDim), _ints(devs), len(devs))
+
+
+def convolve_slab_device(slabs, imDim, kernel, kernelDim, devs):
+    """extension (fcb200_convolve_slab_device): slabs[r] = rank r's z slab, resident on devs[r]"""
+    ptrs = (ctypes.c_void_p * len(slabs))(*[_ptr(s) for s in slabs])
+    _load().fcb200_convolve_slab_device(ptrs, _ints(imDim), _ptr(kernel), _ints(kernelDim), _ints(devs), len(devs))
+
+
+def slab_last_timing(imDim, devs):
+    """-> per rank (forward, fused z, inverse, total) device milliseconds of the most recent slab call"""
+    ms = (ctypes.c_float * (4 * len(devs)))()
+    n = _load().fcb200_slab_last_timing(_ints(imDim), _ints(devs), len(devs), ms, 4 * len(devs))
+    return [tuple(ms[4 * r:4 * r + 4]) for r in range(n)]
+
+
+def slab_devices(imDim, devCUDA=0):
+    out = (ctypes.c_int * 64)()
+    n = _load().fcb200_slab_devices(_ints(imDim), int(devCUDA), out, 64)
+    return list(out[:n])
+
+
+def slab_partition(imDim, world):
+    """(nzp, nyl, [planes of rank r]) of the slab decomposition used by convolve_slab*"""
+    d0, d1, d2 = (int(v) for v in imDim)
+    nzp, nyl = -(-d2 // world), -(-d1 // world)
+    return nzp, nyl, [max(0, min(nzp, d2 - r * nzp)) for r in range(world)]
+
+
 def convolution3DfftCUDA(im, imDim, kernel, kernelDim, devCUDA):
     """reference: src/convolution3Dfft.h:41-45 (legacy: imDim[2] fastest).  Returns a new array."""
     lib = _load()
@@ -251,8 +292,7 @@ def launch_count():
     return _load().fcb200_launch_count()
 
 
-PASS_NAMES = ("psf_clear", "psf_x", "psf_y", "psf_z", "x_fwd", "y_fwd", "z_fused", "y_inv", "x_inv",
-              "xy_fwd", "yx_inv")
+PASS_NAMES = ("psf_clear", "psf_x", "psf_y", "psf_z", "x_fwd", "y_fwd", "z_fused", "y_inv", "x_inv")
 
 
 def profile_enable(on=True):

@@ -10,42 +10,19 @@
 #include <vector>
 
 #include "convolution3Dfft.h"
+#include "fc_api_util.h"
+#include "fc_multi.h"
 #include "fc_plan.h"
 #include "fcb200_ext.h"
 
 using namespace fcb200;
 
-namespace {
-
+namespace fcb200 {
 thread_local std::string g_last_error;
-std::atomic<int> g_error_mode{0};  // 0: throw std::runtime_error (reference convention); 1: record only
+std::atomic<int> g_error_mode{0};
+}  // namespace fcb200
 
-// Runs `fn`, records the message of any exception for fcb200_last_error() and rethrows it as
-// std::runtime_error -- the reference's convention for recoverable failures
-// (/root/reference/src/book.h:112-123; its tests catch it, tests/test_gpu_convolve.cpp:237-247).
-template <typename F>
-auto guarded(F&& fn) -> decltype(fn())
-{
-    try {
-        g_last_error.clear();
-        return fn();
-    } catch (const std::exception& e) {
-        g_last_error = e.what();
-        cudaGetLastError();  // clear non-sticky errors so later calls can proceed
-        if (g_error_mode.load() == 1) return decltype(fn())();
-        throw std::runtime_error(g_last_error);
-    }
-}
-
-void check_dims(const int* imDim, const int* kernelDim)
-{
-    if (!imDim) throw std::runtime_error("fcb200: imDim is NULL");
-    for (int i = 0; i < 3; ++i)
-        if (imDim[i] <= 0) throw std::runtime_error("fcb200: image extents must be positive");
-    if (kernelDim)
-        for (int i = 0; i < 3; ++i)
-            if (kernelDim[i] <= 0) throw std::runtime_error("fcb200: kernel extents must be positive");
-}
+namespace fcb200 {
 
 // Is `p` device memory usable from device `dev`?  (extension: the reference only takes host pointers)
 bool is_device_ptr(const void* p, int dev)
@@ -61,20 +38,6 @@ bool is_device_ptr(const void* p, int dev)
         return true;
     }
     return attr.type == cudaMemoryTypeManaged;
-}
-
-struct DeviceGuard {
-    int dev;
-    explicit DeviceGuard(int d) : dev(d) { FC_CUDA(cudaSetDevice(d)); }  // like the reference, devCUDA stays current
-};
-
-// Core of the in-place convolution.
-//   nx,ny,nz : geometry of the real volume as consumed (nx fastest)
-//   pdims    : (k0,k1,k2,d0,d1,d2) handed to the PSF placement (reference fftShiftKernel arguments)
-bool env_flag(const char* name, bool dflt)
-{
-    const char* e = std::getenv(name);
-    return e ? std::atoi(e) != 0 : dflt;
 }
 
 // PSF taps (host or device pointer) -> PSF spectrum in plan.d_H (or the SaveMemory window buffers).
@@ -110,6 +73,10 @@ bool prepare_psf(ConvPlan& p, const float* kernel, bool k_dev, const int* pdims,
     }
     return false;
 }
+
+}  // namespace fcb200
+
+namespace {
 
 // The PSF passes (three small, partly launch-bound kernels) run on a side stream next to the image's x/y
 // passes and join before the fused z pass.  Off while per-pass profiling is on (events need serial passes).
@@ -210,8 +177,8 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
         if (staged) p.stager.upload(p.d_real, im, p.real_bytes(), st);
         else FC_CUDA(cudaMemcpyAsync(p.d_real, im, p.real_bytes(), cudaMemcpyHostToDevice, st));
         d_im = p.d_real;
-    } else if ((reinterpret_cast<uintptr_t>(im) & 7) != 0) {
-        throw std::runtime_error("fcb200: device image pointer must be 8-byte aligned");
+    } else {
+        check_real_alignment(im, nx);
     }
     run_xy_forward_planes(p, d_im, 0, nz, st);
     join_psf();
@@ -416,13 +383,19 @@ void batch_resources(ConvPlan& p)
     }
 }
 
-void batch_core(float* const* ims, int n, int nx, int ny, int nz, const float* kernel, const int* pdims, int dev,
-                bool save_memory, const PadGeom* pad = nullptr)
+}  // namespace
+
+namespace fcb200 {
+
+// `next` hands out the index of the next block to convolve (-1: none left).  A single-device batch counts
+// 0..n-1; fcb200_convolve_batch_multi gives every device's pipeline the SAME counter, so a device that finishes
+// early simply takes more blocks (work stealing at block granularity, at most three blocks in flight per device).
+void batch_core(float* const* ims, const std::function<int()>& next, BatchKinds kinds, int nx, int ny, int nz,
+                const float* kernel, const int* pdims, int dev, bool save_memory, const PadGeom* pad)
 {
     DeviceGuard guard(dev);
     for (int i = 0; i < 3; ++i)
         if (pdims[i] > pdims[i + 3]) throw std::runtime_error("fcb200: kernel larger than image");
-    if (n <= 0) return;
     auto plan = get_plan(dev, nx, ny, nz);
     std::lock_guard<std::mutex> lock(plan->mu);
     ConvPlan& p = *plan;
@@ -430,22 +403,18 @@ void batch_core(float* const* ims, int n, int nx, int ny, int nz, const float* k
     const size_t bytes = pad ? (size_t)pad->sx * pad->sy * pad->sz * sizeof(float) : p.real_bytes();
     cudaStream_t st = p.stream;
 
-    bool any_pageable = false, any_device = false;
-    for (int b = 0; b < n; ++b) {
-        const HostMem k = classify_pointer(ims[b], dev);
-        any_pageable = any_pageable || k == HostMem::Pageable;
-        any_device = any_device || k == HostMem::Device;
-    }
     const bool window = prepare_psf(p, kernel, is_device_ptr(kernel, dev), pdims, save_memory, st);
     auto convolve = [&](float* d) {
         if (pad) padded_convolve_device(p, d, *pad, st, [] {});
         else if (window) run_convolve_window(p, d, st);
         else run_convolve(p, d, st);
     };
-    if (any_device) {   // device-resident blocks: nothing to overlap
-        for (int b = 0; b < n; ++b) {
+    if (kinds.any_device) {   // device-resident blocks: nothing to overlap
+        if (kinds.any_host) throw std::runtime_error("fcb200: a batch must be all host or all device pointers");
+        for (int b = next(); b >= 0; b = next()) {
             if (classify_pointer(ims[b], dev) != HostMem::Device)
                 throw std::runtime_error("fcb200: a batch must be all host or all device pointers");
+            check_real_alignment(ims[b], nx);
             convolve(ims[b]);
         }
         FC_CUDA(cudaStreamSynchronize(st));
@@ -454,11 +423,13 @@ void batch_core(float* const* ims, int n, int nx, int ny, int nz, const float* k
     batch_resources(p);
     static const bool staging_on = env_flag("FCB200_STAGING", true);
 
-    if (!any_pageable || !staging_on) {
-        // everything is enqueued up front; the three streams are ordered by events only
-        for (int b = 0; b < n; ++b) {
-            const int s = b % 3;
-            if (b >= 3) FC_CUDA(cudaStreamWaitEvent(p.s_h2d, p.ev_down[s], 0));   // buffer free again
+    if (!kinds.any_pageable || !staging_on) {
+        // three streams ordered by events; the host only waits for a ring slot to drain before it takes another block
+        for (int count = 0;; ++count) {
+            const int s = count % 3;
+            if (count >= 3) FC_CUDA(cudaEventSynchronize(p.ev_down[s]));
+            const int b = next();
+            if (b < 0) break;
             FC_CUDA(cudaMemcpyAsync(p.d_ring[s], ims[b], bytes, cudaMemcpyHostToDevice, p.s_h2d));
             FC_CUDA(cudaEventRecord(p.ev_up[s], p.s_h2d));
             FC_CUDA(cudaStreamWaitEvent(st, p.ev_up[s], 0));
@@ -473,69 +444,84 @@ void batch_core(float* const* ims, int n, int nx, int ny, int nz, const float* k
         return;
     }
 
-    // pageable blocks: an uploader thread stages block after block; this thread enqueues the convolutions and
-    // drains the results.  Host-side counters order the event records against the waits that use them.
+    // pageable blocks: an uploader thread takes block after block and stages it; this thread enqueues the
+    // convolutions and drains the results.  Host-side counters order the event records against the waits that use them.
     p.stager.prepare();
     std::mutex mu;
     std::condition_variable cv;
-    int uploaded = 0, downloaded = 0;
+    std::vector<int> order;   // blocks in the order the uploader took them
+    bool upload_done = false;
+    int downloaded = 0;
     std::string upload_error;
     std::thread uploader([&] {
         try {
             FC_CUDA(cudaSetDevice(dev));
-            for (int b = 0; b < n; ++b) {
-                const int s = b % 3;
+            for (int i = 0;; ++i) {
+                const int s = i % 3;
                 {
                     std::unique_lock<std::mutex> l(mu);
-                    cv.wait(l, [&] { return downloaded >= b - 2; });   // ring slot drained
+                    cv.wait(l, [&] { return downloaded >= i - 2; });   // ring slot drained
                 }
+                const int b = next();
+                if (b < 0) break;
                 p.stager.upload(p.d_ring[s], ims[b], bytes, p.s_h2d);
                 FC_CUDA(cudaEventRecord(p.ev_up[s], p.s_h2d));
                 {
                     std::lock_guard<std::mutex> l(mu);
-                    uploaded = b + 1;
+                    order.push_back(b);
                 }
                 cv.notify_all();
             }
         } catch (const std::exception& e) {
             std::lock_guard<std::mutex> l(mu);
             upload_error = e.what();
-            uploaded = n;
-            cv.notify_all();
         }
+        {
+            std::lock_guard<std::mutex> l(mu);
+            upload_done = true;
+        }
+        cv.notify_all();
     });
     std::string error;
     try {
-        int next = 0;   // next block whose convolution has not been enqueued yet
-        for (int b = 0; b < n && error.empty(); ++b) {
+        int next_conv = 0;   // next uploaded block whose convolution has not been enqueued yet
+        for (int i = 0;; ++i) {
+            bool finished = false;
             for (;;) {
                 int up;
                 {
                     std::unique_lock<std::mutex> l(mu);
-                    if (next <= b) cv.wait(l, [&] { return uploaded > next; });
-                    up = uploaded;
+                    if (next_conv <= i) cv.wait(l, [&] { return (int)order.size() > next_conv || upload_done; });
+                    up = (int)order.size();
                     if (!upload_error.empty()) throw std::runtime_error(upload_error);
+                    finished = upload_done && up <= i;
                 }
-                if (next >= n || next >= up || next > b + 1) break;
-                const int s = next % 3;
+                if (next_conv >= up || next_conv > i + 1) break;
+                const int s = next_conv % 3;
                 FC_CUDA(cudaStreamWaitEvent(st, p.ev_up[s], 0));
                 convolve(p.d_ring[s]);
                 FC_CUDA(cudaEventRecord(p.ev_comp[s], st));
-                ++next;
+                ++next_conv;
             }
-            const int s = b % 3;
+            if (finished) break;
+            int b;
+            {
+                std::lock_guard<std::mutex> l(mu);
+                b = order[(size_t)i];
+            }
+            const int s = i % 3;
             FC_CUDA(cudaStreamWaitEvent(p.s_d2h, p.ev_comp[s], 0));
             p.stager.download(ims[b], p.d_ring[s], bytes, p.s_d2h);
             {
                 std::lock_guard<std::mutex> l(mu);
-                downloaded = b + 1;
+                downloaded = i + 1;
             }
             cv.notify_all();
         }
     } catch (const std::exception& e) {
         error = e.what();
         std::lock_guard<std::mutex> l(mu);
-        downloaded = n + 3;   // release the uploader
+        downloaded = 1 << 30;   // release the uploader
         cv.notify_all();
     }
     uploader.join();
@@ -543,6 +529,31 @@ void batch_core(float* const* ims, int n, int nx, int ny, int nz, const float* k
     cudaStreamSynchronize(p.s_d2h);
     cudaStreamSynchronize(st);
     if (!error.empty()) throw std::runtime_error(error);
+}
+
+BatchKinds classify_batch(float* const* ims, int n, int dev)
+{
+    BatchKinds k{};
+    for (int b = 0; b < n; ++b) {
+        const HostMem m = classify_pointer(ims[b], dev);
+        k.any_pageable = k.any_pageable || m == HostMem::Pageable;
+        k.any_device = k.any_device || m == HostMem::Device;
+        k.any_host = k.any_host || m != HostMem::Device;
+    }
+    return k;
+}
+
+}  // namespace fcb200
+
+namespace {
+
+void batch_single(float* const* ims, int n, int nx, int ny, int nz, const float* kernel, const int* pdims, int dev,
+                  bool save_memory, const PadGeom* pad = nullptr)
+{
+    if (n <= 0) return;
+    int counter = 0;
+    batch_core(ims, [&] { return counter < n ? counter++ : -1; }, classify_batch(ims, n, dev), nx, ny, nz, kernel, pdims,
+               dev, save_memory, pad);
 }
 
 // host spectrum [nz][ny][xc] (what numpy.fft.rfftn returns)  <->  device layout [nz][ny][xcp]
@@ -581,8 +592,19 @@ void convolution3DfftCUDAInPlaceSaveMemory(imageType* im, int* imDim, imageType*
 {
     // Same contract as InPlace, same numbers up to fp32 round-off, but the image-sized PSF spectrum is never
     // materialised when the placed PSF spans <= 16 z planes ("SaveMemory").
+    // A HOST volume that does not fit on devCUDA (or FCB200_SLAB=1) is spread in z slabs over every device with
+    // peer access to devCUDA: the 3D transposes become peer stores over NVLink and each device builds only its own
+    // slab of the PSF spectrum (fc_multi.cu) -- BASELINE config 5, which overflows `int` in the reference
+    // (src/convolution3Dfft.cu:423-436).
     guarded([&] {
         check_dims(imDim, kernelDim);
+        if (classify_pointer(im, devCUDA) != HostMem::Device) {
+            const std::vector<int> devs = slab_devices_for(imDim, devCUDA, true);
+            if (devs.size() >= 2) {
+                slab_convolve(im, nullptr, imDim, kernel, kernelDim, devs.data(), (int)devs.size());
+                return;
+            }
+        }
         const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
         convolve_core(im, imDim[0], imDim[1], imDim[2], kernel, pdims, devCUDA, false, nullptr, true);
     });
@@ -595,7 +617,7 @@ void fcb200_convolve_batch(imageType* const* ims, int n, const int* imDim, const
         check_dims(imDim, kernelDim);
         if (!ims && n > 0) throw std::runtime_error("fcb200: ims is NULL");
         const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
-        batch_core(ims, n, imDim[0], imDim[1], imDim[2], kernel, pdims, devCUDA, false);
+        batch_single(ims, n, imDim[0], imDim[1], imDim[2], kernel, pdims, devCUDA, false);
     });
 }
 
@@ -627,7 +649,7 @@ void fcb200_convolve_batch_padded(imageType* const* ims, int n, const int* imDim
         int pd[3];
         const PadGeom g = make_pad_geom(imDim, kernelDim, mode, policy, pd);
         const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], pd[0], pd[1], pd[2]};
-        batch_core(ims, n, pd[0], pd[1], pd[2], kernel, pdims, devCUDA, false, &g);
+        batch_single(ims, n, pd[0], pd[1], pd[2], kernel, pdims, devCUDA, false, &g);
     });
 }
 
@@ -1043,7 +1065,61 @@ void fcb200_slab_psf(const imageType* kernel_dev, const int* kernelDim, const in
     });
 }
 
-void fcb200_release(void) { release_all_plans(); }
+// ---- single-process multi-GPU entry points (fc_multi.cu) ----------------------------------------------
+void fcb200_convolve_slab(imageType* im, const int* imDim, const imageType* kernel, const int* kernelDim, const int* devs,
+                          int ndev)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        if (!im) throw std::runtime_error("fcb200: im is NULL");
+        slab_convolve(im, nullptr, imDim, kernel, kernelDim, devs, ndev);
+    });
+}
+
+void fcb200_convolve_slab_device(imageType* const* slabs, const int* imDim, const imageType* kernel, const int* kernelDim,
+                                 const int* devs, int ndev)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        if (!slabs) throw std::runtime_error("fcb200: slabs is NULL");
+        slab_convolve(nullptr, slabs, imDim, kernel, kernelDim, devs, ndev);
+    });
+}
+
+int fcb200_slab_last_timing(const int* imDim, const int* devs, int ndev, float* ms, int cap)
+{
+    return guarded([&] {
+        check_dims(imDim, nullptr);
+        return slab_last_timing(imDim, devs, ndev, ms, cap);
+    });
+}
+
+int fcb200_slab_devices(const int* imDim, int devCUDA, int* devs, int cap)
+{
+    return guarded([&] {
+        check_dims(imDim, nullptr);
+        const std::vector<int> d = slab_devices_for(imDim, devCUDA, true);
+        for (int i = 0; i < (int)d.size() && i < cap; ++i) devs[i] = d[(size_t)i];
+        cudaSetDevice(devCUDA);
+        return (int)d.size();
+    });
+}
+
+void fcb200_convolve_batch_multi(imageType* const* ims, int n, const int* imDim, const imageType* kernel,
+                                 const int* kernelDim, const int* devs, int ndev, int* blocks_per_dev)
+{
+    guarded([&] {
+        check_dims(imDim, kernelDim);
+        if (!ims && n > 0) throw std::runtime_error("fcb200: ims is NULL");
+        batch_multi(ims, n, imDim, kernel, kernelDim, devs, ndev, blocks_per_dev);
+    });
+}
+
+void fcb200_release(void)
+{
+    release_multi();
+    release_all_plans();
+}
 void fcb200_profile_enable(int on) { profile_enable(on); }
 int fcb200_profile_read(float* ms_sum, long long* counts, int n) { return profile_read(ms_sum, counts, n); }
 long long fcb200_launch_count(void) { return launch_count(); }

@@ -4,7 +4,6 @@
 // (/root/reference/src/convolution3Dfft.cu:442-559).  Here a plan (twiddle / permutation tables,
 // spectrum workspace, stream) is built once per (device, shape) and cached, thread-safe.
 #include "fc_plan.h"
-#include "fft_xyfused.h"
 
 #include <algorithm>
 #include <atomic>
@@ -707,22 +706,6 @@ bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaSt
 void run_xy_forward_planes(ConvPlan& p, const float* d_real, int z0, int n, cudaStream_t st, const PadGeom* pad)
 {
     const size_t rplane = (size_t)p.g.ny * p.g.nx, splane = (size_t)p.g.ny * p.g.xcp;
-    if (pad == nullptr) {   // one kernel for both passes where the cluster kernel covers the shape (fft_xyfused.cu)
-        XYArgs f{};
-        f.in_real = d_real + z0 * rplane;
-        f.spec = p.d_spec + z0 * splane;
-        f.g = p.g;
-        f.Px = p.px.dev;
-        f.Py = p.py.dev;
-        f.twx = p.d_twx;
-        f.nplanes = n;
-        PassTimer t(kPassXYFwd, st);
-        if (launch_xy_fwd_cluster(f, st)) {
-            count_launches(1);
-            return;
-        }
-        t.cancel();
-    }
     XArgs xa = x_args(p);
     xa.in_real = d_real + z0 * rplane;
     xa.spec = p.d_spec + z0 * splane;
@@ -765,22 +748,6 @@ void run_z_fused(ConvPlan& p, bool window, cudaStream_t st)
 void run_yx_inverse_planes(ConvPlan& p, float* d_real, int z0, int n, cudaStream_t st, const PadGeom* pad)
 {
     const size_t rplane = (size_t)p.g.ny * p.g.nx, splane = (size_t)p.g.ny * p.g.xcp;
-    if (pad == nullptr) {
-        XYArgs f{};
-        f.out_real = d_real + z0 * rplane;
-        f.spec = p.d_spec + z0 * splane;
-        f.g = p.g;
-        f.Px = p.px.dev;
-        f.Py = p.py.dev;
-        f.twx = p.d_twx;
-        f.nplanes = n;
-        PassTimer t(kPassYXInv, st);
-        if (launch_yx_inv_cluster(f, st)) {
-            count_launches(1);
-            return;
-        }
-        t.cancel();
-    }
     {
         PassTimer t(kPassYInv, st);
         col_pass(y_args(p, p.d_spec + z0 * splane), 1, n, st);
@@ -844,10 +811,19 @@ static void check_slab(const ConvPlan& p, int nzl, int nyl)
 }
 
 void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2* send, int nzl, int nyl,
-                         cudaStream_t st, float2* const* peers, int rank, int nzp)
+                         cudaStream_t st, float2* const* peers, int rank, int nzp, int z0, int nz_run)
 {
     check_slab(p, nzl, nyl);
     if (nzp < nzl) throw std::runtime_error("fcb200: slab block pitch nzp must be >= the local plane count");
+    // planes [z0, z0 + nz_run) of the local slab only (host-pointer calls overlap the upload of the next planes)
+    if (nz_run < 0) nz_run = nzl - z0;
+    if (z0 < 0 || nz_run < 0 || z0 + nz_run > nzl) throw std::runtime_error("fcb200: slab plane range out of bounds");
+    if (nz_run == 0) return;
+    const size_t rplane = (size_t)p.g.ny * p.g.nx, splane = (size_t)p.g.ny * p.g.xcp;
+    d_real += (size_t)z0 * rplane;
+    zslab += (size_t)z0 * splane;
+    if (send) send += (size_t)z0 * nyl * p.g.xcp;
+    nzl = nz_run;
     XArgs xa = x_args(p);
     xa.in_real = d_real;
     xa.spec = zslab;
@@ -864,7 +840,7 @@ void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2
     if (peers) {   // store straight into the peers' y-slab buffers [P*nzp][nyl][xcp]: my planes start at rank*nzp
         ya.split = nullptr;
         ya.splitPeers = peers;
-        ya.splitPeerOffset = (long long)rank * nzp * nyl * p.g.xcp;
+        ya.splitPeerOffset = ((long long)rank * nzp + z0) * nyl * p.g.xcp;
     }
     {
         PassTimer t(kPassYFwd, st);
@@ -896,10 +872,17 @@ void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, 
 }
 
 void run_slab_yx_inverse(ConvPlan& p, const float2* recv, float2* zslab, float* d_real, int nzl, int nyl,
-                         cudaStream_t st, int nzp)
+                         cudaStream_t st, int nzp, int z0, int nz_run)
 {
     check_slab(p, nzl, nyl);
     if (nzp < nzl) throw std::runtime_error("fcb200: slab block pitch nzp must be >= the local plane count");
+    if (nz_run < 0) nz_run = nzl - z0;
+    if (z0 < 0 || nz_run < 0 || z0 + nz_run > nzl) throw std::runtime_error("fcb200: slab plane range out of bounds");
+    if (nz_run == 0) return;
+    d_real += (size_t)z0 * p.g.ny * p.g.nx;
+    zslab += (size_t)z0 * p.g.ny * p.g.xcp;
+    recv += (size_t)z0 * nyl * p.g.xcp;
+    nzl = nz_run;
     ColArgs ya = y_args(p, zslab);
     ya.split = const_cast<float2*>(recv);
     ya.splitRows = nyl;
@@ -962,11 +945,16 @@ void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, 
         col_pass(y_args(p, scratch), 0, p.n_planes, st);
     }
     // rows [y0, y0+nyl) of every active plane -> its place in the y-slab; the z pass skips other planes
+    // (one 2D copy per run of consecutive planes: a PSF occupies at most two runs, [0, k/2] and [nz - k/2, nz))
     const size_t row_bytes = (size_t)rows_here * p.g.xcp * sizeof(float2);
-    for (int i = 0; i < p.n_planes; ++i) {
+    for (int i = 0; i < p.n_planes;) {
+        int j = i + 1;
+        while (j < p.n_planes && p.h_planes[(size_t)j] == p.h_planes[(size_t)j - 1] + 1) ++j;
         const int z = p.h_planes[(size_t)i];
-        FC_CUDA(cudaMemcpyAsync(Hslab + (size_t)z * nyl * p.g.xcp, scratch + ((size_t)i * p.g.ny + y0) * p.g.xcp,
-                                row_bytes, cudaMemcpyDeviceToDevice, st));
+        FC_CUDA(cudaMemcpy2DAsync(Hslab + (size_t)z * nyl * p.g.xcp, (size_t)nyl * p.g.xcp * sizeof(float2),
+                                  scratch + ((size_t)i * p.g.ny + y0) * p.g.xcp, (size_t)p.g.ny * p.g.xcp * sizeof(float2),
+                                  row_bytes, (size_t)(j - i), cudaMemcpyDeviceToDevice, st));
+        i = j;
     }
     ColArgs za = z_args(p, Hslab);
     const long long C = (long long)nyl * p.g.xcp;

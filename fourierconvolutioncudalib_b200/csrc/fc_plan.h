@@ -95,7 +95,7 @@ void count_launches(int n);
 
 // pass ids for the optional CUDA-event profile (fcb200_profile_*)
 enum PassId { kPassPsfClear = 0, kPassPsfX, kPassPsfY, kPassPsfZ, kPassXFwd, kPassYFwd, kPassZFused, kPassYInv,
-              kPassXInv, kPassXYFwd, kPassYXInv, kNumPassIds };
+              kPassXInv, kNumPassIds };
 void profile_enable(int on);
 bool profile_enabled();
 int profile_read(float* ms_sum, long long* counts, int n);
@@ -144,14 +144,14 @@ void padded_extents(const int* imDim, const int* kernelDim, int policy, int* pad
 // nzp: planes per exchange block (>= nzl; the same on every rank -- ragged slabs: nzp = ceil(nz / P) while the
 // last rank owns fewer planes).  nyl likewise is the ROW PITCH of a ky block, ceil(ny / P).
 void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2* send, int nzl, int nyl,
-                         cudaStream_t st, float2* const* peers, int rank, int nzp);
+                         cudaStream_t st, float2* const* peers, int rank, int nzp, int z0 = 0, int nz_run = -1);
 // fused z pass on the y-slab spectrum (in place) with the y-slab of the PSF spectrum
 // peers != nullptr: the last inverse stage stores each output plane straight into its owner's receive buffer
 void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, cudaStream_t st,
                       float2* const* peers = nullptr, int rank = 0, int nzl = 0);
 // y + x inverse; the y pass reads the exchange (receive) buffer directly
 void run_slab_yx_inverse(ConvPlan& p, const float2* recv, float2* zslab, float* d_real, int nzl, int nyl,
-                         cudaStream_t st, int nzp);
+                         cudaStream_t st, int nzp, int z0 = 0, int nz_run = -1);
 // PSF spectrum of the rank's y-slab: x and y passes on the planes that hold taps (into scratch, compact),
 // rows [y0, y0+nyl) copied into Hslab, z pass with the plane mask.  Returns nothing; scratch must hold
 // psf_slab_scratch_elems() float2.

@@ -131,6 +131,34 @@ FUNCTION_PREFIX long long fcb200_slab_psf_scratch_elems(const int* imDim, const 
 FUNCTION_PREFIX void fcb200_slab_psf(const imageType* kernel_dev, const int* kernelDim, const int* imDim, int y0, int nyl,
                                     float* H_yslab, float* scratch, int devCUDA, void* stream);
 
+/* ---- single-process multi-GPU (one host process, several devices with peer access; no NCCL, no IPC) -------------
+ * The reference's only multi-GPU hook is cudaSetDevice(devCUDA) (src/convolution3Dfft.cu:409): its callers run one
+ * host thread per GPU.  These entry points do the spreading inside the library.
+ *
+ * fcb200_convolve_slab: ONE volume (host pointer, imDim[0] fastest) convolved in place like convolution3DfftCUDAInPlace,
+ *   cut in z slabs over devs[0..ndev) (rank r = devs[r]; extents need not be divisible by ndev).  One worker thread
+ *   per device; x+y forward -> the y pass stores every ky row straight into its owner's buffer over NVLink -> fused
+ *   z pass with the rank's own slab of the PSF spectrum -> planes stored straight back -> y+x inverse.  The phases are
+ *   ordered by CUDA events across devices.  Volumes of 2^31 voxels and more are fine (64-bit sizes throughout).
+ *   convolution3DfftCUDAInPlaceSaveMemory routes here by itself when a host volume does not fit on devCUDA
+ *   (FCB200_SLAB=1 forces it, =0 forbids it; FCB200_SLAB_DEVICES="0,1,.." picks the devices).
+ * fcb200_convolve_slab_device: the same with the volume already resident: slabs[r] = device pointer on devs[r] of
+ *   rank r's planes [r*nzp, min(d2, (r+1)*nzp)), nzp = ceil(d2/ndev).
+ * fcb200_slab_last_timing: device times of the most recent call for (imDim, devs): ms[4*r + 0..3] = x+y forward,
+ *   fused z (incl. waiting for the peers' rows), y+x inverse (incl. waiting), whole call; returns ranks written.
+ * fcb200_slab_devices: the device list SaveMemory would use for a host volume of imDim on devCUDA (0 = single device).
+ * fcb200_convolve_batch_multi: fcb200_convolve_batch over several devices -- one pipelined batch per device, all
+ *   taking blocks from one shared counter (a device that finishes early takes more); blocks_per_dev (optional,
+ *   ndev ints) receives how many blocks each device convolved.  Host blocks only. */
+FUNCTION_PREFIX void fcb200_convolve_slab(imageType* im, const int* imDim, const imageType* kernel, const int* kernelDim,
+                                         const int* devs, int ndev);
+FUNCTION_PREFIX void fcb200_convolve_slab_device(imageType* const* slabs, const int* imDim, const imageType* kernel,
+                                                const int* kernelDim, const int* devs, int ndev);
+FUNCTION_PREFIX int fcb200_slab_last_timing(const int* imDim, const int* devs, int ndev, float* ms, int cap);
+FUNCTION_PREFIX int fcb200_slab_devices(const int* imDim, int devCUDA, int* devs, int cap);
+FUNCTION_PREFIX void fcb200_convolve_batch_multi(imageType* const* ims, int n, const int* imDim, const imageType* kernel,
+                                                const int* kernelDim, const int* devs, int ndev, int* blocks_per_dev);
+
 /* Frees every cached plan and its device workspace on all devices. */
 FUNCTION_PREFIX void fcb200_release(void);
 /* Number of kernels this library has launched since load (for benchmark accounting). */

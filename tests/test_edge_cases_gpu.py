@@ -108,33 +108,3 @@ def test_release_frees_the_plan_cache(fc, dev):
     free_after, _ = torch.cuda.mem_get_info(dev)
     assert free_after > free_before
     fc.convolution3DfftCUDAInPlace(im, (128, 128, 64), np.ones(27, np.float32) / 27, (3, 3, 3), dev)   # rebuilds
-
-
-def test_cluster_fused_xy_kernels_opt_in(dev):
-    """FCB200_XY_CLUSTER=1 routes 512 x 512 planes through the DSMEM-fused x+y kernels (fft_xyfused.cu); the
-    switch is read once per process, so the run happens in a subprocess and is compared with the default path"""
-    import os
-    import subprocess
-    import sys
-    import tempfile
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = (
-        "import sys, numpy as np\n"
-        f"sys.path.insert(0, {root!r})\n"
-        "import fourierconvolutioncudalib_b200 as fc\n"
-        "rng = np.random.default_rng(8)\n"
-        "im = (rng.random(512 * 512 * 20, dtype=np.float32) * 100).astype(np.float32)\n"
-        "k = rng.random(5 * 7 * 3, dtype=np.float32)\n"
-        f"fc.convolution3DfftCUDAInPlace(im, (512, 512, 20), k, (5, 7, 3), {dev})\n"
-        "np.save(sys.argv[1], im)\n")
-    outs = []
-    for flag in ("0", "1"):
-        with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as f:
-            path = f.name
-        env = dict(os.environ, FCB200_XY_CLUSTER=flag)
-        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
-        outs.append(np.load(path))
-        os.unlink(path)
-    scale = np.abs(outs[0]).max()
-    assert np.abs(outs[0] - outs[1]).max() <= 2e-6 * scale
-    assert np.abs(outs[0]).max() > 0
