@@ -350,7 +350,11 @@ static std::shared_ptr<ConvPlan> build_plan(int device, int nx, int ny, int nz, 
     p->g = make_geometry(nx, ny, nz);
     make_axis(p->px, p->g.M, 2);
     make_axis(p->py, ny, 0);
-    make_axis(p->pz, nz, 1);
+    static const int zstyle = [] {   // experiments: FCB200_ZSTYLE=0 plans the z axis like the y axis (L = 256 as (16,16))
+        const char* e = std::getenv("FCB200_ZSTYLE");
+        return e ? std::atoi(e) : 1;
+    }();
+    make_axis(p->pz, nz, zstyle);
     if (!x_pass_supported(p->g, p->px.dev))
         throw std::runtime_error("fcb200: fastest image extent too large for the shared-memory x pass");
     p->txp_y = col_pick_txp(p->py.dev);
@@ -432,6 +436,7 @@ static ColArgs y_args(ConvPlan& p, float2* data)
 
 static void col_pass(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
+    if (launch_col_tma(a, mode, ngroups, st)) return;
     if (launch_col_static(a, mode, ngroups, st)) return;
     if (a.split || a.splitPeers) {   // split (exchange-buffer / peer) layout: static kernels or the generic one
         launch_col(a, mode, ngroups, st);

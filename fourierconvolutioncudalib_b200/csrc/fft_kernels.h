@@ -74,6 +74,9 @@ bool launch_psf_z_pruned(const ColArgs& a, int z0, cudaStream_t st);
 // fast path (fft_col_fast.cu): first/last stage fused with the global loads/stores
 bool col_fast_supported(const AxisPlanDev& P);
 void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
+// TMA-staged persistent kernels (fft_col_tma.cu): tensor-map loads and stores, digit reversal done by the store's
+// tensor map; return false when no configuration matches (plan, layout, mode)
+bool launch_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
 // compile-time specialised kernels (fft_static.cu); return false when none matches the plan
 bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
 // fused z pass that derives the PSF-spectrum tile on the fly from the <=16 window planes starting at z0;
