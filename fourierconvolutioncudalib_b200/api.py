@@ -116,6 +116,12 @@ def slab_devices(imDim, devCUDA=0):
     return list(out[:n])
 
 
+def psf_window_planes(imDim, kernelDim, devCUDA=0):
+    """extension (fcb200_psf_window_planes): 16 / 32 / 64 when the fused z pass derives the PSF spectrum on the fly
+    from that many PSF planes, 0 when the image-sized PSF spectrum is materialised"""
+    return _load().fcb200_psf_window_planes(_ints(imDim), _ints(kernelDim), int(devCUDA))
+
+
 def slab_partition(imDim, world):
     """(nzp, nyl, [planes of rank r]) of the slab decomposition used by convolve_slab*"""
     d0, d1, d2 = (int(v) for v in imDim)

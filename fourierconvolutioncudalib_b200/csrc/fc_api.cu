@@ -47,24 +47,39 @@ bool is_device_ptr(const void* p, int dev)
 bool prepare_psf(ConvPlan& p, const float* kernel, bool k_dev, const int* pdims, bool save_memory, cudaStream_t st)
 {
     static const bool cache_on = env_flag("FCB200_PSF_CACHE", true);
+    // On-the-fly PSF spectrum (the SaveMemory path) is also what InPlace runs when the placed PSF fits a window of
+    // 16 / 32 / 64 z planes: the fused z pass then reads 2 KB .. 8 KB of window rows per tile instead of a whole
+    // PSF-spectrum tile, and no PSF z pass runs at all (C3: step 0.63 -> 0.53 ms).  FCB200_OTF_INPLACE=0 keeps InPlace on
+    // the materialised spectrum.
+    const bool otf_inplace = env_flag("FCB200_OTF_INPLACE", true);   // read per call: tests and tools switch it
     const size_t ktaps = (size_t)pdims[0] * pdims[1] * pdims[2];
-    if (!k_dev && !save_memory && cache_on && p.h_valid && std::memcmp(p.h_dims, pdims, sizeof(int) * 6) == 0 &&
-        p.h_taps.size() == ktaps && std::memcmp(p.h_taps.data(), kernel, ktaps * sizeof(float)) == 0)
-        return false;
+    auto same_taps = [&](bool valid, const int* dims, const std::vector<float>& taps) {
+        return !k_dev && cache_on && valid && std::memcmp(dims, pdims, sizeof(int) * 6) == 0 && taps.size() == ktaps &&
+               std::memcmp(taps.data(), kernel, ktaps * sizeof(float)) == 0;
+    };
+    const bool window = (save_memory || otf_inplace) && psf_window_applies(p, pdims, st);
+    if (window && same_taps(p.hwin_valid, p.hwin_dims, p.hwin_taps)) return true;
+    if (!window && same_taps(p.h_valid, p.h_dims, p.h_taps)) return false;
     const float* d_kernel = kernel;
     if (!k_dev) {
         if (ktaps > p.kernel_cap) {
             cudaFree(p.d_kernel);
             p.d_kernel = nullptr;
+            p.kernel_cap = 0;
             FC_CUDA(cudaMalloc(&p.d_kernel, ktaps * sizeof(float)));
             p.kernel_cap = ktaps;
         }
         FC_CUDA(cudaMemcpyAsync(p.d_kernel, kernel, ktaps * sizeof(float), cudaMemcpyHostToDevice, st));
         d_kernel = p.d_kernel;
     }
-    // SaveMemory: PSF spectrum derived on the fly inside the fused z kernel from <= 16 PSF planes (no
-    // image-sized PSF buffer); falls back to the materialised spectrum when the PSF spans more planes
-    if (save_memory && run_psf_window(p, d_kernel, pdims, st)) return true;
+    if (window && run_psf_window(p, d_kernel, pdims, st)) {
+        if (!k_dev && cache_on) {
+            p.hwin_taps.assign(kernel, kernel + ktaps);
+            std::memcpy(p.hwin_dims, pdims, sizeof(int) * 6);
+            p.hwin_valid = true;
+        }
+        return true;
+    }
     run_psf_spectrum(p, d_kernel, pdims, st);
     if (!k_dev && cache_on) {
         p.h_taps.assign(kernel, kernel + ktaps);
@@ -119,6 +134,12 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
     static const bool staging_on = env_flag("FCB200_STAGING", true);
     const bool staged = im_kind == HostMem::Pageable && staging_on;
 
+    workspace_acquire(p, st);
+    struct Release {
+        ConvPlan& p;
+        cudaStream_t st;
+        ~Release() { try { workspace_release(p, st); } catch (...) {} }
+    } release_on_exit{p, st};
     PsfSide psf(p, st);
     const bool window = prepare_psf(p, kernel, k_dev, pdims, save_memory, psf.stream());
     psf.done();
@@ -203,7 +224,7 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
 // Device-resident unpadded volume d_src convolved on the padded grid of plan p, fused form (the x passes pad and
 // crop, see fft_xpass.cuh); before_z() runs between the forward passes and the fused z pass (PSF join).
 template <typename F>
-void padded_convolve_device(ConvPlan& p, float* d_src, const PadGeom& g, cudaStream_t st, F&& before_z)
+void padded_convolve_device(ConvPlan& p, float* d_src, const PadGeom& g, cudaStream_t st, F&& before_z, bool window)
 {
     const size_t splane = (size_t)p.g.ny * p.g.xcp;
     const int z_lo = g.oz, z_hi = g.oz + g.sz;
@@ -215,7 +236,7 @@ void padded_convolve_device(ConvPlan& p, float* d_src, const PadGeom& g, cudaStr
         else run_xy_forward_planes(p, d_src, r0[i], rn[i], st, &g);
     }
     before_z();
-    run_z_fused(p, false, st);
+    run_z_fused(p, window, st);
     run_yx_inverse_planes(p, d_src, z_lo, g.sz, st, &g);
 }
 
@@ -263,8 +284,14 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
         d_src = p.d_unpadded;
     }
 
+    workspace_acquire(p, st);
+    struct Release {
+        ConvPlan& p;
+        cudaStream_t st;
+        ~Release() { try { workspace_release(p, st); } catch (...) {} }
+    } release_on_exit{p, st};
     PsfSide psf(p, st);
-    prepare_psf(p, kernel, k_dev, pdims, false, psf.stream());
+    const bool window = prepare_psf(p, kernel, k_dev, pdims, false, psf.stream());
     psf.done();
 
     const size_t splane = (size_t)p.g.ny * p.g.xcp;
@@ -330,7 +357,7 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
         }
         if (mode != 0) halo_forward();
         psf.join();
-        run_z_fused(p, false, st);
+        run_z_fused(p, window, st);
         for (int c = 0; c < nch; ++c) {
             const int z0 = z0_of(c), n = z0_of(c + 1) - z0;
             if (n <= 0) continue;
@@ -352,7 +379,7 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
     forward_planes(z_lo, g.sz);
     halo_forward();
     psf.join();
-    run_z_fused(p, false, st);
+    run_z_fused(p, window, st);
     inverse_planes(0, g.sz);
     if (!im_dev) {
         if (staged) p.stager.download(im, d_src, src_bytes, st);
@@ -402,10 +429,16 @@ void batch_core(float* const* ims, const std::function<int()>& next, BatchKinds 
     // padded batches: (nx, ny, nz) is the padded grid of the plan, the blocks and the ring buffers hold UNPADDED volumes
     const size_t bytes = pad ? (size_t)pad->sx * pad->sy * pad->sz * sizeof(float) : p.real_bytes();
     cudaStream_t st = p.stream;
+    workspace_acquire(p, st);
+    struct Release {
+        ConvPlan& p;
+        cudaStream_t st;
+        ~Release() { try { workspace_release(p, st); } catch (...) {} }
+    } release_on_exit{p, st};
 
     const bool window = prepare_psf(p, kernel, is_device_ptr(kernel, dev), pdims, save_memory, st);
     auto convolve = [&](float* d) {
-        if (pad) padded_convolve_device(p, d, *pad, st, [] {});
+        if (pad) padded_convolve_device(p, d, *pad, st, [] {}, window);
         else if (window) run_convolve_window(p, d, st);
         else run_convolve(p, d, st);
     };
@@ -914,6 +947,7 @@ void fcb200_debug_psf_spectrum(const imageType* kernel, const int* kernelDim, co
         if (ktaps > p.kernel_cap) {
             cudaFree(p.d_kernel);
             p.d_kernel = nullptr;
+            p.kernel_cap = 0;
             FC_CUDA(cudaMalloc(&p.d_kernel, ktaps * sizeof(float)));
             p.kernel_cap = ktaps;
         }
@@ -931,6 +965,9 @@ void fcb200_slab_xy_forward(const imageType* real_slab, float* zslab_spec, float
     guarded([&] {
         check_dims(imDim, nullptr);
         DeviceGuard guard(devCUDA);
+        check_real_alignment(real_slab, imDim[0]);
+        check_spec_alignment(zslab_spec);
+        check_spec_alignment(send);
         auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
         std::lock_guard<std::mutex> lock(plan->mu);
         run_slab_xy_forward(*plan, real_slab, reinterpret_cast<float2*>(zslab_spec), reinterpret_cast<float2*>(send), nzl,
@@ -943,6 +980,8 @@ void fcb200_slab_z_fused(float* yslab_spec, const float* H_yslab, const int* imD
     guarded([&] {
         check_dims(imDim, nullptr);
         DeviceGuard guard(devCUDA);
+        check_spec_alignment(yslab_spec);
+        check_spec_alignment(H_yslab);
         auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
         std::lock_guard<std::mutex> lock(plan->mu);
         run_slab_z_fused(*plan, reinterpret_cast<float2*>(yslab_spec), reinterpret_cast<const float2*>(H_yslab), nyl,
@@ -956,6 +995,9 @@ void fcb200_slab_yx_inverse(const float* recv, float* zslab_spec, imageType* rea
     guarded([&] {
         check_dims(imDim, nullptr);
         DeviceGuard guard(devCUDA);
+        check_real_alignment(real_slab, imDim[0]);
+        check_spec_alignment(zslab_spec);
+        check_spec_alignment(recv);
         auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
         std::lock_guard<std::mutex> lock(plan->mu);
         run_slab_yx_inverse(*plan, reinterpret_cast<const float2*>(recv), reinterpret_cast<float2*>(zslab_spec), real_slab,
@@ -969,6 +1011,8 @@ void fcb200_slab_xy_forward_peer(const imageType* real_slab, float* zslab_spec, 
     guarded([&] {
         check_dims(imDim, nullptr);
         DeviceGuard guard(devCUDA);
+        check_real_alignment(real_slab, imDim[0]);
+        check_spec_alignment(zslab_spec);
         auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
         std::lock_guard<std::mutex> lock(plan->mu);
         run_slab_xy_forward(*plan, real_slab, reinterpret_cast<float2*>(zslab_spec), nullptr, nzl, nyl, (cudaStream_t)stream,
@@ -982,6 +1026,8 @@ void fcb200_slab_z_fused_peer(float* yslab_spec, const float* H_yslab, void* con
     guarded([&] {
         check_dims(imDim, nullptr);
         DeviceGuard guard(devCUDA);
+        check_spec_alignment(yslab_spec);
+        check_spec_alignment(H_yslab);
         auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2], false);
         std::lock_guard<std::mutex> lock(plan->mu);
         run_slab_z_fused(*plan, reinterpret_cast<float2*>(yslab_spec), reinterpret_cast<const float2*>(H_yslab), nyl,
@@ -1112,6 +1158,18 @@ void fcb200_convolve_batch_multi(imageType* const* ims, int n, const int* imDim,
         check_dims(imDim, kernelDim);
         if (!ims && n > 0) throw std::runtime_error("fcb200: ims is NULL");
         batch_multi(ims, n, imDim, kernel, kernelDim, devs, ndev, blocks_per_dev);
+    });
+}
+
+int fcb200_psf_window_planes(const int* imDim, const int* kernelDim, int devCUDA)
+{
+    return guarded([&] {
+        check_dims(imDim, kernelDim);
+        DeviceGuard guard(devCUDA);
+        auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2]);
+        std::lock_guard<std::mutex> lock(plan->mu);
+        const int pdims[6] = {kernelDim[0], kernelDim[1], kernelDim[2], imDim[0], imDim[1], imDim[2]};
+        return psf_window_applies(*plan, pdims, plan->stream) ? plan->psf_window_planes : 0;
     });
 }
 

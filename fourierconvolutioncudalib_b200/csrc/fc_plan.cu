@@ -282,6 +282,7 @@ ConvPlan::~ConvPlan()
     }
     for (cudaEvent_t e : ev_chunk)
         if (e) cudaEventDestroy(e);
+    if (ev_busy) cudaEventDestroy(ev_busy);
     if (s_psf) cudaStreamDestroy(s_psf);
     if (ev_psf_fork) cudaEventDestroy(ev_psf_fork);
     if (ev_psf_done) cudaEventDestroy(ev_psf_done);
@@ -401,6 +402,17 @@ std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz, bool work
     return p;
 }
 
+void workspace_acquire(ConvPlan& p, cudaStream_t st)
+{
+    if (p.ev_busy) FC_CUDA(cudaStreamWaitEvent(st, p.ev_busy, 0));
+}
+
+void workspace_release(ConvPlan& p, cudaStream_t st)
+{
+    if (!p.ev_busy) FC_CUDA(cudaEventCreateWithFlags(&p.ev_busy, cudaEventDisableTiming));
+    FC_CUDA(cudaEventRecord(p.ev_busy, st));
+}
+
 void release_all_plans()
 {
     std::lock_guard<std::mutex> lock(g_cache_mu);
@@ -429,6 +441,7 @@ static ColArgs y_args(ConvPlan& p, float2* data)
     a.splitRows = 0;
     a.splitBlock = a.splitGroup = 0;
     a.winSlot = nullptr;
+    a.winPlanes = 0;
     a.splitPeers = nullptr;
     a.splitPeerOffset = 0;
     return a;
@@ -467,6 +480,7 @@ static ColArgs z_args(ConvPlan& p, float2* data)
     a.splitRows = 0;
     a.splitBlock = a.splitGroup = 0;
     a.winSlot = nullptr;
+    a.winPlanes = 0;
     a.splitPeers = nullptr;
     a.splitPeerOffset = 0;
     return a;
@@ -509,25 +523,56 @@ void run_forward(ConvPlan& p, const float* d_real, float2* dst, int passes, cuda
     }
 }
 
+// Planes of the padded PSF volume that the PSF passes work on.  mask[z] = 1: plane z holds at least one tap.
+// When every such plane lies inside a window of 16, 32 or 64 consecutive planes (mod nz) the list is that window in
+// WINDOW order (list entry n = plane (z0 + n) mod nz, tapless planes included: they transform to zeros), so that the
+// compact buffers of the on-the-fly path are indexed by window position; otherwise the planes with taps, ascending.
+static void psf_plane_list(const int* pdims, const Geometry& g, std::vector<unsigned char>& mask, std::vector<int>& planes,
+                           int& win_z0, int& win_planes)
+{
+    std::vector<int> arows = psf_active_rows(pdims + 3, pdims, g.nx);
+    mask.assign((size_t)g.nz, 0);
+    for (int r : arows) mask[(size_t)(r / g.ny)] = 1;
+    std::vector<int> active;
+    for (int z = 0; z < g.nz; ++z)
+        if (mask[(size_t)z]) active.push_back(z);
+    win_z0 = -1;
+    win_planes = 0;
+    for (int wp = 16; wp <= 64 && wp <= g.nz && win_z0 < 0; wp *= 2)
+        for (int z0 : active) {
+            bool ok = true;
+            for (int z : active) ok = ok && (((z - z0) % g.nz + g.nz) % g.nz < wp);
+            if (ok) {
+                win_z0 = z0;
+                win_planes = wp;
+                break;
+            }
+        }
+    planes.clear();
+    if (win_z0 >= 0)
+        for (int n = 0; n < win_planes; ++n) planes.push_back((win_z0 + n) % g.nz);
+    else
+        planes = active;
+}
+
 // PSF pruning lists (cached per placement dims): only z planes that receive a tap are non-zero before
 // the z pass.  The x pass runs on every row of those planes (rows without taps transform to zeros, so
 // nothing needs clearing), the y pass on those planes only, and the z pass reads only those planes.
 static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
 {
     if (std::memcmp(p.psf_key, pdims, sizeof(int) * 6) != 0 || p.d_rows == nullptr) {
-        std::vector<int> arows = psf_active_rows(pdims + 3, pdims, p.g.nx);
-        std::vector<unsigned char> mask((size_t)p.g.nz, 0);
-        for (int r : arows) mask[(size_t)(r / p.g.ny)] = 1;
+        std::vector<unsigned char> mask;
         std::vector<int> planes, rows;
-        for (int z = 0; z < p.g.nz; ++z)
-            if (mask[(size_t)z]) {
-                planes.push_back(z);
-                for (int y = 0; y < p.g.ny; ++y) rows.push_back(z * p.g.ny + y);
-            }
+        int win_z0 = -1, win_planes = 0;
+        psf_plane_list(pdims, p.g, mask, planes, win_z0, win_planes);
+        for (int z : planes)
+            for (int y = 0; y < p.g.ny; ++y) rows.push_back(z * p.g.ny + y);
         FC_CUDA(cudaStreamSynchronize(st));  // earlier launches on this stream may still read the old lists
+        std::memset(p.psf_key, 0, sizeof(p.psf_key));   // a failed rebuild must not leave a key that matches stale lists
         if (rows.size() > p.rows_cap) {
             cudaFree(p.d_rows);
             p.d_rows = nullptr;
+            p.rows_cap = 0;
             FC_CUDA(cudaMalloc(&p.d_rows, sizeof(int) * rows.size()));
             p.rows_cap = rows.size();
         }
@@ -539,16 +584,9 @@ static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
         p.n_rows = (long long)rows.size();
         p.n_planes = (int)planes.size();
         p.h_planes = planes;
-        // window of 16 consecutive planes (mod nz) that holds every active plane, if there is one
-        p.psf_window_z0 = -1;
-        for (int z0 : planes) {
-            bool ok = true;
-            for (int z : planes) ok = ok && (((z - z0) % p.g.nz + p.g.nz) % p.g.nz < 16);
-            if (ok) {
-                p.psf_window_z0 = z0;
-                break;
-            }
-        }
+        p.psf_window_z0 = win_z0;
+        p.psf_window_planes = win_planes;
+        p.hwin_valid = false;
         // CSR tap lists over the processed rows: tap (a,b,c) -> flat position (reference placement,
         // src/convolution3Dfft.cu:145-164) -> (row, x)
         {
@@ -602,6 +640,7 @@ static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
                 cudaFree(p.d_tap_x);
                 cudaFree(p.d_tap_idx);
                 p.d_tap_x = p.d_tap_idx = nullptr;
+                p.taps_cap = 0;
                 FC_CUDA(cudaMalloc(&p.d_tap_x, sizeof(int) * K));
                 FC_CUDA(cudaMalloc(&p.d_tap_idx, sizeof(int) * K));
                 p.taps_cap = K;
@@ -652,20 +691,40 @@ void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cuda
         PassTimer t(kPassPsfZ, st);
         ColArgs za = z_args(p, p.d_H);
         za.rowMask = p.d_plane_mask;
-        if (!(p.psf_window_z0 >= 0 && launch_psf_z_pruned(za, p.psf_window_z0, st))) col_pass(za, 0, 1, st);
+        if (!(p.psf_window_z0 >= 0 && p.psf_window_planes == 16 && launch_psf_z_pruned(za, p.psf_window_z0, st)))
+            col_pass(za, 0, 1, st);
     }
     count_launches(3);
 }
 
-bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
+static bool otf_launch(ConvPlan& p, ColArgs& za, cudaStream_t st, bool probe)
+{
+    za.winPlanes = p.psf_window_planes;
+    if (launch_col_otf_tma(za, 1, p.psf_window_z0, st, probe)) return true;
+    return p.psf_window_planes == 16 && launch_col_otf(za, 1, p.psf_window_z0, st, probe);
+}
+
+bool psf_window_applies(ConvPlan& p, const int* pdims, cudaStream_t st)
 {
     psf_lists(p, pdims, st);
-    if (p.psf_window_z0 < 0 || p.n_planes > 16) return false;
-    {
-        ColArgs probe = z_args(p, p.d_spec);
-        if (!launch_col_otf(probe, 1, p.psf_window_z0, st, true)) return false;
+    if (p.psf_window_z0 < 0) return false;
+    ColArgs probe = z_args(p, p.d_spec);
+    return otf_launch(p, probe, st, true);
+}
+
+bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
+{
+    if (!psf_window_applies(p, pdims, st)) return false;
+    const size_t need = (size_t)p.psf_window_planes * p.g.ny * p.g.xcp;
+    if (need > p.hwin_cap) {
+        FC_CUDA(cudaStreamSynchronize(st));
+        cudaFree(p.d_Hwin);
+        p.d_Hwin = nullptr;
+        p.hwin_cap = 0;
+        FC_CUDA(cudaMalloc(&p.d_Hwin, need * sizeof(float2)));
+        p.hwin_cap = need;
     }
-    if (!p.d_Hwin) FC_CUDA(cudaMalloc(&p.d_Hwin, (size_t)16 * p.g.ny * p.g.xcp * sizeof(float2)));
+    p.hwin_valid = false;
     if (!p.d_win_slot) FC_CUDA(cudaMalloc(&p.d_win_slot, 16 * sizeof(int)));
     if (std::memcmp(p.win_key, pdims, sizeof(int) * 6) != 0) {
         int slots[16];
@@ -741,7 +800,7 @@ void run_z_fused(ConvPlan& p, bool window, cudaStream_t st)
     if (window) {
         za.H = p.d_Hwin;
         za.winSlot = p.d_win_slot;
-        if (!launch_col_otf(za, 1, p.psf_window_z0, st, false))
+        if (!otf_launch(p, za, st, false))
             throw std::runtime_error("fcb200: internal error, on-the-fly z pass unavailable");
     } else {
         za.H = p.d_H;
@@ -910,12 +969,11 @@ void run_slab_yx_inverse(ConvPlan& p, const float2* recv, float2* zslab, float* 
 
 size_t psf_slab_scratch_elems(ConvPlan& p, const int* pdims)
 {
-    std::vector<int> arows = psf_active_rows(pdims + 3, pdims, p.g.nx);
-    std::vector<unsigned char> mask((size_t)p.g.nz, 0);
-    for (int r : arows) mask[(size_t)(r / p.g.ny)] = 1;
-    size_t planes = 0;
-    for (unsigned char m : mask) planes += m;
-    return planes * (size_t)p.g.ny * p.g.xcp;
+    std::vector<unsigned char> mask;
+    std::vector<int> planes;
+    int z0 = -1, wp = 0;
+    psf_plane_list(pdims, p.g, mask, planes, z0, wp);
+    return planes.size() * (size_t)p.g.ny * p.g.xcp;
 }
 
 void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, int nyl, float2* Hslab,
@@ -969,7 +1027,8 @@ void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, 
     za.rowMask = p.d_plane_mask;
     {
         PassTimer t(kPassPsfZ, st);
-        if (!(p.psf_window_z0 >= 0 && launch_psf_z_pruned(za, p.psf_window_z0, st))) col_pass(za, 0, 1, st);
+        if (!(p.psf_window_z0 >= 0 && p.psf_window_planes == 16 && launch_psf_z_pruned(za, p.psf_window_z0, st)))
+            col_pass(za, 0, 1, st);
     }
     count_launches(3);
 }

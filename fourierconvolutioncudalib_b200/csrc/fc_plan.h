@@ -54,14 +54,24 @@ struct ConvPlan {
     int* d_planes = nullptr;     // z planes that hold >= 1 tap
     int n_planes = 0;
     std::vector<int> h_planes;   // host copy of d_planes
-    float2* d_Hwin = nullptr;    // SaveMemory path: compact (x,y)-transformed PSF planes [n_planes<=16][ny][xcp]
-    int* d_win_slot = nullptr;   // [16] compact plane of window position n, -1 = none
-    int psf_window_z0 = -1;      // >= 0: every active plane lies in [z0, z0+16) mod nz (pruned z pass applies)
+    float2* d_Hwin = nullptr;    // on-the-fly path: (x,y)-transformed PSF planes of the window [psf_window_planes][ny][xcp]
+    size_t hwin_cap = 0;         // float2 elements
+    int* d_win_slot = nullptr;   // [16] compact plane of window position n, -1 = none (16-plane windows, register kernel)
+    int psf_window_z0 = -1;      // >= 0: every plane that holds a tap lies in [z0, z0 + psf_window_planes) mod nz
+    int psf_window_planes = 0;   // 16, 32 or 64; the plane lists are then in WINDOW order (list plane n = z0 + n)
+    // the window buffer holds the planes of exactly these host taps (PSF cache of the on-the-fly path)
+    bool hwin_valid = false;
+    int hwin_dims[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<float> hwin_taps;
     int* d_tap_start = nullptr;  // CSR tap lists over d_rows (see XArgs)
     int* d_tap_x = nullptr;
     int* d_tap_idx = nullptr;
     size_t taps_cap = 0;
     unsigned char* d_plane_mask = nullptr;   // [nz] 1 = plane active
+    // "workspace busy": recorded on the stream of every call when its last kernel has been enqueued; the next call --
+    // possibly on another stream -- makes its stream wait for it before it touches d_spec / d_H / the PSF buffers
+    // (stream-ordered async calls of one shape on different streams would otherwise race on the shared workspace)
+    cudaEvent_t ev_busy = nullptr;
     cudaStream_t stream = nullptr;   // used for host-pointer calls
     // host-pointer pipeline: pinned staging for pageable buffers, ring of device image buffers + copy
     // streams for the batch entry point (ring[0] aliases d_real)
@@ -89,6 +99,9 @@ struct ConvPlan {
 // The caller must hold plan->mu while using the workspace.
 // workspace = false: tables only (slab mode, where the caller owns the slab-sized buffers).
 std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz, bool workspace = true);
+// Orders a call on stream `st` after the previous user of the plan's workspace / marks the end of this call's use.
+void workspace_acquire(ConvPlan& p, cudaStream_t st);
+void workspace_release(ConvPlan& p, cudaStream_t st);
 void release_all_plans();
 long long launch_count();
 void count_launches(int n);
@@ -104,9 +117,11 @@ int profile_read(float* ms_sum, long long* counts, int n);
 // PSF spectrum into plan.d_H.  pdims = the six ints handed to fftShiftKernel by the reference
 // (k0,k1,k2,d0,d1,d2); d_kernel = taps on the device.
 void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st);
-// SaveMemory path: only the <=16 z planes that hold taps are (x,y)-transformed, into a compact buffer; the
-// fused z kernel derives the PSF spectrum on the fly.  Returns false (nothing done) when the path does
-// not apply (taps span more than 16 planes, or no kernel for the z length): use the functions above.
+// On-the-fly path: only the z planes of the PSF window (16..64 consecutive planes mod nz that hold every tap) are
+// (x,y)-transformed, into a compact buffer; the fused z kernel derives the PSF spectrum from them tile by tile.
+// psf_window_applies: can this plan / PSF placement take that path (no device work is enqueued)?
+// run_psf_window: returns false (nothing done) when it does not apply: use the functions above.
+bool psf_window_applies(ConvPlan& p, const int* pdims, cudaStream_t st);
 bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st);
 void run_convolve_window(ConvPlan& p, float* d_real, cudaStream_t st);
 void ensure_full_workspace(ConvPlan& p);   // allocates the image-sized PSF spectrum buffer on first use

@@ -272,7 +272,54 @@ struct TmaArgs {
     int totalTiles;
     int boxRows;          // rows per natural-order box (L % boxRows == 0)
     float scale;
+    int reverse;          // walk the tiles from the last to the first
+    const int* pos;       // MODE 3: pos[k] = position that holds frequency k
+    int z0;               // MODE 3: first plane of the PSF window
 };
+
+// PSF-spectrum tile of 2*TXP pencils from the (x,y)-transformed PSF planes of the window [z0, z0 + 16*NH) mod L:
+//   H[k1*Q + k2] = w16^(z0 k1) * sum_{n<16} [ sum_h win[16h + n] w_L^((z0 + 16h + n) k2) ] w16^(n k1),  Q = L / 16
+// i.e. one radix-16 butterfly per output residue k2 on twiddled inputs (an input-pruned FFT: the other L - 16*NH
+// planes of the padded PSF are zero).  Written in digit-reversed POSITION order, like the data tile at the multiply.
+template <int L, int NH, int NW, int TXP>
+__device__ __forceinline__ void otf_h_tile(const float4* __restrict__ win, float4* __restrict__ hb,
+                                           const float4* __restrict__ tw, const int* __restrict__ pos_s, int z0, int cp, int w)
+{
+    constexpr int Q = L / 16;
+    const int s16 = z0 & 15;
+    for (int k2 = w; k2 < Q; k2 += NW) {
+        p2 r[16], i[16];
+        int e = (z0 * k2) % L;
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+            const float4 v = win[n * TXP + cp];
+            r[n] = make_float2(v.x, v.y);
+            i[n] = make_float2(v.z, v.w);
+            cmul(r[n], i[n], tw[e]);
+            e += k2;
+            if (e >= L) e -= L;
+        }
+#pragma unroll
+        for (int h = 1; h < NH; ++h) {
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+                const float4 v = win[(16 * h + n) * TXP + cp];
+                p2 tr = make_float2(v.x, v.y), ti = make_float2(v.z, v.w);
+                cmul(tr, ti, tw[e]);
+                r[n] = padd(r[n], tr);
+                i[n] = padd(i[n], ti);
+                e += k2;
+                if (e >= L) e -= L;
+            }
+        }
+        Dft<16>::run(r, i);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+            if (s16 != 0 && k1 != 0) cmul(r[k1], i[k1], tw[((s16 * k1) & 15) * Q]);
+            hb[pos_s[k1 * Q + k2] * TXP + cp] = make_float4(r[k1].x, r[k1].y, i[k1].x, i[k1].y);
+        }
+    }
+}
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {
@@ -291,18 +338,23 @@ __device__ __forceinline__ void consumer_sync()
 //   done[s]  : every consumer has finished slot s     (THREADS arrivals, after a fence.proxy.async each)
 // shared memory: [NBUF][slot] | twiddles [L] float4 | full[NBUF] | done[NBUF]
 //   slot = data tile (+ H tile for MODE 2), each L * TXP float4
-template <int MODE, class P, int THREADS, int NBUF, int TXP, bool GROUPS>
+//   MODE 3: MODE 2 with the PSF-spectrum tile derived ON THE FLY from the 16*NH window planes (h_map = window buffer):
+//   slot = data tile + window rows; one shared H tile; no image-sized PSF spectrum is read (or exists)
+template <int MODE, class P, int THREADS, int NBUF, int TXP, bool GROUPS, int NH = 0>
 __global__ void __launch_bounds__(THREADS + 32, 1)
     col_tma_kernel(const __grid_constant__ CUtensorMap nat_map, const __grid_constant__ CUtensorMap perm_map,
                    const __grid_constant__ CUtensorMap h_map, TmaArgs a)
 {
     constexpr int L = P::L, NW = THREADS / TXP, TILE = L * TXP;
-    constexpr int SLOT = TILE * (MODE == 2 ? 2 : 1);
-    constexpr unsigned TILE_BYTES = (unsigned)TILE * sizeof(float4);
+    constexpr int WIN = 16 * NH * TXP;
+    constexpr int SLOT = MODE == 2 ? 2 * TILE : (MODE == 3 ? TILE + WIN : TILE);
+    constexpr unsigned SLOT_BYTES = (unsigned)SLOT * sizeof(float4);
     extern __shared__ __align__(128) float4 smem[];
     float4* bufs = smem;
-    float4* tw = bufs + (size_t)NBUF * SLOT;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(tw + L);
+    float4* hbuf = bufs + (size_t)NBUF * SLOT;                  // MODE 3 only
+    float4* tw = hbuf + (MODE == 3 ? TILE : 0);
+    int* pos_s = reinterpret_cast<int*>(tw + L);                // MODE 3 only
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(pos_s + (MODE == 3 ? L : 0));
     unsigned long long* done = full + NBUF;
 
     const int t = threadIdx.x;
@@ -318,6 +370,8 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
     }
     pdl_launch_dependents();
     load_twiddles(tw, a.tw, L);
+    if constexpr (MODE == 3)
+        for (int r = t; r < L; r += THREADS + 32) pos_s[r] = __ldg(a.pos + r);
     __syncthreads();
     pdl_wait();   // everything below reads what the previous pass wrote
 
@@ -325,13 +379,15 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
         // ---------------- producer warp ----------------
         if (t != THREADS) return;
         auto issue_load = [&](int tile, int slot) {
+            if (a.reverse) tile = a.totalTiles - 1 - tile;
             const int gi = tile / a.tilesPerGroup;
             const int tt = tile - gi * a.tilesPerGroup;
             float4* dst = bufs + (size_t)slot * SLOT;
-            mbar_expect_tx(full + slot, TILE_BYTES * (MODE == 2 ? 2 : 1));
+            mbar_expect_tx(full + slot, SLOT_BYTES);
             for (int r0 = 0; r0 < L; r0 += a.boxRows)
                 tma_load_3d(dst + (size_t)r0 * TXP, &nat_map, tt * 4 * TXP, r0, gi, full + slot);
             if (MODE == 2) perm_load<P::ns, GROUPS>(dst + TILE, &h_map, tt * 4 * TXP, gi, full + slot);
+            if (MODE == 3) tma_load_3d(dst + TILE, &h_map, tt * 4 * TXP, 0, 0, full + slot);
         };
 #pragma unroll
         for (int k = 0; k < NBUF; ++k) {
@@ -343,9 +399,10 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             const int slot = it % NBUF;
             float4* sm = bufs + (size_t)slot * SLOT;
             mbar_wait(done + slot, (unsigned)((it / NBUF) & 1));
-            const int gi = tile / a.tilesPerGroup;
-            const int tt = tile - gi * a.tilesPerGroup;
-            if constexpr (MODE == 2) {
+            const int tq = a.reverse ? a.totalTiles - 1 - tile : tile;
+            const int gi = tq / a.tilesPerGroup;
+            const int tt = tq - gi * a.tilesPerGroup;
+            if constexpr (MODE >= 2) {
                 for (int r0 = 0; r0 < L; r0 += a.boxRows)
                     tma_store_3d(&nat_map, tt * 4 * TXP, r0, gi, sm + (size_t)r0 * TXP);
             } else {
@@ -370,7 +427,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
         float4* sm = bufs + (size_t)slot * SLOT;
         mbar_wait(full + slot, (unsigned)((it / NBUF) & 1));
 
-        if constexpr (MODE != 2) {
+        if constexpr (MODE < 2) {
             // forward stage sequence, in place; MODE 1 exchanges re/im on the way in and on the way out
             if constexpr (P::ns == 2) {
                 sstage<P::R0, L, L, NW, false, TXP, MODE == 1>(sm, tw, cp, w);
@@ -396,6 +453,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             }
         } else {
             sstage<P::R0, L, L, NW, false, TXP>(sm, tw, cp, w);
+            if constexpr (MODE == 3) otf_h_tile<L, NH, NW, TXP>(sm + TILE, hbuf, tw, pos_s, a.z0, cp, w);
             consumer_sync<THREADS>();
             if constexpr (P::ns >= 3) {
                 sstage<P::R1, L, L / P::R0, NW, false, TXP>(sm, tw, cp, w);
@@ -405,7 +463,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 sstage<P::R2, L, L / (P::R0 * P::R1), NW, false, TXP>(sm, tw, cp, w);
                 consumer_sync<THREADS>();
             }
-            smid_fused_tma<P::RL, L, NW, TXP>(sm + TILE, sm, cp, w, a.scale);
+            smid_fused_tma<P::RL, L, NW, TXP>(MODE == 3 ? hbuf : sm + TILE, sm, cp, w, a.scale);
             consumer_sync<THREADS>();
             if constexpr (P::ns >= 4) {
                 sstage<P::R2, L, P::R2 * P::R3, NW, true, TXP>(sm, tw, cp, w);
@@ -467,7 +525,11 @@ bool run_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
         if ((reinterpret_cast<uintptr_t>(a.H) & 15) != 0) return false;
         if (!encode(&hmap, const_cast<float2*>(a.H), ps)) return false;
     }
-    TmaArgs ta{a.P.tw, tpg, (int)total, boxRows, a.scale};
+    // plain y passes walk the planes from the last to the first: the x pass before a forward y pass has just written
+    // the last planes (still in the 126 MB L2), and the x pass after an inverse y pass starts with the first ones
+    static const int rev_env = env_int("FCB200_TMA_REVERSE", 1);
+    const int reverse = (rev_env == 1 && ngroups > 1 && mode != 2) ? 1 : (rev_env == 2 ? 1 : 0);
+    TmaArgs ta{a.P.tw, tpg, (int)total, boxRows, a.scale, reverse, nullptr, 0};
     auto go = [&](auto kernel) {
         FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 1;
@@ -488,7 +550,67 @@ bool run_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
     return true;
 }
 
+// fused z pass with the PSF spectrum derived on the fly from the window planes in a.H ([winPlanes][ny][xcp])
+template <class P, int THREADS, int NBUF, int TXP>
+bool run_col_otf_tma(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, bool probe)
+{
+    constexpr int L = P::L;
+    static_assert(L % 16 == 0, "on-the-fly PSF spectrum needs L % 16 == 0");
+    if (!plan_matches<P>(a.P)) return false;
+    if (a.split || a.splitPeers || a.rowMask || a.groupList || ngroups != 1) return false;
+    const int nh = a.winPlanes / 16;
+    if (a.winPlanes % 16 != 0 || (nh != 1 && nh != 2 && nh != 4) || a.winPlanes > L) return false;
+    if (!encode_fn()) return false;
+    if ((a.stride % 2) != 0) return false;
+    const int boxFloats = 4 * TXP;
+    const int tpg = (a.rowLen * 2 + boxFloats - 1) / boxFloats;
+    int boxRows = std::min(L, 256);
+    while (L % boxRows) --boxRows;
+    const size_t tile = (size_t)L * TXP * sizeof(float4), win = (size_t)a.winPlanes * TXP * sizeof(float4);
+    const size_t smem = (size_t)NBUF * (tile + win) + tile + (size_t)L * (sizeof(float4) + sizeof(int)) +
+                        2 * NBUF * sizeof(unsigned long long);
+    if (smem > (size_t)kMaxDynSmem) return false;
+    if (probe) return true;
+    if (tpg == 0) return true;
+    if ((reinterpret_cast<uintptr_t>(a.data) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.H) & 15) != 0) return false;
+    CUtensorMap nat, wmap;
+    if (!encode(&nat, a.data, natural_spec(a, 1, L, boxRows, boxFloats))) return false;
+    MapSpec ws;
+    ws.rank = 3;
+    ws.dims[0] = (cuuint64_t)a.rowLen * 2;
+    ws.dims[1] = (cuuint64_t)a.winPlanes;
+    ws.dims[2] = 1;
+    ws.strides[0] = (cuuint64_t)a.stride * sizeof(float2);
+    ws.strides[1] = ws.strides[0] * (cuuint64_t)a.winPlanes;
+    ws.box[0] = (cuuint32_t)boxFloats;
+    ws.box[1] = (cuuint32_t)a.winPlanes;
+    ws.box[2] = 1;
+    if (!encode(&wmap, const_cast<float2*>(a.H), ws)) return false;
+    TmaArgs ta{a.P.tw, tpg, tpg, boxRows, a.scale, 0, a.P.pos, z0};
+    auto go = [&](auto kernel) {
+        FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = std::min(tpg, sm_count_of_current_device());
+        launch_pdl(a.pdl != 0, kernel, dim3(grid), dim3(THREADS + 32), smem, st, nat, nat, wmap, ta);
+        FC_CUDA_KERNEL();
+    };
+    if (nh == 1) go(col_tma_kernel<3, P, THREADS, NBUF, TXP, false, 1>);
+    else if (nh == 2) go(col_tma_kernel<3, P, THREADS, NBUF, TXP, false, 2>);
+    else go(col_tma_kernel<3, P, THREADS, NBUF, TXP, false, 4>);
+    return true;
+}
+
 }  // namespace
+
+bool launch_col_otf_tma(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, bool probe)
+{
+    const int on = env_int("FCB200_TMA", 1);
+    static const int otf_on = env_int("FCB200_OTF_TMA", 1);
+    if (!on || !otf_on || !static_enabled() || a.txp != 8) return false;
+    static const long long max_stride = (long long)env_int("FCB200_TMA_MAXSTRIDE_KB", 2048) << 10;
+    if (a.stride * (long long)sizeof(float2) > max_stride) return false;
+    return run_col_otf_tma<P256b, 256, 4, 8>(a, ngroups, z0, st, probe) || run_col_otf_tma<P384, 192, 3, 8>(a, ngroups, z0, st, probe) ||
+           run_col_otf_tma<P512, 256, 4, 4>(a, ngroups, z0, st, probe);
+}
 
 // FCB200_TMA: 0 = off, 1 (default) = the configurations measured to win, 2 = every configuration compiled below
 bool launch_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
@@ -506,6 +628,8 @@ bool launch_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t 
     if (a.txp != 8) return false;
     // measured (profiles/r02_tma_ab.jsonl): C3 y passes 0.117 -> 0.100 ms, fused z 0.163 -> 0.144 ms; 384^3 y 0.098 -> 0.081,
     // fused z 0.170 -> 0.143; 1024^2 y passes (64-byte rows) 1.05 -> 0.75 ms; 512^3 fused z (L = 512, 64-byte rows) 0.401 -> 0.367
+    static const int t512 = env_int("FCB200_TMA_T512", 512);
+    if (plan_matches<P512>(a.P) && mode != 2 && t512 == 256) return run_col_tma<P512, 256, 3, 8>(a, mode, ngroups, st);
     if (plan_matches<P512>(a.P) && mode != 2) return run_col_tma<P512, 512, 3, 8>(a, mode, ngroups, st);
     if (plan_matches<P512>(a.P) && mode == 2) return run_col_tma<P512, 256, 3, 4>(a, mode, ngroups, st);
     if (plan_matches<P256b>(a.P) && mode == 2) return run_col_tma<P256b, 256, 3, 8>(a, mode, ngroups, st);

@@ -48,6 +48,7 @@ struct ColArgs {
     //   split + (r / splitRows) * splitBlock + group * splitGroup + (r % splitRows) * stride + column
     // so the y pass produces / consumes the all-to-all send / receive buffer directly (no pack pass).
     const int* winSlot;     // on-the-fly PSF path: compact plane slot of window position n (16 ints, -1 = no taps)
+    int winPlanes;          // on-the-fly PSF path: planes of the window buffer a.H (16, 32 or 64), in window order
     float2* split;
     int splitRows;
     long long splitBlock;
@@ -82,6 +83,8 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
 // fused z pass that derives the PSF-spectrum tile on the fly from the <=16 window planes starting at z0;
 // a.H = buffer holding those planes (after the x and y passes); probe = only test applicability
 bool launch_col_otf(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, bool probe);
+// the same on the TMA pipeline (fft_col_tma.cu); windows of 16..64 planes
+bool launch_col_otf_tma(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, bool probe);
 bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st);
 bool launch_x_inv_static(const XArgs& a, cudaStream_t st);
 

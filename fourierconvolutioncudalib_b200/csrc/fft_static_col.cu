@@ -223,15 +223,19 @@ __global__ void __launch_bounds__(THREADS, 1) col_pipe_kernel(ColArgs a, int til
     cpa_wait<0>();
 }
 
+// SM count of the CURRENT device (one process may drive several GPUs: fc_multi.cu)
 static int sm_count()
 {
-    static int n = [] {
-        int dev = 0, v = 148;
-        cudaGetDevice(&dev);
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int v = 148;
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        return v;
-    }();
-    return n;
+        cache[dev] = v;
+    }
+    return cache[dev];
 }
 
 template <class P, int THREADS, int NBUF>

@@ -57,6 +57,12 @@ FUNCTION_PREFIX void fcb200_plan_tables_style(int L, int style, int* rev, int* p
 FUNCTION_PREFIX int fcb200_spectrum_pitch(int nx);
 /* Bytes of device workspace a cached plan for imDim holds (spectrum + PSF spectrum + tables). */
 FUNCTION_PREFIX long long fcb200_workspace_bytes(const int* imDim);
+/* On-the-fly PSF spectrum: when every z plane of the placed PSF (reference placement, src/convolution3Dfft.cu:128-166)
+ * that holds a tap lies inside a window of 16, 32 or 64 consecutive planes (mod imDim[2]) and the z length has a
+ * kernel for it, the fused z pass derives the PSF spectrum tile by tile from those planes and no image-sized PSF
+ * spectrum is allocated, written or read.  Returns the window size the library uses for (imDim, kernelDim) on
+ * devCUDA, 0 when it materialises the spectrum instead. */
+FUNCTION_PREFIX int fcb200_psf_window_planes(const int* imDim, const int* kernelDim, int devCUDA);
 /* Rows (z*d1+y) of the padded PSF volume that hold at least one tap (PSF pruning); returns count.
  * rows may be NULL. */
 FUNCTION_PREFIX long long fcb200_psf_active_rows(const int* imDim, const int* kernelDim, int* rows, long long cap);

@@ -108,3 +108,45 @@ def test_release_frees_the_plan_cache(fc, dev):
     free_after, _ = torch.cuda.mem_get_info(dev)
     assert free_after > free_before
     fc.convolution3DfftCUDAInPlace(im, (128, 128, 64), np.ones(27, np.float32) / 27, (3, 3, 3), dev)   # rebuilds
+
+
+def test_async_calls_of_one_shape_on_two_streams_do_not_race(fc, dev):
+    """the stream-ordered entry point shares one workspace per (device, shape): a call on a second stream must be
+    ordered after the call still running on the first (per-plan "workspace busy" event), not race with it"""
+    import torch
+    imDim, kDim = (256, 256, 128), (9, 9, 9)
+    n = int(np.prod(imDim))
+    device = torch.device(f"cuda:{dev}")
+    rng = np.random.default_rng(31)
+    k = torch.from_numpy(rng.random(int(np.prod(kDim)), dtype=np.float32)).to(device)
+    ims = [torch.rand(n, device=device) * 100 for _ in range(4)]
+    want = []
+    for im in ims:
+        w = im.clone()
+        fc.convolve_device_async(w, imDim, k, kDim, dev, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        want.append(w)
+    streams = [torch.cuda.Stream(device=device) for _ in range(2)]
+    torch.cuda.synchronize()
+    got = [im.clone() for im in ims]
+    for rep in range(5):
+        for i, g in enumerate(got):
+            g.copy_(ims[i])
+        torch.cuda.synchronize()
+        for i, g in enumerate(got):
+            fc.convolve_device_async(g, imDim, k, kDim, dev, streams[i % 2].cuda_stream)
+        torch.cuda.synchronize()
+        for g, w in zip(got, want):
+            assert torch.equal(g, w)
+
+
+def test_misaligned_device_pointers_are_rejected_not_faulted(fc, dev):
+    import torch
+    imDim, kDim = (64, 64, 8), (3, 3, 3)
+    n = int(np.prod(imDim))
+    buf = torch.zeros(n + 1, device=f"cuda:{dev}")
+    k = torch.ones(27, device=f"cuda:{dev}")
+    with pytest.raises(fc.api.FourierConvolutionError):
+        fc.convolve_batch([buf[1:]], imDim, k, kDim, dev)         # 4-byte aligned slice
+    fc.convolve_batch([buf[:n]], imDim, k, kDim, dev)             # the context is still healthy
+    torch.cuda.synchronize()

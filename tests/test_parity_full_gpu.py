@@ -1,0 +1,144 @@
+"""Full-size parity of the named BASELINE configurations against the reference's own cuFFT build (oracle/_ref) on
+identical inputs, through the C ABI with HOST buffers -- the reference needs about a second per call at these sizes,
+so the direct comparison is cheap.  Tolerance (north_star): max|err| <= 1e-4 * max|out|, relative L2 <= 1e-5.
+
+Also: the library-padded call against the reference driven the way its own tests drive it on the caller-padded
+grid, and an 8-rank slab run of a 2 GiB volume against the single-GPU result with the error recorded."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def gaussian_psf(kDim):
+    ax = [np.exp(-0.5 * ((np.arange(k) - k // 2) / (k / 6.0)) ** 2) for k in kDim]
+    psf = ax[0][:, None, None] * ax[1][None, :, None] * ax[2][None, None, :]
+    return (psf / psf.sum()).astype(np.float32)
+
+
+def errors(got, want):
+    got = np.asarray(got, np.float64).ravel()
+    want = np.asarray(want, np.float64).ravel()
+    return float(np.abs(got - want).max() / np.abs(want).max()), float(np.linalg.norm(got - want) / np.linalg.norm(want))
+
+
+FULL = [
+    ("C2", (256, 256, 256), (15, 15, 15)),
+    ("C3", (512, 512, 256), (31, 31, 41)),
+    ("C4-block", (384, 384, 384), (25, 25, 61)),
+    ("C3-caller-padded", (560, 560, 300), (31, 31, 41)),
+    ("C4-caller-padded", (420, 420, 448), (25, 25, 61)),
+    ("C2-caller-padded", (270, 270, 270), (15, 15, 15)),
+]
+
+
+@pytest.mark.parametrize("name,imDim,kDim", FULL, ids=[c[0] for c in FULL])
+@pytest.mark.parametrize("entry", ["InPlace", "SaveMemory"])
+def test_full_size_matches_reference_build(fc, dev, reflib, name, imDim, kDim, entry):
+    import reflib as R
+    rng = np.random.default_rng(2024)
+    im = (rng.random(int(np.prod(imDim)), dtype=np.float32) * 1000).astype(np.float32)
+    k = gaussian_psf(kDim).reshape(-1)
+    ref = R.convolve_inplace(im, imDim, k, kDim, dev)
+    got = im.copy()
+    if entry == "InPlace":
+        fc.convolution3DfftCUDAInPlace(got, imDim, k, kDim, dev)
+    else:
+        fc.convolution3DfftCUDAInPlaceSaveMemory(got, imDim, k, kDim, dev)
+    mx, l2 = errors(got, ref)
+    print(f"{name} {entry}: max_rel {mx:.2e} rel_l2 {l2:.2e}")
+    assert mx <= 1e-4 and l2 <= 1e-5, (mx, l2)
+
+
+def test_tma_kernels_equal_the_register_kernels_bit_for_bit(fc, dev, monkeypatch):
+    """FCB200_TMA=0 routes the y / z passes through the cp.async / register kernels: same arithmetic, same order"""
+    import torch
+    imDim, kDim = (512, 512, 256), (31, 31, 41)
+    n = int(np.prod(imDim))
+    g = torch.Generator(device=f"cuda:{dev}")
+    g.manual_seed(5)
+    base = torch.rand(n, device=f"cuda:{dev}", generator=g) * 1000
+    d_k = torch.from_numpy(gaussian_psf(kDim).reshape(-1)).to(f"cuda:{dev}")
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("FCB200_TMA", flag)
+        x = base.clone()
+        fc.convolve_device_async(x, imDim, d_k, kDim, dev, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs.append(x)
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_eight_rank_slab_of_a_2gib_volume_matches_single_gpu(fc, dev):
+    """1024x1024x512 (x) 31x31x41 over 8 ranks (real GPUs when the box has them, emulated ranks on one GPU
+    otherwise) against the single-GPU result; the error is recorded in gpurun_out/ when that directory exists"""
+    import torch
+    imDim, kDim, world = (1024, 1024, 512), (31, 31, 41), 8
+    have = fc.getNumDevicesCUDA()
+    devs = list(range(world)) if have >= world else [dev] * world
+    n = int(np.prod(imDim))
+    plane = imDim[0] * imDim[1]
+    g = torch.Generator(device=f"cuda:{dev}")
+    g.manual_seed(9)
+    full = torch.rand(n, device=f"cuda:{dev}", generator=g) * 1000
+    d_k = torch.from_numpy(gaussian_psf(kDim).reshape(-1)).to(f"cuda:{dev}")
+    nzp, _, planes = fc.slab_partition(imDim, world)
+    slabs = [full[r * nzp * plane:(r * nzp + planes[r]) * plane].to(f"cuda:{devs[r]}").clone() for r in range(world)]
+    fc.convolve_slab_device(slabs, imDim, d_k, kDim, devs)
+    fc.release()
+    fc.convolve_device_async(full, imDim, d_k, kDim, dev, torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize(dev)
+    scale = float(full.abs().max())
+    worst, num, den = 0.0, 0.0, 0.0
+    for r in range(world):
+        got = slabs[r].to(f"cuda:{dev}")
+        want = full[r * nzp * plane:(r * nzp + planes[r]) * plane]
+        d = (got - want).double()
+        worst = max(worst, float(d.abs().max()))
+        num += float((d * d).sum())
+        den += float((want.double() ** 2).sum())
+    mx, l2 = worst / scale, (num / den) ** 0.5
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "slab_8rank_vs_1gpu.json"), "w") as f:
+            json.dump({"dims": imDim + kDim, "ranks": world, "real_gpus": have >= world, "max_rel_err": mx, "rel_l2": l2}, f)
+    fc.release()
+    assert mx <= 1e-4 and l2 <= 1e-5, (mx, l2)
+
+
+@pytest.mark.parametrize("name,imDim,kDim,planes", [("C3", (512, 512, 256), (31, 31, 41), 16),
+                                                    ("C4-block", (384, 384, 384), (25, 25, 61), 32)])
+def test_savememory_allocates_no_image_sized_psf_spectrum(fc, dev, name, imDim, kDim, planes):
+    """convolution3DfftCUDAInPlaceSaveMemory on the named configs: the placed PSF of C3 spans 16 z planes and that of
+    C4 25 (a 32-plane window), so the fused z pass derives the PSF spectrum on the fly and the library holds ONE
+    spectrum-sized buffer (the image spectrum) plus the window planes -- never a second, PSF-spectrum-sized one"""
+    import torch
+    assert fc.psf_window_planes(imDim, kDim, dev) == planes
+    fc.release()
+    torch.cuda.empty_cache()
+    n = int(np.prod(imDim))
+    d_im = torch.rand(n, device=f"cuda:{dev}")
+    d_k = torch.from_numpy(gaussian_psf(kDim).reshape(-1)).to(f"cuda:{dev}")
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(dev)
+    fc.convolution3DfftCUDAInPlaceSaveMemory(d_im, imDim, d_k, kDim, dev)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(dev)
+    spec = imDim[2] * imDim[1] * fc.spectrum_pitch(imDim[0]) * 8
+    window = planes * imDim[1] * fc.spectrum_pitch(imDim[0]) * 8
+    used = free0 - free1
+    assert used < spec + window + (64 << 20), (used, spec, window)      # 64 MiB: tables, tap lists, allocator granularity
+    assert used >= spec
+    fc.release()
+
+
+def test_config5_psf_fits_a_32_plane_window(fc, dev):
+    """the placement of the 63x63x101 PSF on 2048x2048x1024 (reference formula, src/convolution3Dfft.cu:145-164)
+    touches z planes {0..15, 1008..1023}: 32 planes -- planner-level check, nothing of that size is allocated"""
+    from oracle import fc_oracle as fo
+    rows = fc.psf_active_rows((2048, 2048, 1024), (63, 63, 101))
+    planes = sorted(set(int(r) // 2048 for r in rows))
+    assert planes == list(range(16)) + list(range(1008, 1024))

@@ -22,8 +22,12 @@ d_k = torch.from_numpy(bench.gaussian_psf(k_dim).reshape(-1)).cuda()
 st = torch.cuda.current_stream().cuda_stream
 out = {"dims": im_dim + k_dim}
 res = {}
-for mode in ("0", os.environ.get("TMA_MODE", "1")):
-    os.environ["FCB200_TMA"] = mode
+# variants: "0" = no TMA kernels, materialised PSF spectrum; "1"/"2" = TMA kernels (FCB200_TMA value), materialised;
+#           "otf" = TMA kernels + PSF spectrum derived on the fly in the fused z pass (the default InPlace path)
+variants = os.environ.get("TMA_VARIANTS", "0,1,otf").split(",")
+for mode in variants:
+    os.environ["FCB200_TMA"] = "1" if mode == "otf" else mode
+    os.environ["FCB200_OTF_INPLACE"] = "1" if mode == "otf" else "0"
     x = base.clone()
     fc.convolve_device_async(x, im_dim, d_k, k_dim, 0, st)
     torch.cuda.synchronize()
@@ -47,7 +51,8 @@ for mode in ("0", os.environ.get("TMA_MODE", "1")):
     fc.profile_enable(False)
     out["tma=" + mode] = {"ms_step": round(e0.elapsed_time(e1) / steps, 4),
                           "passes": {k: round(ms / c, 4) for k, (ms, c) in prof.items() if c}}
-a, b = res.values()
-out["max_rel_diff"] = float((a - b).abs().max() / a.abs().max())
-out["env"] = {k: v for k, v in os.environ.items() if k.startswith("FCB200_") and k != "FCB200_TMA"}
+vals = list(res.values())
+out["max_rel_diff_vs_first"] = [float((v - vals[0]).abs().max() / vals[0].abs().max()) for v in vals[1:]]
+out["window_planes"] = fc.psf_window_planes(im_dim, k_dim, 0)
+out["env"] = {k: v for k, v in os.environ.items() if k.startswith("FCB200_") and k not in ("FCB200_TMA", "FCB200_OTF_INPLACE")}
 print(json.dumps(out))
