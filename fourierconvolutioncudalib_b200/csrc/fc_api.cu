@@ -47,11 +47,12 @@ bool is_device_ptr(const void* p, int dev)
 bool prepare_psf(ConvPlan& p, const float* kernel, bool k_dev, const int* pdims, bool save_memory, cudaStream_t st)
 {
     static const bool cache_on = env_flag("FCB200_PSF_CACHE", true);
-    // On-the-fly PSF spectrum (the SaveMemory path) is also what InPlace runs when the placed PSF fits a window of
-    // 16 / 32 / 64 z planes: the fused z pass then reads 2 KB .. 8 KB of window rows per tile instead of a whole
-    // PSF-spectrum tile, and no PSF z pass runs at all (C3: step 0.63 -> 0.53 ms).  FCB200_OTF_INPLACE=0 keeps InPlace on
-    // the materialised spectrum.
-    const bool otf_inplace = env_flag("FCB200_OTF_INPLACE", true);   // read per call: tests and tools switch it
+    // On-the-fly PSF spectrum is the SaveMemory path (windows of 16 / 32 / 64 PSF planes).  FCB200_OTF_INPLACE=1 makes
+    // InPlace take it too: the whole call gets a little faster when the PSF spectrum cannot be reused (no PSF z pass,
+    // no H read: C3 0.624 -> 0.612 ms, 384^3 0.595 -> 0.556 ms), but the fused z pass itself turns compute-bound
+    // (0.144 -> 0.203 ms) and a cached materialised spectrum (repeated host PSFs, the deconvolution pattern) beats
+    // both, so InPlace keeps the materialised spectrum by default.
+    const bool otf_inplace = env_flag("FCB200_OTF_INPLACE", false);   // read per call: tests and tools switch it
     const size_t ktaps = (size_t)pdims[0] * pdims[1] * pdims[2];
     auto same_taps = [&](bool valid, const int* dims, const std::vector<float>& taps) {
         return !k_dev && cache_on && valid && std::memcmp(dims, pdims, sizeof(int) * 6) == 0 && taps.size() == ktaps &&
@@ -155,7 +156,7 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
     const int nch = (int)std::max<long long>(
         1, std::min<long long>(std::min(8, chunks_env), std::min<long long>(nz, (long long)(p.real_bytes() >> 25))));
     if (im_kind == HostMem::Pinned && nch > 1) {
-        if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+        if (!p.d_real) FC_CUDA(device_alloc_retry(&p.d_real, p.real_bytes()));
         if (!p.s_h2d) FC_CUDA(cudaStreamCreateWithFlags(&p.s_h2d, cudaStreamNonBlocking));
         if (!p.s_d2h) FC_CUDA(cudaStreamCreateWithFlags(&p.s_d2h, cudaStreamNonBlocking));
         for (cudaEvent_t& e : p.ev_chunk)
@@ -194,7 +195,7 @@ void convolve_core(float* im, int nx, int ny, int nz, const float* kernel, const
 
     float* d_im = im;
     if (!im_dev) {
-        if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+        if (!p.d_real) FC_CUDA(device_alloc_retry(&p.d_real, p.real_bytes()));
         if (staged) p.stager.upload(p.d_real, im, p.real_bytes(), st);
         else FC_CUDA(cudaMemcpyAsync(p.d_real, im, p.real_bytes(), cudaMemcpyHostToDevice, st));
         d_im = p.d_real;
@@ -270,7 +271,7 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
     // Fused (default): the x passes assemble the padded rows while loading the unpadded volume and store only the
     // interior back, so no padded real volume exists.  FCB200_PAD_FUSED=0: separate embed / crop kernels.
     static const bool fused = env_flag("FCB200_PAD_FUSED", true);
-    if (!fused && !p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+    if (!fused && !p.d_real) FC_CUDA(device_alloc_retry(&p.d_real, p.real_bytes()));
     const size_t src_plane = (size_t)g.sy * g.sx, src_elems = src_plane * g.sz, src_bytes = src_elems * sizeof(float);
     float* d_src = im;
     if (!im_dev) {
@@ -278,7 +279,7 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
             cudaFree(p.d_unpadded);
             p.d_unpadded = nullptr;
             p.unpadded_cap = 0;
-            FC_CUDA(cudaMalloc(&p.d_unpadded, src_bytes));
+            FC_CUDA(device_alloc_retry(&p.d_unpadded, src_bytes));
             p.unpadded_cap = src_elems;
         }
         d_src = p.d_unpadded;
@@ -397,10 +398,10 @@ void padded_core(float* im, const int* imDim, const float* kernel, const int* ke
 // ------------------------------------------------------------------------------------------------
 void batch_resources(ConvPlan& p)
 {
-    if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+    if (!p.d_real) FC_CUDA(device_alloc_retry(&p.d_real, p.real_bytes()));
     p.d_ring[0] = p.d_real;
     for (int i = 1; i < 3; ++i)
-        if (!p.d_ring[i]) FC_CUDA(cudaMalloc(&p.d_ring[i], p.real_bytes()));
+        if (!p.d_ring[i]) FC_CUDA(device_alloc_retry(&p.d_ring[i], p.real_bytes()));
     if (!p.s_h2d) FC_CUDA(cudaStreamCreateWithFlags(&p.s_h2d, cudaStreamNonBlocking));
     if (!p.s_d2h) FC_CUDA(cudaStreamCreateWithFlags(&p.s_d2h, cudaStreamNonBlocking));
     for (int i = 0; i < 3; ++i) {
@@ -743,7 +744,7 @@ imageType* convolution3DfftCUDA_test(imageType* im, int* imDim, imageType* kerne
         std::lock_guard<std::mutex> lock(plan->mu);
         ConvPlan& p = *plan;
         cudaStream_t st = p.stream;
-        if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+        if (!p.d_real) FC_CUDA(device_alloc_retry(&p.d_real, p.real_bytes()));
         // kernel is already image-sized and used as is (no shift), reference :253, :270
         FC_CUDA(cudaMemcpyAsync(p.d_real, kernel, n * sizeof(float), cudaMemcpyHostToDevice, st));
         ensure_full_workspace(p);
@@ -902,7 +903,7 @@ void fcb200_debug_rfft3(const imageType* im, const int* imDim, float* spec, int 
         auto plan = get_plan(devCUDA, imDim[0], imDim[1], imDim[2]);
         std::lock_guard<std::mutex> lock(plan->mu);
         ConvPlan& p = *plan;
-        if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+        if (!p.d_real) FC_CUDA(device_alloc_retry(&p.d_real, p.real_bytes()));
         FC_CUDA(cudaMemcpyAsync(p.d_real, im, p.real_bytes(), cudaMemcpyHostToDevice, p.stream));
         run_forward(p, p.d_real, p.d_spec, passes, p.stream);
         download_spectrum(p, p.d_spec, spec, p.stream);
@@ -927,7 +928,7 @@ void fcb200_debug_irfft3(const float* spec, const int* imDim, imageType* out, in
                 hf[f] = s[r * g.xc + k].x;
                 hf[f + 2] = s[r * g.xc + k].y;
             }
-        if (!p.d_real) FC_CUDA(cudaMalloc(&p.d_real, p.real_bytes()));
+        if (!p.d_real) FC_CUDA(device_alloc_retry(&p.d_real, p.real_bytes()));
         FC_CUDA(cudaMemcpyAsync(p.d_spec, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice, p.stream));
         run_inverse(p, p.d_spec, p.d_real, p.stream);
         FC_CUDA(cudaMemcpyAsync(out, p.d_real, p.real_bytes(), cudaMemcpyDeviceToHost, p.stream));

@@ -18,7 +18,8 @@ struct AxisPlanDev {
     int L;                    // transform length
     int ns;                   // number of stages
     int radix[kMaxStages];    // stage radices, product == L
-    int generic;              // 1 when a radix outside {2,3,4,5,7,8,16} is present (needs two tile buffers)
+    int generic;              // 1 when a prime factor above 23 is present (direct-sum stage, needs two tile buffers)
+    int big;                  // 1 when a radix 11, 13, 17, 19 or 23 is present (kernels compiled with those butterflies)
     const float2* tw;         // L roots: exp(-2*pi*i*t/L), computed in double
     const int* rev;           // rev[p]  = frequency held at position p after the forward transform
     const int* pos;           // pos[k]  = position that holds frequency k (inverse permutation)

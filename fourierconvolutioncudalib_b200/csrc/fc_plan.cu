@@ -72,7 +72,7 @@ std::vector<int> factorize(int L, bool* generic, int style)
         while (n % p == 0) {
             out.push_back(p);
             n /= p;
-            gen = true;
+            if (p > 23) gen = true;   // 11, 13, 17, 19, 23 have register butterflies (fft_butterflies.cuh: DftOddPrime)
         }
     }
     if (out.empty()) out.push_back(1);
@@ -252,6 +252,9 @@ static void make_axis(AxisPlan& a, int L, int style)
     a.dev.ns = (int)a.radix.size();
     for (int i = 0; i < kMaxStages; ++i) a.dev.radix[i] = i < a.dev.ns ? a.radix[i] : 1;
     a.dev.generic = a.generic ? 1 : 0;
+    a.dev.big = 0;
+    for (int r : a.radix)
+        if (r == 11 || r == 13 || r == 17 || r == 19 || r == 23) a.dev.big = 1;
     a.dev.tw = a.d_tw;
     a.dev.rev = a.d_rev;
     a.dev.pos = a.d_pos;
@@ -332,6 +335,8 @@ static size_t max_cached_plans()
     return 4;
 }
 
+static void enforce_byte_budget_locked(const ConvPlan* keep);
+
 static void evict_lru_locked(size_t keep)
 {
     while (g_cache.size() > keep) {
@@ -384,6 +389,7 @@ std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz, bool work
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
         it->second->last_use = ++g_tick;
+        enforce_byte_budget_locked(it->second.get());
         return it->second;
     }
     std::shared_ptr<ConvPlan> p;
@@ -399,7 +405,65 @@ std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz, bool work
     g_cache[key] = p;
     size_t keep = max_cached_plans();
     evict_lru_locked(keep == 0 ? 1 : keep);
+    enforce_byte_budget_locked(p.get());
     return p;
+}
+
+cudaError_t device_alloc_retry(void** p, size_t bytes)
+{
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaErrorMemoryAllocation) return e;
+    cudaGetLastError();
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        evict_lru_locked(0);   // plans in use are held by their callers (use_count > 1) and survive
+    }
+    return cudaMalloc(p, bytes);
+}
+
+// The cache is bounded by a plan count (FCB200_MAX_PLANS) and by a byte budget (FCB200_CACHE_MB, default: half of the
+// device memory): idle least-recently-used plans go first.  The plan just handed out is never evicted.
+static size_t plan_bytes(const ConvPlan& p)
+{
+    size_t b = 0;
+    if (p.d_spec) b += p.spec_bytes();
+    if (p.d_H) b += p.spec_bytes();
+    if (p.d_real) b += p.real_bytes();
+    for (int i = 1; i < 3; ++i)
+        if (p.d_ring[i]) b += p.real_bytes();
+    b += p.unpadded_cap * sizeof(float) + p.hwin_cap * sizeof(float2);
+    return b;
+}
+
+static void enforce_byte_budget_locked(const ConvPlan* keep)
+{
+    static const long long budget_mb = [] {
+        const char* e = std::getenv("FCB200_CACHE_MB");
+        return e ? std::atoll(e) : -1LL;
+    }();
+    size_t budget;
+    if (budget_mb >= 0) {
+        budget = (size_t)budget_mb << 20;
+    } else {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        budget = total_b / 2;
+    }
+    for (;;) {
+        size_t sum = 0;
+        for (auto& kv : g_cache) sum += plan_bytes(*kv.second);
+        if (sum <= budget) return;
+        auto victim = g_cache.end();
+        for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+            if (it->second.get() != keep && it->second.use_count() == 1 &&
+                (victim == g_cache.end() || it->second->last_use < victim->second->last_use))
+                victim = it;
+        if (victim == g_cache.end()) return;
+        g_cache.erase(victim);
+    }
 }
 
 void workspace_acquire(ConvPlan& p, cudaStream_t st)
@@ -655,7 +719,7 @@ static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
 
 void ensure_full_workspace(ConvPlan& p)
 {
-    if (!p.d_H) FC_CUDA(cudaMalloc(&p.d_H, p.spec_bytes()));
+    if (!p.d_H) FC_CUDA(device_alloc_retry(&p.d_H, p.spec_bytes()));
 }
 
 void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cudaStream_t st)
@@ -721,7 +785,7 @@ bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaSt
         cudaFree(p.d_Hwin);
         p.d_Hwin = nullptr;
         p.hwin_cap = 0;
-        FC_CUDA(cudaMalloc(&p.d_Hwin, need * sizeof(float2)));
+        FC_CUDA(device_alloc_retry(&p.d_Hwin, need * sizeof(float2)));
         p.hwin_cap = need;
     }
     p.hwin_valid = false;

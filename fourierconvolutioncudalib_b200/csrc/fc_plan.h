@@ -103,6 +103,12 @@ std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz, bool work
 void workspace_acquire(ConvPlan& p, cudaStream_t st);
 void workspace_release(ConvPlan& p, cudaStream_t st);
 void release_all_plans();
+// cudaMalloc for the lazily allocated, volume-sized buffers of a plan (PSF spectrum, staging, ring, window): when the
+// device is out of memory every IDLE cached plan is dropped and the allocation retried once -- the reference frees
+// everything after each call, so a call with a new large shape must not fail because idle plans still hold memory.
+cudaError_t device_alloc_retry(void** p, size_t bytes);
+template <typename T>
+inline cudaError_t device_alloc_retry(T** p, size_t bytes) { return device_alloc_retry(reinterpret_cast<void**>(p), bytes); }
 long long launch_count();
 void count_launches(int n);
 

@@ -387,6 +387,62 @@ template <> struct Dft<10> : DftCT<2, 5> {};
 template <> struct Dft<12> : DftCT<4, 3> {};
 template <> struct Dft<15> : DftCT<3, 5> {};
 
+// ---- odd primes 11, 13, 17, 19, 23 in registers ----------------------------------------------------------------
+// The extents reference callers pad to by image + kernel - 1 are rarely 7-smooth (its own tests use 130 = 2*5*13,
+// 132 = 4*3*11, 46 = 2*23, 66 = 2*3*11 ...: /root/reference/tests/test_gpu_numerical_stability.cpp).  A prime radix R runs
+// as the symmetric direct DFT in the registers of one thread, (R-1)^2 / 2 packed multiply-adds on compile-time roots:
+//   t_j = x_j + x_(R-j),  u_j = x_j - x_(R-j),  j = 1 .. (R-1)/2
+//   X_m, X_(R-m) = (x_0 + sum_j cos(2 pi j m / R) t_j)  -/+  i (sum_j sin(2 pi j m / R) u_j)
+// instead of an O(R) sum per OUTPUT through shared memory (the generic stage, still used for larger primes).
+template <int R>
+struct DftOddPrime {
+    static __device__ __forceinline__ void run(p2* r, p2* i)
+    {
+        constexpr ctrig::Roots<R> W{};
+        constexpr int H = (R - 1) / 2;
+        p2 tr[H], ti[H], ur[H], ui[H];
+#pragma unroll
+        for (int j = 1; j <= H; ++j) {
+            tr[j - 1] = padd(r[j], r[R - j]);
+            ti[j - 1] = padd(i[j], i[R - j]);
+            ur[j - 1] = psub(r[j], r[R - j]);
+            ui[j - 1] = psub(i[j], i[R - j]);
+        }
+        const p2 x0r = r[0], x0i = i[0];
+        p2 sr = x0r, si = x0i;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            sr = padd(sr, tr[j]);
+            si = padd(si, ti[j]);
+        }
+        r[0] = sr;
+        i[0] = si;
+#pragma unroll
+        for (int m = 1; m <= H; ++m) {
+            p2 ar = x0r, ai = x0i;
+            p2 br = make_float2(0.f, 0.f), bi = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 1; j <= H; ++j) {
+                const float C = W.c[(j * m) % R], S = W.s[(j * m) % R];
+                ar = pfmas(tr[j - 1], C, ar);
+                ai = pfmas(ti[j - 1], C, ai);
+                br = pfmas(ur[j - 1], S, br);
+                bi = pfmas(ui[j - 1], S, bi);
+            }
+            // X_m = a - i b,  X_(R-m) = a + i b
+            r[m] = padd(ar, bi);
+            i[m] = psub(ai, br);
+            r[R - m] = psub(ar, bi);
+            i[R - m] = padd(ai, br);
+        }
+    }
+};
+template <> struct Dft<11> : DftOddPrime<11> {};
+template <> struct Dft<13> : DftOddPrime<13> {};
+template <> struct Dft<17> : DftOddPrime<17> {};
+template <> struct Dft<19> : DftOddPrime<19> {};
+template <> struct Dft<23> : DftOddPrime<23> {};
+
 // Twiddles are kept in shared memory as float4 (c, c, s, s): both packed operands come out of one
 // 128-bit load as aligned register pairs.
 // (xr + i*xi) *= (c + i*s)

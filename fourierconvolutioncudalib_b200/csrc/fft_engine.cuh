@@ -13,7 +13,7 @@
 // reversal).  Inverse (DIT, stages mirrored) takes that order back to natural order.  Callers map
 // positions to global rows, so natural order in global memory costs nothing for the strided axes.
 //
-// Radices 2,3,4,5,6,7,8,9,10,12,15,16 run in registers (6..15: composite, fft_butterflies.cuh).  Any other prime factor p runs as a direct O(p) sum per
+// Radices 2,3,4,5,6,7,8,9,10,12,15,16 and the primes 11,13,17,19,23 run in registers (fft_butterflies.cuh).  Any larger prime factor p runs as a direct O(p) sum per
 // output between two tile buffers (ping-pong), so every length the C ABI can receive is supported
 // (the reference's own tests use 79, 109, 173, 37, 23, 53, ... -- SURVEY.md section 4).
 //
@@ -85,7 +85,13 @@ __device__ __forceinline__ void stage_smem(float4* __restrict__ buf, const float
     }
 }
 
-// Generic prime radix p (run-time), src -> dst (distinct tile buffers).
+// Generic prime radix p > 23 (run-time), src -> dst (distinct tile buffers): the symmetric direct DFT.
+//   t_k = x_k + x_(p-k),  u_k = x_k - x_(p-k),  k = 1 .. H = (p-1)/2
+//   sum_k x_k w_p^(+-km) = (x_0 + sum_k cos(2 pi k m / p) t_k)  -+  i (sum_k sin(2 pi k m / p) u_k)
+// One work item = one sub-sequence (beta, j) and TWO output pairs (m, p-m), (m+1, p-m-1): every input pair is loaded
+// once for four outputs and every root once for two -- 4 shared-memory loads and 12 packed operations per k for four
+// outputs, against 8 loads and 16 operations in the plain one-output-at-a-time sum (158x158x218: 0.95 -> see
+// profiles/r02_odd_sizes.jsonl).  The item with m = 1 also produces output 0.
 template <bool INV>
 __device__ __forceinline__ void stage_generic(const float4* __restrict__ src, float4* __restrict__ dst,
                                               const float4* __restrict__ tw, int L, int Li, int p, int cp, int w,
@@ -94,49 +100,108 @@ __device__ __forceinline__ void stage_generic(const float4* __restrict__ src, fl
     const int S = Li / p;
     const int tstep = L / Li;
     const int rstep = L / p;
-    const float invS = 1.0f / (float)S, invLi = 1.0f / (float)Li;
-    for (int o = w; o < L; o += W) {
-        const int beta = __float2int_rz(((float)o + 0.5f) * invLi);
-        const int rr = o - beta * Li;
-        const int m = __float2int_rz(((float)rr + 0.5f) * invS);
-        const int j = rr - m * S;
+    const int H = (p - 1) / 2, Qn = (H + 1) / 2;   // Qn items per sub-sequence
+    const int nseq = L / p;                        // sub-sequences (beta, j)
+    const float invQ = 1.0f / (float)Qn, invS = 1.0f / (float)S;
+    for (int it = w; it < nseq * Qn; it += W) {
+        const int sq = __float2int_rz(((float)it + 0.5f) * invQ);   // sub-sequence index = beta * S + j
+        const int q = it - sq * Qn;
+        const int beta = __float2int_rz(((float)sq + 0.5f) * invS);
+        const int j = sq - beta * S;
         const int base = beta * Li + j;
-        // forward: y_m = w_Li^{j m} * sum_k x_k w_p^{k m}
-        // inverse: y_m = sum_k x_k conj(w_Li^{j k} w_p^{k m})      (both roots come from the one table)
-        const int inc = INV ? (j * tstep + m * rstep) : (m * rstep);
-        int idx = 0;
-        p2 ar = make_float2(0.f, 0.f), ai = make_float2(0.f, 0.f);
-        for (int k = 0; k < p; ++k) {
-            const float4 t = tw[idx];
-            const float4 v = src[(base + k * S) * txp + cp];
-            const p2 C = make_float2(t.x, t.y), Sn = make_float2(t.z, t.w);
-            const p2 xr = make_float2(v.x, v.y), xi = make_float2(v.z, v.w);
-            if (INV) {
-                ar = pfma(xr, C, pfma(xi, Sn, ar));
-                ai = pfma(xi, C, pfma(xr, pneg(Sn), ai));
-            } else {
-                ar = pfma(xr, C, pfma(xi, pneg(Sn), ar));
-                ai = pfma(xi, C, pfma(xr, Sn, ai));
+        const int m1 = 1 + 2 * q, m2 = m1 + 1;
+        const bool has2 = m2 <= H;
+        // x_0 (inverse: inputs are twiddled by conj(w_Li^(j k)) first; k = 0 needs none)
+        const float4 v0 = src[base * txp + cp];
+        const p2 x0r = make_float2(v0.x, v0.y), x0i = make_float2(v0.z, v0.w);
+        p2 a1r = x0r, a1i = x0i, a2r = x0r, a2i = x0i, s0r = x0r, s0i = x0i;
+        p2 b1r = make_float2(0.f, 0.f), b1i = b1r, b2r = b1r, b2i = b1r;
+        int e1 = 0, e2 = 0, ej = 0, ejn = 0;   // root indices k*m1*rstep, k*m2*rstep, j*k*tstep, j*(p-k)*tstep (mod L)
+        const int inc1 = (m1 * rstep) % L, inc2 = (m2 * rstep) % L, incj = (j * tstep) % L;
+        ejn = (int)(((long long)j * tstep * p) % L);
+        for (int k = 1; k <= H; ++k) {
+            e1 += inc1;
+            if (e1 >= L) e1 -= L;
+            e2 += inc2;
+            if (e2 >= L) e2 -= L;
+            const float4 va = src[(base + k * S) * txp + cp];
+            const float4 vb = src[(base + (p - k) * S) * txp + cp];
+            p2 xar = make_float2(va.x, va.y), xai = make_float2(va.z, va.w);
+            p2 xbr = make_float2(vb.x, vb.y), xbi = make_float2(vb.z, vb.w);
+            if (INV && S > 1) {
+                ej += incj;
+                if (ej >= L) ej -= L;
+                ejn -= incj;
+                if (ejn < 0) ejn += L;
+                cmulc(xar, xai, tw[ej]);
+                cmulc(xbr, xbi, tw[ejn]);
             }
-            idx += inc;
-            if (idx >= L) idx -= L;
+            const p2 tr = padd(xar, xbr), ti = padd(xai, xbi), ur = psub(xar, xbr), ui = psub(xai, xbi);
+            const float4 r1 = tw[e1];   // (c, c, -s, -s) of exp(-2 pi i k m1 / p)
+            const p2 c1 = make_float2(r1.x, r1.y), n1 = make_float2(r1.z, r1.w);
+            a1r = pfma(tr, c1, a1r);
+            a1i = pfma(ti, c1, a1i);
+            b1r = pfma(ur, n1, b1r);     // b = -sum sin * u
+            b1i = pfma(ui, n1, b1i);
+            if (has2) {
+                const float4 r2 = tw[e2];
+                const p2 c2 = make_float2(r2.x, r2.y), n2 = make_float2(r2.z, r2.w);
+                a2r = pfma(tr, c2, a2r);
+                a2i = pfma(ti, c2, a2i);
+                b2r = pfma(ur, n2, b2r);
+                b2i = pfma(ui, n2, b2i);
+            }
+            if (q == 0) {
+                s0r = padd(s0r, tr);
+                s0i = padd(s0i, ti);
+            }
         }
-        if (!INV && S > 1) cmul(ar, ai, tw[j * m * tstep]);
-        dst[o * txp + cp] = make_float4(ar.x, ar.y, ai.x, ai.y);
+        // with n = -sin:  forward  X_m = a - i*(sum sin u) = a + i*b,  X_(p-m) = a - i*b ;  inverse: the conjugate roots
+        auto emit = [&](int m, p2 ar, p2 ai, p2 br, p2 bi) {
+            p2 yr, yi, zr, zi;   // y = output m, z = output p - m
+            if (INV) {
+                yr = padd(ar, bi); yi = psub(ai, br);      // a - i*b
+                zr = psub(ar, bi); zi = padd(ai, br);      // a + i*b
+            } else {
+                yr = psub(ar, bi); yi = padd(ai, br);      // a + i*b
+                zr = padd(ar, bi); zi = psub(ai, br);      // a - i*b
+                if (S > 1) {
+                    cmul(yr, yi, tw[(int)(((long long)j * m * tstep) % L)]);
+                    cmul(zr, zi, tw[(int)(((long long)j * (p - m) * tstep) % L)]);
+                }
+            }
+            dst[(base + m * S) * txp + cp] = make_float4(yr.x, yr.y, yi.x, yi.y);
+            dst[(base + (p - m) * S) * txp + cp] = make_float4(zr.x, zr.y, zi.x, zi.y);
+        };
+        emit(m1, a1r, a1i, b1r, b1i);
+        if (has2) emit(m2, a2r, a2i, b2r, b2i);
+        if (q == 0) dst[base * txp + cp] = make_float4(s0r.x, s0r.y, s0i.x, s0i.y);
     }
 }
 
 __device__ __forceinline__ bool is_fast_radix(int R)
 {
     return R == 1 || R == 2 || R == 3 || R == 4 || R == 5 || R == 6 || R == 7 || R == 8 || R == 9 || R == 10 || R == 12 ||
-           R == 15 || R == 16;
+           R == 15 || R == 16 || R == 11 || R == 13 || R == 17 || R == 19 || R == 23;
 }
 
-template <bool INV>
+// BIG: the kernel is compiled with the register butterflies of the primes 11..23 (they cost registers, so plans
+// without such a radix run kernels compiled without them; AxisPlanDev::big tells the launcher which)
+template <bool INV, bool BIG = false>
 __device__ __forceinline__ void stage_dispatch(int R, float4*& cur, float4*& oth, const float4* tw, int L, int Li,
                                                int cp, int w, int W, int txp, bool active)
 {
     if (active) {
+        if constexpr (BIG) {
+            switch (R) {
+                case 11: stage_smem<11, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                case 13: stage_smem<13, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                case 17: stage_smem<17, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                case 19: stage_smem<19, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                case 23: stage_smem<23, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                default: break;
+            }
+        }
         switch (R) {
             case 1: break;
             case 2: stage_smem<2, INV>(cur, tw, L, Li, cp, w, W, txp); break;
@@ -165,7 +230,7 @@ __device__ __forceinline__ void stage_dispatch(int R, float4*& cur, float4*& oth
 // Ends with a __syncthreads(); returns the buffer that holds the result.
 //   forward: natural order in, position p holds frequency P.rev[p] out
 //   inverse: the mirror image (scaled by L, like cuFFT's unnormalised inverse)
-template <bool INV>
+template <bool INV, bool BIG = false>
 __device__ __forceinline__ float4* engine_run(const AxisPlanDev& P, float4* A, float4* B, const float4* tw, int cp,
                                               int w, int W, int txp, bool active)
 {
@@ -175,7 +240,7 @@ __device__ __forceinline__ float4* engine_run(const AxisPlanDev& P, float4* A, f
         int Li = P.L;
         for (int s = 0; s < P.ns; ++s) {
             const int R = P.radix[s];
-            stage_dispatch<false>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active);
+            stage_dispatch<false, BIG>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active);
             Li /= R;
             __syncthreads();
         }
@@ -184,7 +249,7 @@ __device__ __forceinline__ float4* engine_run(const AxisPlanDev& P, float4* A, f
         for (int s = P.ns - 1; s >= 0; --s) {
             const int R = P.radix[s];
             Li *= R;
-            stage_dispatch<true>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active);
+            stage_dispatch<true, BIG>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active);
             __syncthreads();
         }
     }

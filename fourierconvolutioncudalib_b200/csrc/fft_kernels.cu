@@ -22,7 +22,7 @@ namespace fcb200 {
 // ------------------------------------------------------------------------------------------------
 // Strided-axis passes (y, z): generic all-shared-memory version (any length, any tile width)
 // ------------------------------------------------------------------------------------------------
-template <int MODE>  // 0 forward, 1 inverse, 2 forward * H * scale, inverse
+template <int MODE, bool BIG>  // 0 forward, 1 inverse, 2 forward * H * scale, inverse; BIG: with the prime radices 11..23
 __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
 {
     extern __shared__ float4 smem[];
@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
 
     float4* cur;
     if (MODE == 1) {
-        cur = engine_run<true>(a.P, A, B, tw_s, cp, w, W, txp, active);
+        cur = engine_run<true, BIG>(a.P, A, B, tw_s, cp, w, W, txp, active);
     } else {
-        cur = engine_run<false>(a.P, A, B, tw_s, cp, w, W, txp, active);
+        cur = engine_run<false, BIG>(a.P, A, B, tw_s, cp, w, W, txp, active);
     }
 
     if (MODE == 2) {
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
         }
         __syncthreads();
         float4* oth = (cur == A) ? B : A;
-        cur = engine_run<true>(a.P, cur, oth, tw_s, cp, w, W, txp, active);
+        cur = engine_run<true, BIG>(a.P, cur, oth, tw_s, cp, w, W, txp, active);
     }
 
     if (active) {
@@ -156,12 +156,16 @@ void launch_x_fwd(const XArgs& a, bool psf, cudaStream_t st)
     const size_t smem = x_smem_bytes(a.g, a.P, b.txp);
     const long long tiles = (a.nrows + 2 * b.txp - 1) / (2 * b.txp);
     if (tiles == 0) return;
-    if (psf) {
-        set_smem(x_fwd_kernel<1, DynPlan, kColThreads>, smem);
-        x_fwd_kernel<1, DynPlan, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a2);
+    auto go = [&](auto kernel) {
+        set_smem(kernel, smem);
+        kernel<<<(unsigned)tiles, x_threads(), smem, st>>>(a2);
+    };
+    if (a.P.big) {
+        if (psf) go(x_fwd_kernel<1, DynPlanBig, kColThreads>);
+        else go(x_fwd_kernel<0, DynPlanBig, kColThreads>);
     } else {
-        set_smem(x_fwd_kernel<0, DynPlan, kColThreads>, smem);
-        x_fwd_kernel<0, DynPlan, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a2);
+        if (psf) go(x_fwd_kernel<1, DynPlan, kColThreads>);
+        else go(x_fwd_kernel<0, DynPlan, kColThreads>);
     }
     FC_CUDA_KERNEL();
 }
@@ -175,8 +179,13 @@ void launch_x_inv(const XArgs& a, cudaStream_t st)
     const size_t smem = x_smem_bytes(a.g, a.P, b.txp);
     const long long tiles = (a.nrows + 2 * b.txp - 1) / (2 * b.txp);
     if (tiles == 0) return;
-    set_smem(x_inv_kernel<DynPlan, kColThreads>, smem);
-    x_inv_kernel<DynPlan, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a2);
+    if (a.P.big) {
+        set_smem(x_inv_kernel<DynPlanBig, kColThreads>, smem);
+        x_inv_kernel<DynPlanBig, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a2);
+    } else {
+        set_smem(x_inv_kernel<DynPlan, kColThreads>, smem);
+        x_inv_kernel<DynPlan, kColThreads><<<(unsigned)tiles, x_threads(), smem, st>>>(a2);
+    }
     FC_CUDA_KERNEL();
 }
 
@@ -186,19 +195,18 @@ void launch_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
     const long long grid = ngroups * a.tilesPerGroup;
     if (grid == 0) return;
     if (grid > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");
-    switch (mode) {
-        case 0:
-            set_smem(col_kernel<0>, smem);
-            col_kernel<0><<<(unsigned)grid, kColThreads, smem, st>>>(a);
-            break;
-        case 1:
-            set_smem(col_kernel<1>, smem);
-            col_kernel<1><<<(unsigned)grid, kColThreads, smem, st>>>(a);
-            break;
-        default:
-            set_smem(col_kernel<2>, smem);
-            col_kernel<2><<<(unsigned)grid, kColThreads, smem, st>>>(a);
-            break;
+    auto go = [&](auto kernel) {
+        set_smem(kernel, smem);
+        kernel<<<(unsigned)grid, kColThreads, smem, st>>>(a);
+    };
+    if (a.P.big) {
+        if (mode == 0) go(col_kernel<0, true>);
+        else if (mode == 1) go(col_kernel<1, true>);
+        else go(col_kernel<2, true>);
+    } else {
+        if (mode == 0) go(col_kernel<0, false>);
+        else if (mode == 1) go(col_kernel<1, false>);
+        else go(col_kernel<2, false>);
     }
     FC_CUDA_KERNEL();
 }

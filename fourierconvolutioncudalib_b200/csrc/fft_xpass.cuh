@@ -7,6 +7,9 @@
 namespace fcb200 {
 
 struct DynPlan {};
+struct DynPlanBig {};   // run-time radices including the register butterflies of the primes 11..23
+template <class P> struct IsBigPlan { static constexpr bool value = false; };
+template <> struct IsBigPlan<DynPlanBig> { static constexpr bool value = true; };
 
 template <class P>
 struct PlanLen {
@@ -14,6 +17,10 @@ struct PlanLen {
 };
 template <>
 struct PlanLen<DynPlan> {
+    static __device__ __forceinline__ int get(const AxisPlanDev& d) { return d.L; }
+};
+template <>
+struct PlanLen<DynPlanBig> {
     static __device__ __forceinline__ int get(const AxisPlanDev& d) { return d.L; }
 };
 
@@ -32,6 +39,14 @@ struct PlanRun<DynPlan, NW, INV> {
                                                   int cp, int w, int W)
     {
         return engine_run<INV>(d, A, B, tw, cp, w, W, 8, true);
+    }
+};
+template <int NW, bool INV>
+struct PlanRun<DynPlanBig, NW, INV> {
+    static __device__ __forceinline__ float4* run(const AxisPlanDev& d, float4* A, float4* B, const float4* tw,
+                                                  int cp, int w, int W)
+    {
+        return engine_run<INV, true>(d, A, B, tw, cp, w, W, 8, true);
     }
 };
 
@@ -217,10 +232,14 @@ template <>
 struct IsStaticPlan<DynPlan> {
     static constexpr bool value = false;
 };
+template <>
+struct IsStaticPlan<DynPlanBig> {
+    static constexpr bool value = false;
+};
 
 // P = DynPlan: run-time radices (any length);  P = SPlan<...>: compile-time specialised stages.
 template <int LOADER, class PL, int THREADS>  // LOADER 0: dense real rows, 1: PSF gather
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kernel(XArgs a)
+__global__ void __launch_bounds__(THREADS, (IsBigPlan<PL>::value ? 1 : (THREADS <= 256 ? 3 : 1))) x_fwd_kernel(XArgs a)
 {
     extern __shared__ float4 smem[];
     const Geometry g = a.g;
@@ -320,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) x_fwd_kerne
             sm.A[pos * TXP + cp] = make_float4(u.x, v.x, u.y, v.y);
         }
         __syncthreads();
-        cur = engine_run<false>(a.P, sm.A, sm.B, sm.tw, cp, w, W, TXP, true);
+        cur = engine_run<false, IsBigPlan<PL>::value>(a.P, sm.A, sm.B, sm.tw, cp, w, W, TXP, true);
     }
 
     // ---- engine tile -> row tile (interleaved spectrum rows, natural kx); even nx: split the packed
@@ -493,7 +512,7 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
         __syncthreads();
         sstage_rows_last_inv<PL::R0, PL::L, NW>(sm.A, rowt, P, sm.tw, cp, w);
     } else {
-        float4* cur = engine_run<true>(a.P, sm.A, sm.B, sm.tw, cp, w, W, TXP, true);
+        float4* cur = engine_run<true, IsBigPlan<PL>::value>(a.P, sm.A, sm.B, sm.tw, cp, w, W, TXP, true);
         for (int pos = w; pos < L; pos += W) {
             const float4 v = cur[pos * TXP + cp];
             rowt[(2 * cp) * P + pos] = make_float2(v.x, v.z);

@@ -43,7 +43,8 @@ FUNCTION_PREFIX void fcb200_convolve_padded_device_async(imageType* im_dev, cons
 
 /* Planner introspection (pure host code; callable without a GPU).
  * fcb200_plan_radices: writes the stage radices of a length-L transform (at most 16), returns the
- * number of stages; *generic is 1 when a radix outside {2,3,4,5,7,8} is needed. */
+ * number of stages; *generic is 1 when a prime factor above 23 is present (those stages run as direct sums between
+ * two tile buffers; 2..16 and the primes 11, 13, 17, 19, 23 run as register butterflies). */
 FUNCTION_PREFIX int fcb200_plan_radices(int L, int* radices, int* generic);
 /* rev[p]: frequency at position p after the forward transform; pos = inverse permutation;
  * tw: L interleaved (re,im) roots exp(-2*pi*i*t/L).  Any pointer may be NULL. */

@@ -51,7 +51,7 @@ def test_c_planner_matches_model(fc, L, style):
     radices, generic = fc.plan_radices(L, style)
     assert radices == em.factorize(L, style)
     assert int(np.prod(radices)) == L
-    assert generic == any(r not in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16) for r in radices)
+    assert generic == any(r not in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 19, 23) for r in radices)
     rev, pos, tw = fc.plan_tables(L, style)
     assert np.array_equal(rev, em.rev_positions(L, radices))
     assert np.array_equal(pos[rev], np.arange(L))
@@ -75,7 +75,8 @@ def test_psf_active_rows_match_oracle_placement(fc):
 def test_c_planner_matches_model_exhaustively_up_to_1200(fc):
     """every length a caller can pass on an axis (up to 1200, plus the padded config-5 extents): same radix
     sequence as the numpy model, product == L, stages bounded, digit reversal a permutation"""
-    fast = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16)
+    fast = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 19, 23)     # register butterflies
+    smooth7 = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16)
     for L in list(range(1, 1201)) + [1125, 2048, 2160, 4096]:
         for style in (0, 1, 2):
             radices, generic = fc.plan_radices(L, style)
@@ -83,7 +84,7 @@ def test_c_planner_matches_model_exhaustively_up_to_1200(fc):
             assert int(np.prod(radices)) == L
             assert generic == any(r not in fast for r in radices)
         r0 = em.factorize(L)
-        smooth = [r for r in r0 if r in fast]
+        smooth = [r for r in r0 if r in smooth7]
         if len(smooth) == len(r0) and L > 1:
             # 7-smooth lengths never need more than four shared-memory round trips up to 1200 ... except the few with
             # many repeated small primes that even composite radices cannot pack into four stages

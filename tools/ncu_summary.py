@@ -32,6 +32,14 @@ def pass_of(name, grid):
         return "x_fwd"
     if "xrow_inv" in name or "xrowg_inv" in name or "x_inv_kernel" in name:
         return "x_inv"
+    if "col_tma_kernel<0" in name or "col_tma_kernel<(int)0" in name:
+        return "psf_y" if g < 100 else "y_fwd"
+    if "col_tma_kernel<1" in name or "col_tma_kernel<(int)1" in name:
+        return "y_inv"
+    if "col_tma_kernel<2" in name or "col_tma_kernel<(int)2" in name:
+        return "z_fused"
+    if "col_tma_kernel<3" in name or "col_tma_kernel<(int)3" in name:
+        return "z_fused_otf"
     if "col_pipe_kernel<0" in name:
         return "y_fwd"
     if "col_pipe_kernel<1" in name:
