@@ -755,7 +755,7 @@ void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cuda
         PassTimer t(kPassPsfZ, st);
         ColArgs za = z_args(p, p.d_H);
         za.rowMask = p.d_plane_mask;
-        if (!(p.psf_window_z0 >= 0 && p.psf_window_planes == 16 && launch_psf_z_pruned(za, p.psf_window_z0, st)))
+        if (!(p.psf_window_z0 >= 0 && launch_psf_z_pruned(za, p.psf_window_z0, p.psf_window_planes, st)))
             col_pass(za, 0, 1, st);
     }
     count_launches(3);
@@ -1091,7 +1091,7 @@ void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, 
     za.rowMask = p.d_plane_mask;
     {
         PassTimer t(kPassPsfZ, st);
-        if (!(p.psf_window_z0 >= 0 && p.psf_window_planes == 16 && launch_psf_z_pruned(za, p.psf_window_z0, st)))
+        if (!(p.psf_window_z0 >= 0 && launch_psf_z_pruned(za, p.psf_window_z0, p.psf_window_planes, st)))
             col_pass(za, 0, 1, st);
     }
     count_launches(3);

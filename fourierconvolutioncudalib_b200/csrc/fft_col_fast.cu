@@ -307,25 +307,21 @@ void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t
         // one radix-8 butterfly per worker and stage: L/8 workers of 8 lanes, within [128, maxT]
         threads = ((a.P.L + 31) / 32) * 32;
     }
-    const int maxT = (variant == 2) ? 512 : 256;
+    (void)variant;
+    const int maxT = 256;
     threads = std::max(64, std::min(threads, maxT));
     auto go = [&](auto kernel) {
         if (smem > 48 * 1024)
             FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kernel<<<(unsigned)grid, threads, smem, st>>>(a);
     };
-#define FC_GO(M)                                                     \
-    switch (variant) {                                               \
-        case 1: go(col_fast_kernel<M, 256, 3, 8>); break;            \
-        case 2: go(col_fast_kernel<M, 512, 2, 8>); break;            \
-        default: go(col_fast_kernel<M, 256, 2, 16>); break;          \
-    }
+    // (the <=80- and <=64-register variants of round 1 spilled in the radix-16 / 15 / 12 arms and never won a sweep:
+    // removed; this build keeps at most 92 bytes of spill stores)
     switch (mode) {
-        case 0: FC_GO(0); break;
-        case 1: FC_GO(1); break;
-        default: FC_GO(2); break;
+        case 0: go(col_fast_kernel<0, 256, 2, 16>); break;
+        case 1: go(col_fast_kernel<1, 256, 2, 16>); break;
+        default: go(col_fast_kernel<2, 256, 2, 16>); break;
     }
-#undef FC_GO
     FC_CUDA_KERNEL();
 }
 
@@ -335,9 +331,10 @@ void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t
 // i.e. one radix-16 butterfly per output residue k2 on the 16 twiddled inputs: no shared-memory
 // stages, no barriers after the 2 KB window is staged.  L % 16 == 0.
 // ------------------------------------------------------------------------------------------------
+template <int NH>   // window of 16 * NH planes
 __global__ void __launch_bounds__(1024) psf_z_pruned_kernel(ColArgs a, int z0)
 {
-    __shared__ float4 win[16 * 8];
+    __shared__ float4 win[16 * NH * 8];
     const int L = a.P.L, Q = L / 16;
     const int t = threadIdx.x, cp = t & 7, w = t >> 3;   // w = residue k2 in [0, Q)
     const int col0 = blockIdx.x * 16;
@@ -346,17 +343,19 @@ __global__ void __launch_bounds__(1024) psf_z_pruned_kernel(ColArgs a, int z0)
     float2* base = a.data + col0 + 2 * cp;
     const size_t stride = (size_t)a.stride;
 
-    if (t < 128) {
-        const int n = t >> 3;
+    for (int q = t; q < 128 * NH; q += blockDim.x) {
+        const int n = q >> 3;
         int z = z0 + n;
         if (z >= L) z -= L;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active && (a.rowMask == nullptr || a.rowMask[z])) v = *reinterpret_cast<const float4*>(base + (size_t)z * stride);
-        win[n * 8 + cp] = v;
+        if ((q & 7) < npairs && (a.rowMask == nullptr || a.rowMask[z]))
+            v = *reinterpret_cast<const float4*>(a.data + col0 + 2 * (q & 7) + (size_t)z * stride);
+        win[q] = v;
     }
     __syncthreads();
     if (!active) return;
 
+    // sum over the 16-plane sub-windows first: w16^(n k1) only depends on n mod 16
     p2 r[16], i[16];
     int e = (int)(((long long)z0 * w) % L);   // exponent (z0 + n) * k2 mod L, advanced by k2 per input
 #pragma unroll
@@ -368,6 +367,20 @@ __global__ void __launch_bounds__(1024) psf_z_pruned_kernel(ColArgs a, int z0)
         cmul(r[n], i[n], make_float4(tw.x, tw.x, tw.y, tw.y));
         e += w;
         if (e >= L) e -= L;
+    }
+#pragma unroll
+    for (int h = 1; h < NH; ++h) {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+            const float4 v = win[(16 * h + n) * 8 + cp];
+            const float2 tw = __ldg(a.P.tw + e);
+            p2 tr = make_float2(v.x, v.y), ti = make_float2(v.z, v.w);
+            cmul(tr, ti, make_float4(tw.x, tw.x, tw.y, tw.y));
+            r[n] = padd(r[n], tr);
+            i[n] = padd(i[n], ti);
+            e += w;
+            if (e >= L) e -= L;
+        }
     }
     Dft<16>::run(r, i);
     const int s16 = z0 & 15;   // w16^(z0 k1) = w_L^((z0 k1 mod 16) * Q)
@@ -381,14 +394,18 @@ __global__ void __launch_bounds__(1024) psf_z_pruned_kernel(ColArgs a, int z0)
     }
 }
 
-bool launch_psf_z_pruned(const ColArgs& a, int z0, cudaStream_t st)
+// planes: size of the window (16, 32 or 64 consecutive planes from z0, mod L) that holds every non-zero input plane
+bool launch_psf_z_pruned(const ColArgs& a, int z0, int planes, cudaStream_t st)
 {
     static const bool on = env_int("FCB200_PSF_PRUNED", 1) != 0;
     const int L = a.P.L;
     if (!on || L % 16 != 0 || L / 16 * 8 > 1024 || L / 16 * 8 < 128 || a.groupStride != 0) return false;
+    if ((planes != 16 && planes != 32 && planes != 64) || planes > L) return false;
     const int tiles = (a.rowLen + 15) / 16;
     if (tiles == 0) return true;
-    psf_z_pruned_kernel<<<tiles, L / 16 * 8, 0, st>>>(a, z0);
+    if (planes == 16) psf_z_pruned_kernel<1><<<tiles, L / 16 * 8, 0, st>>>(a, z0);
+    else if (planes == 32) psf_z_pruned_kernel<2><<<tiles, L / 16 * 8, 0, st>>>(a, z0);
+    else psf_z_pruned_kernel<4><<<tiles, L / 16 * 8, 0, st>>>(a, z0);
     FC_CUDA_KERNEL();
     return true;
 }

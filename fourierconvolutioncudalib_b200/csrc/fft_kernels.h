@@ -68,10 +68,10 @@ int col_pick_txp(const AxisPlanDev& P);
 void launch_x_fwd(const XArgs& a, bool psf, cudaStream_t st);
 void launch_x_inv(const XArgs& a, cudaStream_t st);
 void launch_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
-// PSF z pass when all non-zero input planes lie in a window of 16 consecutive planes starting at z0
+// PSF z pass when all non-zero input planes lie in a window of `planes` = 16, 32 or 64 consecutive planes starting at z0
 // (mod L) and L % 16 == 0: each output residue is one radix-16 butterfly of the 16 twiddled inputs
 // (input-pruned FFT); in place on `data` with the geometry of a z pass.  Returns false if not applicable.
-bool launch_psf_z_pruned(const ColArgs& a, int z0, cudaStream_t st);
+bool launch_psf_z_pruned(const ColArgs& a, int z0, int planes, cudaStream_t st);
 // fast path (fft_col_fast.cu): first/last stage fused with the global loads/stores
 bool col_fast_supported(const AxisPlanDev& P);
 void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
