@@ -300,6 +300,7 @@ ConvPlan::~ConvPlan()
     cudaFree(d_kernel);
     cudaFree(d_unpadded);
     cudaFree(d_rows);
+    cudaFree(d_rows_c);
     cudaFree(d_planes);
     cudaFree(d_plane_mask);
     cudaFree(d_tap_start);
@@ -389,7 +390,6 @@ std::shared_ptr<ConvPlan> get_plan(int device, int nx, int ny, int nz, bool work
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
         it->second->last_use = ++g_tick;
-        enforce_byte_budget_locked(it->second.get());
         return it->second;
     }
     std::shared_ptr<ConvPlan> p;
@@ -445,12 +445,20 @@ static void enforce_byte_budget_locked(const ConvPlan* keep)
     if (budget_mb >= 0) {
         budget = (size_t)budget_mb << 20;
     } else {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
-            cudaGetLastError();
-            return;
+        // half of the device memory; queried once per device (cudaMemGetInfo costs about a millisecond)
+        static size_t total_of[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return;
+        if (total_of[dev] == 0) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+                cudaGetLastError();
+                return;
+            }
+            total_of[dev] = total_b;
         }
-        budget = total_b / 2;
+        budget = total_of[dev] / 2;
     }
     for (;;) {
         size_t sum = 0;
@@ -629,17 +637,39 @@ static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
         std::vector<int> planes, rows;
         int win_z0 = -1, win_planes = 0;
         psf_plane_list(pdims, p.g, mask, planes, win_z0, win_planes);
-        for (int z : planes)
-            for (int y = 0; y < p.g.ny; ++y) rows.push_back(z * p.g.ny + y);
+        // the x pass transforms only the rows that hold a tap (a few dozen of the ny rows of a plane: C3 31 of 512,
+        // C5 63 of 2048); the other rows of the listed planes are zero and are cleared with a memset instead.
+        // rows[i]: global row z*ny + y (output row of the materialised path); rows_c[i]: row in a compact buffer that
+        // holds the listed planes back to back (window buffer, slab scratch): (list plane)*ny + y
+        std::vector<int> rows_c, row_index((size_t)planes.size() * p.g.ny, -1);
+        {
+            std::vector<int> plane_slot0((size_t)p.g.nz, -1);
+            for (size_t i = 0; i < planes.size(); ++i) plane_slot0[(size_t)planes[i]] = (int)i;
+            std::vector<unsigned char> has((size_t)planes.size() * p.g.ny, 0);
+            for (int r : psf_active_rows(pdims + 3, pdims, p.g.nx)) {
+                const int slot = plane_slot0[(size_t)(r / p.g.ny)];
+                if (slot >= 0) has[(size_t)slot * p.g.ny + (size_t)(r % p.g.ny)] = 1;
+            }
+            for (size_t slot = 0; slot < planes.size(); ++slot)
+                for (int y = 0; y < p.g.ny; ++y)
+                    if (has[slot * p.g.ny + (size_t)y]) {
+                        row_index[slot * p.g.ny + (size_t)y] = (int)rows.size();
+                        rows.push_back(planes[slot] * p.g.ny + y);
+                        rows_c.push_back((int)slot * p.g.ny + y);
+                    }
+        }
         FC_CUDA(cudaStreamSynchronize(st));  // earlier launches on this stream may still read the old lists
         std::memset(p.psf_key, 0, sizeof(p.psf_key));   // a failed rebuild must not leave a key that matches stale lists
         if (rows.size() > p.rows_cap) {
             cudaFree(p.d_rows);
-            p.d_rows = nullptr;
+            cudaFree(p.d_rows_c);
+            p.d_rows = p.d_rows_c = nullptr;
             p.rows_cap = 0;
             FC_CUDA(cudaMalloc(&p.d_rows, sizeof(int) * rows.size()));
+            FC_CUDA(cudaMalloc(&p.d_rows_c, sizeof(int) * rows.size()));
             p.rows_cap = rows.size();
         }
+        FC_CUDA(cudaMemcpy(p.d_rows_c, rows_c.data(), sizeof(int) * rows_c.size(), cudaMemcpyHostToDevice));
         if (!p.d_planes) FC_CUDA(cudaMalloc(&p.d_planes, sizeof(int) * p.g.nz));
         if (!p.d_plane_mask) FC_CUDA(cudaMalloc(&p.d_plane_mask, (size_t)p.g.nz));
         FC_CUDA(cudaMemcpy(p.d_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice));
@@ -673,7 +703,7 @@ static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
                         const long long flat = cq + d2 * (bq + d1 * aq);
                         const long long grow = flat / p.g.nx;
                         const int slot = plane_slot[(size_t)(grow / p.g.ny)];
-                        lrow[t] = slot * p.g.ny + (int)(grow % p.g.ny);
+                        lrow[t] = row_index[(size_t)slot * p.g.ny + (size_t)(grow % p.g.ny)];
                         start[(size_t)lrow[t] + 1]++;
                     }
                 }
@@ -717,6 +747,18 @@ static void psf_lists(ConvPlan& p, const int* pdims, cudaStream_t st)
     }
 }
 
+// zero the planes of `spec` ([nz][ny][xcp]) that the PSF passes work on, one memset per run of consecutive planes
+static void clear_listed_planes(ConvPlan& p, float2* spec, cudaStream_t st)
+{
+    const size_t splane = (size_t)p.g.ny * p.g.xcp;
+    for (int i = 0; i < p.n_planes;) {
+        int j = i + 1;
+        while (j < p.n_planes && p.h_planes[(size_t)j] == p.h_planes[(size_t)j - 1] + 1) ++j;
+        FC_CUDA(cudaMemsetAsync(spec + (size_t)p.h_planes[(size_t)i] * splane, 0, (size_t)(j - i) * splane * sizeof(float2), st));
+        i = j;
+    }
+}
+
 void ensure_full_workspace(ConvPlan& p)
 {
     if (!p.d_H) FC_CUDA(device_alloc_retry(&p.d_H, p.spec_bytes()));
@@ -727,6 +769,7 @@ void run_psf_spectrum(ConvPlan& p, const float* d_kernel, const int* pdims, cuda
     p.h_valid = false;   // the caller re-validates the cache when it knows the taps (host-pointer calls)
     ensure_full_workspace(p);
     psf_lists(p, pdims, st);
+    clear_listed_planes(p, p.d_H, st);   // rows without taps are not transformed (psf_lists)
     XArgs xa = x_args(p);
     xa.spec = p.d_H;
     xa.nrows = p.n_rows;
@@ -802,11 +845,11 @@ bool run_psf_window(ConvPlan& p, const float* d_kernel, const int* pdims, cudaSt
         FC_CUDA(cudaMemcpy(p.d_win_slot, slots, sizeof(slots), cudaMemcpyHostToDevice));
         std::memcpy(p.win_key, pdims, sizeof(int) * 6);
     }
+    FC_CUDA(cudaMemsetAsync(p.d_Hwin, 0, need * sizeof(float2), st));   // rows without taps are not transformed
     XArgs xa = x_args(p);
     xa.spec = p.d_Hwin;
     xa.nrows = p.n_rows;
-    xa.rowList = p.d_rows;
-    xa.compactOut = 1;
+    xa.rowList = p.d_rows_c;   // output row in the compact buffer
     xa.psf.kernel = d_kernel;
     xa.psf.k0 = pdims[0];
     xa.psf.k1 = pdims[1];
@@ -1047,12 +1090,12 @@ void run_slab_psf(ConvPlan& p, const float* d_kernel, const int* pdims, int y0, 
     if (y0 < 0 || y0 >= p.g.ny) throw std::runtime_error("fcb200: PSF slab out of range");
     const int rows_here = std::min(nyl, p.g.ny - y0);   // ragged last slab: fewer valid rows, same pitch
     psf_lists(p, pdims, st);
-    // x pass (gather loader) on every row of the planes that hold taps, written compactly
+    // x pass (gather loader) on the rows that hold taps, written into the compact scratch (cleared first)
+    FC_CUDA(cudaMemsetAsync(scratch, 0, (size_t)p.n_planes * p.g.ny * p.g.xcp * sizeof(float2), st));
     XArgs xa = x_args(p);
     xa.spec = scratch;
     xa.nrows = p.n_rows;
-    xa.rowList = p.d_rows;
-    xa.compactOut = 1;
+    xa.rowList = p.d_rows_c;
     xa.psf.kernel = d_kernel;
     xa.psf.k0 = pdims[0];
     xa.psf.k1 = pdims[1];

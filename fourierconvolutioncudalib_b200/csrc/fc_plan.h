@@ -48,7 +48,8 @@ struct ConvPlan {
     // PSF pruning lists, cached per kernel shape / placement dims
     int psf_key[6] = {0, 0, 0, 0, 0, 0};
     int win_key[6] = {0, 0, 0, 0, 0, 0};
-    int* d_rows = nullptr;       // rows (z*ny+y) the PSF x pass processes: every row of every active plane
+    int* d_rows = nullptr;       // rows (z*ny+y) the PSF x pass processes: the rows of the listed planes that hold a tap
+    int* d_rows_c = nullptr;     // the same rows as indices into a compact buffer of the listed planes: (list plane)*ny + y
     long long n_rows = 0;
     size_t rows_cap = 0;
     int* d_planes = nullptr;     // z planes that hold >= 1 tap

@@ -238,6 +238,38 @@ __device__ __forceinline__ void sstage_swapout(float4* __restrict__ buf, const f
     }
 }
 
+// In-place stage whose twiddles live in REGISTERS.  In a persistent kernel the twiddles of the second stage are the same
+// for every butterfly a thread ever runs (j = b mod S with NW a multiple of S), and in shared memory they are the
+// accesses that conflict: consecutive workers read roots m*tstep*16 bytes apart, a multiple of 128 bytes once
+// tstep >= 8, i.e. a 4-way bank conflict on every twiddle load (ncu: 15 % of the shared-memory wavefronts of the
+// y pass).  tc / ts: cos / -sin of w_L^(j m tstep), m = 1 .. R-1.
+template <int R, int L, int Li, int NW, bool INV, int TXP>
+__device__ __forceinline__ void sstage_regtw(float4* __restrict__ buf, int cp, int w, const float* tc, const float* ts)
+{
+    constexpr int S = Li / R, nb = L / R;
+    constexpr int ITER = (nb + NW - 1) / NW;
+    static_assert(S > 1 && NW % S == 0, "register twiddles need a tile-invariant j");
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int b = w + it * NW;
+        if ((nb % NW) != 0 && b >= nb) break;
+        const int beta = b / S, j = b % S;
+        const int idx0 = (beta * Li + j) * TXP + cp;
+        p2 r[R], i[R];
+        load_pairs<R>(buf, idx0, S * TXP, r, i);
+        if (INV) {
+#pragma unroll
+            for (int k = 1; k < R; ++k) cmulc(r[k], i[k], make_float4(tc[k - 1], tc[k - 1], ts[k - 1], ts[k - 1]));
+            Dft<R>::run(i, r);
+        } else {
+            Dft<R>::run(r, i);
+#pragma unroll
+            for (int m = 1; m < R; ++m) cmul(r[m], i[m], make_float4(tc[m - 1], tc[m - 1], ts[m - 1], ts[m - 1]));
+        }
+        store_pairs<R>(buf, idx0, S * TXP, r, i);
+    }
+}
+
 // last forward stage, x H x c, first inverse stage; H tile in shared memory in the SAME (digit-reversed) order
 template <int R, int L, int NW, int TXP>
 __device__ __forceinline__ void smid_fused_tma(const float4* __restrict__ hs, float4* __restrict__ sm, int cp, int w, float c)
@@ -421,6 +453,19 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
 
     // ---------------- consumers ----------------
     const int cp = t % TXP, w = t / TXP;
+    // second-stage twiddles in registers (see sstage_regtw): plans with >= 3 stages whose stage-2 j is tile-invariant
+    constexpr int S2 = (L / P::R0) / P::R1;
+    constexpr bool REG2 = (P::ns >= 3) && (S2 > 1) && (NW % (S2 > 1 ? S2 : 1) == 0) && (P::R1 <= 16);
+    float tc2[REG2 ? P::R1 - 1 : 1], ts2[REG2 ? P::R1 - 1 : 1];
+    if constexpr (REG2) {
+        const int j2 = w % S2;
+#pragma unroll
+        for (int m = 1; m < P::R1; ++m) {
+            const float4 tv = tw[j2 * m * P::R0];   // w_L^(j m tstep), tstep = L / Li = R0
+            tc2[m - 1] = tv.x;
+            ts2[m - 1] = tv.z;
+        }
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < a.totalTiles; tile += stride, ++it) {
         const int slot = it % NBUF;
@@ -437,14 +482,16 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             } else if constexpr (P::ns == 3) {
                 sstage<P::R0, L, L, NW, false, TXP, MODE == 1>(sm, tw, cp, w);
                 consumer_sync<THREADS>();
-                sstage<P::R1, L, L / P::R0, NW, false, TXP>(sm, tw, cp, w);
+                if constexpr (REG2) sstage_regtw<P::R1, L, L / P::R0, NW, false, TXP>(sm, cp, w, tc2, ts2);
+                else sstage<P::R1, L, L / P::R0, NW, false, TXP>(sm, tw, cp, w);
                 consumer_sync<THREADS>();
                 if constexpr (MODE == 1) sstage_swapout<P::R2, L, L / (P::R0 * P::R1), NW, TXP>(sm, tw, cp, w);
                 else sstage<P::R2, L, L / (P::R0 * P::R1), NW, false, TXP>(sm, tw, cp, w);
             } else {
                 sstage<P::R0, L, L, NW, false, TXP, MODE == 1>(sm, tw, cp, w);
                 consumer_sync<THREADS>();
-                sstage<P::R1, L, L / P::R0, NW, false, TXP>(sm, tw, cp, w);
+                if constexpr (REG2) sstage_regtw<P::R1, L, L / P::R0, NW, false, TXP>(sm, cp, w, tc2, ts2);
+                else sstage<P::R1, L, L / P::R0, NW, false, TXP>(sm, tw, cp, w);
                 consumer_sync<THREADS>();
                 sstage<P::R2, L, L / (P::R0 * P::R1), NW, false, TXP>(sm, tw, cp, w);
                 consumer_sync<THREADS>();
@@ -456,7 +503,8 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             if constexpr (MODE == 3) otf_h_tile<L, NH, NW, TXP>(sm + TILE, hbuf, tw, pos_s, a.z0, cp, w);
             consumer_sync<THREADS>();
             if constexpr (P::ns >= 3) {
-                sstage<P::R1, L, L / P::R0, NW, false, TXP>(sm, tw, cp, w);
+                if constexpr (REG2) sstage_regtw<P::R1, L, L / P::R0, NW, false, TXP>(sm, cp, w, tc2, ts2);
+                else sstage<P::R1, L, L / P::R0, NW, false, TXP>(sm, tw, cp, w);
                 consumer_sync<THREADS>();
             }
             if constexpr (P::ns >= 4) {
@@ -470,7 +518,8 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 consumer_sync<THREADS>();
             }
             if constexpr (P::ns >= 3) {
-                sstage<P::R1, L, P::R1 * P::R2 * P::R3, NW, true, TXP>(sm, tw, cp, w);
+                if constexpr (REG2) sstage_regtw<P::R1, L, P::R1 * P::R2 * P::R3, NW, true, TXP>(sm, cp, w, tc2, ts2);
+                else sstage<P::R1, L, P::R1 * P::R2 * P::R3, NW, true, TXP>(sm, tw, cp, w);
                 consumer_sync<THREADS>();
             }
             sstage<P::R0, L, L, NW, true, TXP>(sm, tw, cp, w);   // natural order again
