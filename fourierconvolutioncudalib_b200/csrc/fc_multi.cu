@@ -55,7 +55,7 @@ struct SlabRank {
     int dev = 0, rank = 0;
     int nzl = 0, ny_here = 0;
     std::shared_ptr<ConvPlan> plan;   // tables only; the slab-sized buffers live here
-    cudaStream_t st = nullptr, s_psf = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t st = nullptr, s_psf = nullptr, s_h2d = nullptr, s_d2h = nullptr, s_x = nullptr;   // s_x: exchange copies
     float* real = nullptr;            // host-pointer calls: this rank's z slab
     float2 *zslab = nullptr, *recv = nullptr, *yslab = nullptr, *H = nullptr, *scratch = nullptr;
     size_t scratch_cap = 0;
@@ -66,7 +66,7 @@ struct SlabRank {
     cudaEvent_t ev_fwd = nullptr, ev_z = nullptr, ev_done = nullptr, ev_psf = nullptr;
     cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_chunk[16] = {};
-    cudaEvent_t ev_d2h = nullptr;
+    cudaEvent_t ev_d2h = nullptr, ev_x = nullptr;
     std::unique_ptr<HostStager> stager;   // pageable host volumes (per rank: emulated ranks share a plan)
     bool timed = false;
 };
@@ -78,6 +78,7 @@ struct SlabCall {
     HostMem im_kind = HostMem::Device;
     bool psf_cached = false;
     int pdims[6] = {0, 0, 0, 0, 0, 0};
+    bool copy_exchange = false;   // forward exchange by copy engines (see run_call)
 };
 
 struct SlabContext {
@@ -102,6 +103,8 @@ struct SlabContext {
     int h_dims[6] = {0, 0, 0, 0, 0, 0};
     std::vector<float> h_taps;
     unsigned long long last_use = 0;
+    int scratch_key[6] = {0, 0, 0, 0, 0, 0};   // PSF scratch size of these placement dims (host-side row scan, cached)
+    size_t scratch_need = 0;
 
     size_t slab_spec_elems() const { return (size_t)P * nzp * nyl * xcp; }
     void worker(int r);
@@ -135,8 +138,14 @@ void SlabContext::run_call(int r)
     float* h_slab = c.im ? c.im + z_first * rplane : nullptr;
     static const bool staging_on = env_flag("FCB200_STAGING", true);
     const bool pinned = c.im && (c.im_kind == HostMem::Pinned || !staging_on);
+    // Forward exchange.  Peer stores from the y pass are 128-byte segments (64-byte for L = 2048, whose tile only fits
+    // shared memory with half rows): config 5 on 8 GPUs reached 300 GB/s per GPU that way and the forward phase took
+    // 6.3 ms for 2.5 ms of local work.  With copy_exchange the y pass writes the exchange layout LOCALLY ([P][nzp][nyl][xcp],
+    // into the receive buffer, which is idle until the fused z pass of the peers) and the copy engines move block q to
+    // rank q in one contiguous transfer per chunk of planes, while the next chunk is being transformed.
+    const bool copy_x = c.copy_exchange && P > 1;
     const int nch = c.im ? (int)std::max<long long>(1, std::min<long long>(8, std::min<long long>(k.nzl, (long long)(slab_bytes >> 25))))
-                         : 1;
+                         : (copy_x ? (int)std::max(1, std::min(4, k.nzl / 8)) : 1);
     const int per = (k.nzl + nch - 1) / nch;
     auto z0_of = [&](int ch) { return std::min(k.nzl, ch * per); };
 
@@ -164,7 +173,25 @@ void SlabContext::run_call(int r)
                 FC_CUDA(cudaEventRecord(k.ev_chunk[ch], k.s_h2d));
                 FC_CUDA(cudaStreamWaitEvent(k.st, k.ev_chunk[ch], 0));
             }
-            run_slab_xy_forward(p, real, k.zslab, nullptr, k.nzl, nyl, k.st, k.d_peer_yslab, r, nzp, z0, n);
+            if (!copy_x) {
+                run_slab_xy_forward(p, real, k.zslab, nullptr, k.nzl, nyl, k.st, k.d_peer_yslab, r, nzp, z0, n);
+                continue;
+            }
+            float2* send = k.recv;
+            run_slab_xy_forward(p, real, k.zslab, send, k.nzl, nyl, k.st, nullptr, r, nzp, z0, n);
+            FC_CUDA(cudaEventRecord(k.ev_chunk[8 + ch], k.st));
+            FC_CUDA(cudaStreamWaitEvent(k.s_x, k.ev_chunk[8 + ch], 0));
+            const size_t rowblk = (size_t)nyl * xcp;
+            for (int i = 1; i <= P; ++i) {   // start with the next rank so that the peers are hit evenly
+                const int q = (r + i) % P;
+                FC_CUDA(cudaMemcpyAsync(ranks[(size_t)q].yslab + ((size_t)r * nzp + z0) * rowblk,
+                                        send + ((size_t)q * nzp + z0) * rowblk, (size_t)n * rowblk * sizeof(float2),
+                                        cudaMemcpyDefault, k.s_x));
+            }
+        }
+        if (copy_x) {
+            FC_CUDA(cudaEventRecord(k.ev_x, k.s_x));
+            FC_CUDA(cudaStreamWaitEvent(k.st, k.ev_x, 0));
         }
         FC_CUDA(cudaEventRecord(k.ev_fwd, k.st));
         FC_CUDA(cudaEventRecord(k.ev_t[1], k.st));
@@ -255,11 +282,11 @@ SlabContext::~SlabContext()
         cudaFree(k.d_peer_yslab);
         cudaFree(k.d_peer_recv);
         k.stager.reset();
-        for (cudaEvent_t e : {k.ev_fwd, k.ev_z, k.ev_done, k.ev_psf, k.ev_d2h, k.ev_t[0], k.ev_t[1], k.ev_t[2], k.ev_t[3]})
+        for (cudaEvent_t e : {k.ev_fwd, k.ev_z, k.ev_done, k.ev_psf, k.ev_d2h, k.ev_x, k.ev_t[0], k.ev_t[1], k.ev_t[2], k.ev_t[3]})
             if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : k.ev_chunk)
             if (e) cudaEventDestroy(e);
-        for (cudaStream_t s : {k.st, k.s_psf, k.s_h2d, k.s_d2h})
+        for (cudaStream_t s : {k.st, k.s_psf, k.s_h2d, k.s_d2h, k.s_x})
             if (s) cudaStreamDestroy(s);
     }
     if (prev >= 0) cudaSetDevice(prev);
@@ -317,13 +344,13 @@ std::shared_ptr<SlabContext> build_context(const int* imDim, const int* devs, in
         k.ny_here = std::min(c.nyl, imDim[1] - r * c.nyl);
         FC_CUDA(cudaSetDevice(k.dev));
         k.plan = get_plan(k.dev, imDim[0], imDim[1], imDim[2], false);
-        for (cudaStream_t* s : {&k.st, &k.s_psf, &k.s_h2d, &k.s_d2h})
+        for (cudaStream_t* s : {&k.st, &k.s_psf, &k.s_h2d, &k.s_d2h, &k.s_x})
             FC_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
         for (float2** b : {&k.zslab, &k.recv, &k.yslab, &k.H}) {
             FC_CUDA(cudaMalloc(b, spec_bytes));
             FC_CUDA(cudaMemset(*b, 0, spec_bytes));   // ragged slabs leave the pad rows / planes of a block unwritten
         }
-        for (cudaEvent_t* e : {&k.ev_fwd, &k.ev_z, &k.ev_done, &k.ev_psf, &k.ev_d2h})
+        for (cudaEvent_t* e : {&k.ev_fwd, &k.ev_z, &k.ev_done, &k.ev_psf, &k.ev_d2h, &k.ev_x})
             FC_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         k.stager.reset(new HostStager());
         for (cudaEvent_t& e : k.ev_t) FC_CUDA(cudaEventCreate(&e));
@@ -405,6 +432,10 @@ void slab_convolve(float* im, float* const* slabs, const int* imDim, const float
     if (cudaPointerGetAttributes(&attr, kernel) == cudaSuccess) k_dev = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
     else cudaGetLastError();
     static const bool cache_on = env_flag("FCB200_PSF_CACHE", true);
+    {
+        const char* e = std::getenv("FCB200_SLAB_EXCHANGE");   // 1 (default): copy engines for the forward exchange, 0: peer stores
+        call.copy_exchange = !(e && std::atoi(e) == 0);
+    }
     call.psf_cached = !k_dev && cache_on && c.h_valid && std::memcmp(c.h_dims, pdims, sizeof(pdims)) == 0 &&
                       c.h_taps.size() == ktaps && std::memcmp(c.h_taps.data(), kernel, ktaps * sizeof(float)) == 0;
     c.h_valid = false;
@@ -429,7 +460,11 @@ void slab_convolve(float* im, float* const* slabs, const int* imDim, const float
                 k.d_kernel = nk;
                 k.kernel_cap = ktaps;
             }
-            const size_t need = std::max<size_t>(1, psf_slab_scratch_elems(*k.plan, pdims));
+            if (std::memcmp(c.scratch_key, pdims, sizeof(pdims)) != 0) {
+                c.scratch_need = std::max<size_t>(1, psf_slab_scratch_elems(*k.plan, pdims));
+                std::memcpy(c.scratch_key, pdims, sizeof(pdims));
+            }
+            const size_t need = c.scratch_need;
             if (need > k.scratch_cap) {
                 float2* ns = nullptr;
                 FC_CUDA(cudaMalloc(&ns, need * sizeof(float2)));

@@ -84,6 +84,34 @@ def test_slab_matches_single_device(fc, dev, imDim, kDim, world, kind):
     check(got, want)
 
 
+@pytest.mark.parametrize("exchange", ["0", "1"])
+def test_both_forward_exchanges(fc, dev, monkeypatch, exchange):
+    """FCB200_SLAB_EXCHANGE=1 (default): the y pass writes the exchange layout locally and the copy engines move the
+    blocks, chunk by chunk; =0: the y pass stores straight into the peers' buffers.  Same result either way."""
+    import torch
+    monkeypatch.setenv("FCB200_SLAB_EXCHANGE", exchange)
+    imDim, kDim, world = (128, 96, 160), (7, 5, 9), 4          # 40 planes per rank: the copy exchange runs in 4 chunks
+    devs = device_list(fc, world)
+    rng = np.random.default_rng(33)
+    im = (rng.random(int(np.prod(imDim)), dtype=np.float32) * 1000).astype(np.float32)
+    k = gaussian_psf(kDim).reshape(-1)
+    want = im.copy()
+    fc.convolution3DfftCUDAInPlace(want, imDim, k, kDim, dev)
+    nzp, _, planes = fc.slab_partition(imDim, world)
+    plane = imDim[0] * imDim[1]
+    slabs = [torch.from_numpy(im[r * nzp * plane:(r * nzp + planes[r]) * plane]).to(f"cuda:{devs[r]}") for r in range(world)]
+    d_k = torch.from_numpy(k).to(f"cuda:{devs[0]}")
+    for _ in range(2):
+        for r in range(world):
+            slabs[r].copy_(torch.from_numpy(im[r * nzp * plane:(r * nzp + planes[r]) * plane]))
+        torch.cuda.synchronize()
+        fc.convolve_slab_device(slabs, imDim, d_k, kDim, devs)
+    check(np.concatenate([s.cpu().numpy() for s in slabs]), want)
+    t = torch.from_numpy(im.copy()).pin_memory()
+    fc.convolve_slab(t, imDim, k, kDim, devs)
+    check(t.numpy(), want)
+
+
 def test_slab_psf_cache_and_new_psf(fc, dev):
     """a second call with the same host PSF may reuse the PSF-spectrum slabs; a different PSF must not"""
     imDim, world = (96, 64, 48), 2
