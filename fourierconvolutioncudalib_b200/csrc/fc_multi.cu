@@ -55,7 +55,8 @@ struct SlabRank {
     int dev = 0, rank = 0;
     int nzl = 0, ny_here = 0;
     std::shared_ptr<ConvPlan> plan;   // tables only; the slab-sized buffers live here
-    cudaStream_t st = nullptr, s_psf = nullptr, s_h2d = nullptr, s_d2h = nullptr, s_x = nullptr;   // s_x: exchange copies
+    cudaStream_t st = nullptr, s_psf = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_x[4] = {nullptr, nullptr, nullptr, nullptr};   // exchange copies (several copy engines at once)
     float* real = nullptr;            // host-pointer calls: this rank's z slab
     float2 *zslab = nullptr, *recv = nullptr, *yslab = nullptr, *H = nullptr, *scratch = nullptr;
     size_t scratch_cap = 0;
@@ -66,7 +67,8 @@ struct SlabRank {
     cudaEvent_t ev_fwd = nullptr, ev_z = nullptr, ev_done = nullptr, ev_psf = nullptr;
     cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_chunk[16] = {};
-    cudaEvent_t ev_d2h = nullptr, ev_x = nullptr;
+    cudaEvent_t ev_d2h = nullptr;
+    cudaEvent_t ev_x[4] = {nullptr, nullptr, nullptr, nullptr};
     std::unique_ptr<HostStager> stager;   // pageable host volumes (per rank: emulated ranks share a plan)
     bool timed = false;
 };
@@ -144,8 +146,16 @@ void SlabContext::run_call(int r)
     // into the receive buffer, which is idle until the fused z pass of the peers) and the copy engines move block q to
     // rank q in one contiguous transfer per chunk of planes, while the next chunk is being transformed.
     const bool copy_x = c.copy_exchange && P > 1;
+    static const int xchunks = [] {
+        const char* e = std::getenv("FCB200_SLAB_XCHUNKS");
+        return std::max(1, std::min(8, e ? std::atoi(e) : 4));
+    }();
+    static const int nxs = [] {   // exchange streams (measured on 8 GPUs, config 5: 1 stream 11.3 ms, 4 streams 11.6 ms)
+        const char* e = std::getenv("FCB200_SLAB_XSTREAMS");
+        return std::max(1, std::min(4, e ? std::atoi(e) : 1));
+    }();
     const int nch = c.im ? (int)std::max<long long>(1, std::min<long long>(8, std::min<long long>(k.nzl, (long long)(slab_bytes >> 25))))
-                         : (copy_x ? (int)std::max(1, std::min(4, k.nzl / 8)) : 1);
+                         : (copy_x ? (int)std::max(1, std::min(xchunks, k.nzl / 8)) : 1);
     const int per = (k.nzl + nch - 1) / nch;
     auto z0_of = [&](int ch) { return std::min(k.nzl, ch * per); };
 
@@ -180,18 +190,20 @@ void SlabContext::run_call(int r)
             float2* send = k.recv;
             run_slab_xy_forward(p, real, k.zslab, send, k.nzl, nyl, k.st, nullptr, r, nzp, z0, n);
             FC_CUDA(cudaEventRecord(k.ev_chunk[8 + ch], k.st));
-            FC_CUDA(cudaStreamWaitEvent(k.s_x, k.ev_chunk[8 + ch], 0));
+            for (int xs = 0; xs < nxs; ++xs) FC_CUDA(cudaStreamWaitEvent(k.s_x[xs], k.ev_chunk[8 + ch], 0));
             const size_t rowblk = (size_t)nyl * xcp;
             for (int i = 1; i <= P; ++i) {   // start with the next rank so that the peers are hit evenly
                 const int q = (r + i) % P;
                 FC_CUDA(cudaMemcpyAsync(ranks[(size_t)q].yslab + ((size_t)r * nzp + z0) * rowblk,
                                         send + ((size_t)q * nzp + z0) * rowblk, (size_t)n * rowblk * sizeof(float2),
-                                        cudaMemcpyDefault, k.s_x));
+                                        cudaMemcpyDefault, k.s_x[i % nxs]));
             }
         }
         if (copy_x) {
-            FC_CUDA(cudaEventRecord(k.ev_x, k.s_x));
-            FC_CUDA(cudaStreamWaitEvent(k.st, k.ev_x, 0));
+            for (int xs = 0; xs < nxs; ++xs) {
+                FC_CUDA(cudaEventRecord(k.ev_x[xs], k.s_x[xs]));
+                FC_CUDA(cudaStreamWaitEvent(k.st, k.ev_x[xs], 0));
+            }
         }
         FC_CUDA(cudaEventRecord(k.ev_fwd, k.st));
         FC_CUDA(cudaEventRecord(k.ev_t[1], k.st));
@@ -282,11 +294,12 @@ SlabContext::~SlabContext()
         cudaFree(k.d_peer_yslab);
         cudaFree(k.d_peer_recv);
         k.stager.reset();
-        for (cudaEvent_t e : {k.ev_fwd, k.ev_z, k.ev_done, k.ev_psf, k.ev_d2h, k.ev_x, k.ev_t[0], k.ev_t[1], k.ev_t[2], k.ev_t[3]})
+        for (cudaEvent_t e : {k.ev_fwd, k.ev_z, k.ev_done, k.ev_psf, k.ev_d2h, k.ev_x[0], k.ev_x[1], k.ev_x[2], k.ev_x[3], k.ev_t[0],
+                              k.ev_t[1], k.ev_t[2], k.ev_t[3]})
             if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : k.ev_chunk)
             if (e) cudaEventDestroy(e);
-        for (cudaStream_t s : {k.st, k.s_psf, k.s_h2d, k.s_d2h, k.s_x})
+        for (cudaStream_t s : {k.st, k.s_psf, k.s_h2d, k.s_d2h, k.s_x[0], k.s_x[1], k.s_x[2], k.s_x[3]})
             if (s) cudaStreamDestroy(s);
     }
     if (prev >= 0) cudaSetDevice(prev);
@@ -344,13 +357,13 @@ std::shared_ptr<SlabContext> build_context(const int* imDim, const int* devs, in
         k.ny_here = std::min(c.nyl, imDim[1] - r * c.nyl);
         FC_CUDA(cudaSetDevice(k.dev));
         k.plan = get_plan(k.dev, imDim[0], imDim[1], imDim[2], false);
-        for (cudaStream_t* s : {&k.st, &k.s_psf, &k.s_h2d, &k.s_d2h, &k.s_x})
+        for (cudaStream_t* s : {&k.st, &k.s_psf, &k.s_h2d, &k.s_d2h, &k.s_x[0], &k.s_x[1], &k.s_x[2], &k.s_x[3]})
             FC_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
         for (float2** b : {&k.zslab, &k.recv, &k.yslab, &k.H}) {
             FC_CUDA(cudaMalloc(b, spec_bytes));
             FC_CUDA(cudaMemset(*b, 0, spec_bytes));   // ragged slabs leave the pad rows / planes of a block unwritten
         }
-        for (cudaEvent_t* e : {&k.ev_fwd, &k.ev_z, &k.ev_done, &k.ev_psf, &k.ev_d2h, &k.ev_x})
+        for (cudaEvent_t* e : {&k.ev_fwd, &k.ev_z, &k.ev_done, &k.ev_psf, &k.ev_d2h, &k.ev_x[0], &k.ev_x[1], &k.ev_x[2], &k.ev_x[3]})
             FC_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         k.stager.reset(new HostStager());
         for (cudaEvent_t& e : k.ev_t) FC_CUDA(cudaEventCreate(&e));
