@@ -192,7 +192,11 @@ void SlabContext::run_call(int r)
             FC_CUDA(cudaEventRecord(k.ev_chunk[8 + ch], k.st));
             for (int xs = 0; xs < nxs; ++xs) FC_CUDA(cudaStreamWaitEvent(k.s_x[xs], k.ev_chunk[8 + ch], 0));
             const size_t rowblk = (size_t)nyl * xcp;
-            for (int i = 1; i <= P; ++i) {   // start with the next rank so that the peers are hit evenly
+            static const int debug_nocopy = [] {   // timing experiments only (results are wrong): skip the exchange copies
+                const char* e = std::getenv("FCB200_SLAB_DEBUG_NOCOPY");
+                return e ? std::atoi(e) : 0;
+            }();
+            for (int i = 1; i <= P && !debug_nocopy; ++i) {   // start with the next rank so that the peers are hit evenly
                 const int q = (r + i) % P;
                 FC_CUDA(cudaMemcpyAsync(ranks[(size_t)q].yslab + ((size_t)r * nzp + z0) * rowblk,
                                         send + ((size_t)q * nzp + z0) * rowblk, (size_t)n * rowblk * sizeof(float2),

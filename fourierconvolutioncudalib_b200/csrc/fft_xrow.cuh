@@ -48,7 +48,10 @@ __global__ void __launch_bounds__(THREADS) xrow_fwd_kernel(XArgs a)
     pdl_wait();
     __syncthreads();
 
-    const long long rowA = ((long long)blockIdx.x * RP + grp) * 2;
+    // grid-stride over blocks of RP row pairs (persistent launch: the twiddle table is built once per CTA)
+    const long long nblk = (a.nrows + 2 * RP - 1) / (2 * RP);
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const long long rowA = (blk * RP + grp) * 2;
     const bool hasA = rowA < a.nrows, hasB = rowA + 1 < a.nrows;
     const float2* srcA = reinterpret_cast<const float2*>(a.in_real + rowA * g.nx);
     const float2* srcB = reinterpret_cast<const float2*>(a.in_real + (rowA + 1) * g.nx);
@@ -123,6 +126,8 @@ __global__ void __launch_bounds__(THREADS) xrow_fwd_kernel(XArgs a)
             for (int k = M + 1; k < g.xcp; ++k) dstB[k] = make_float2(0.f, 0.f);
         }
     }
+    __syncwarp();   // the exchange buffer is free for the next block of rows
+    }
 }
 
 template <int R, int THREADS>
@@ -145,11 +150,13 @@ __global__ void __launch_bounds__(THREADS) xrow_inv_kernel(XArgs a)
     pdl_wait();
     __syncthreads();
 
-    const long long rowA = ((long long)blockIdx.x * RP + grp) * 2;
+    const bool odd = lane & 1;
+    const long long nblk = (a.nrows + 2 * RP - 1) / (2 * RP);
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {   // persistent, see xrow_fwd_kernel
+    const long long rowA = (blk * RP + grp) * 2;
     const bool hasA = rowA < a.nrows, hasB = rowA + 1 < a.nrows;
     const float2* srcA = a.spec + rowA * g.xcp;
     const float2* srcB = a.spec + (rowA + 1) * g.xcp;
-    const bool odd = lane & 1;
 
     // pair-planar rows -> (re, im) of bin k = j + R*m for both rows
     p2 r[R], i[R];
@@ -211,6 +218,8 @@ __global__ void __launch_bounds__(THREADS) xrow_inv_kernel(XArgs a)
     for (int m = 0; m < R; ++m) {
         if (hasA) dstA[j + R * m] = make_float2(r[m].x, i[m].x);
         if (hasB) dstB[j + R * m] = make_float2(r[m].y, i[m].y);
+    }
+    __syncwarp();   // the exchange buffer is free for the next block of rows
     }
 }
 

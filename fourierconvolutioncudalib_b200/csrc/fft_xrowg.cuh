@@ -84,11 +84,15 @@ __global__ void __launch_bounds__(THREADS) xrowg_fwd_kernel(XArgs a)
     pdl_wait();
     __syncthreads();
 
-    const long long rowA = ((long long)blockIdx.x * RP + grp) * 2;
+    // Persistent: the CTA walks over blocks of RP row pairs, so the twiddle tables above (M + M/R0 roots, as much
+    // data as half a row pair for nx = 2048) are built once per CTA instead of once per 2*RP rows.
+    float4* x = xch + (size_t)grp * G::PADM;
+    const long long nblk = (a.nrows + 2 * RP - 1) / (2 * RP);
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const long long rowA = (blk * RP + grp) * 2;
     const bool hasA = rowA < a.nrows, hasB = rowA + 1 < a.nrows;
     const float2* srcA = reinterpret_cast<const float2*>(a.in_real + rowA * g.nx);
     const float2* srcB = reinterpret_cast<const float2*>(a.in_real + (rowA + 1) * g.nx);
-    float4* x = xch + (size_t)grp * G::PADM;
 
     p2 r[R0], i[R0];
     // ---- stage 1 (radix R0, stride S1 = TG): thread tl owns butterfly j = tl
@@ -208,6 +212,8 @@ __global__ void __launch_bounds__(THREADS) xrowg_fwd_kernel(XArgs a)
             for (int k = M + 1; k < g.xcp; ++k) dstB[k] = make_float2(0.f, 0.f);
         }
     }
+    group_sync<TG>(grp);   // the exchange buffer is free for the next block of rows
+    }
 }
 
 template <int R0, int R1, int R2, int THREADS>
@@ -243,12 +249,14 @@ __global__ void __launch_bounds__(THREADS) xrowg_inv_kernel(XArgs a)
     pdl_wait();
     __syncthreads();
 
-    const long long rowA = ((long long)blockIdx.x * RP + grp) * 2;
+    const bool odd = lane & 1;
+    float4* x = xch + (size_t)grp * G::PADM;
+    const long long nblk = (a.nrows + 2 * RP - 1) / (2 * RP);
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {   // persistent, see xrowg_fwd_kernel
+    const long long rowA = (blk * RP + grp) * 2;
     const bool hasA = rowA < a.nrows, hasB = rowA + 1 < a.nrows;
     const float2* srcA = a.spec + rowA * g.xcp;
     const float2* srcB = a.spec + (rowA + 1) * g.xcp;
-    const bool odd = lane & 1;
-    float4* x = xch + (size_t)grp * G::PADM;
 
     // ---- pair-planar rows -> natural-order (re, im) copy of X in the exchange buffer
 #pragma unroll
@@ -353,6 +361,8 @@ __global__ void __launch_bounds__(THREADS) xrowg_inv_kernel(XArgs a)
             if (hasA) dstA[tl + m * S1] = make_float2(r[m].x, i[m].x);
             if (hasB) dstB[tl + m * S1] = make_float2(r[m].y, i[m].y);
         }
+    }
+    group_sync<TG>(grp);   // the exchange buffer is free for the next block of rows
     }
 }
 
