@@ -9,6 +9,22 @@ namespace fcb200 {
 
 namespace {
 
+// FCB200_XTILE_PERSIST=n > 0: the tiled x kernels are launched with n x (resident CTAs) CTAs that walk over the tiles
+// (twiddle table loaded once per CTA); 0 (default): one tile of 16 rows per CTA.  Measured: no clear gain, unlike the
+// row-wise kernels (560: x forward 0.238 -> 0.248 ms, 420: 0.220 -> 0.212, 270: 0.063 -> 0.060) -- these kernels are
+// bound by their two-tile structure, not by the table loads.
+template <typename K>
+long long x_tile_grid(K kernel, int threads, size_t smem, long long tiles, bool psf)
+{
+    static const int persist = env_int("FCB200_XTILE_PERSIST", 0);
+    if (persist <= 0 || psf) return tiles;
+    int per_sm = 1, dev = 0, sms = 148;
+    FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return std::min<long long>(tiles, (long long)sms * std::max(1, per_sm) * persist);
+}
+
 template <class P, int THREADS>
 bool try_x_fwd(const XArgs& a, bool psf, long long tiles, cudaStream_t st)
 {
@@ -18,7 +34,7 @@ bool try_x_fwd(const XArgs& a, bool psf, long long tiles, cudaStream_t st)
     auto go = [&](auto kernel) {
         if (smem > 48 * 1024)
             FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        launch_pdl(a.pdl != 0, kernel, dim3((unsigned)tiles), dim3(THREADS), smem, st, a);
+        launch_pdl(a.pdl != 0, kernel, dim3((unsigned)x_tile_grid(kernel, THREADS, smem, tiles, psf)), dim3(THREADS), smem, st, a);
         FC_CUDA_KERNEL();
     };
     if (psf) go(x_fwd_kernel<1, P, THREADS>);
@@ -34,7 +50,7 @@ bool try_x_inv(const XArgs& a, long long tiles, cudaStream_t st)
     if (smem > (size_t)kMaxDynSmem) return false;
     auto kernel = x_inv_kernel<P, THREADS>;
     if (smem > 48 * 1024) FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(a.pdl != 0, kernel, dim3((unsigned)tiles), dim3(THREADS), smem, st, a);
+    launch_pdl(a.pdl != 0, kernel, dim3((unsigned)x_tile_grid(kernel, THREADS, smem, tiles, false)), dim3(THREADS), smem, st, a);
     FC_CUDA_KERNEL();
     return true;
 }

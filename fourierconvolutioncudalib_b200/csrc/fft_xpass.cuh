@@ -255,12 +255,15 @@ __global__ void __launch_bounds__(THREADS, (IsBigPlan<PL>::value ? 1 : (THREADS 
     const int t = threadIdx.x;
     const int cp = t % TXP, w = t / TXP, W = blockDim.x / TXP;
     const int lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
-    const long long row0 = (long long)blockIdx.x * NROWS;
 
     pdl_launch_dependents();
     load_twiddles(sm.tw, a.P.tw, L);
     pdl_wait();
 
+    // grid-stride over tiles of NROWS rows (persistent launch: the twiddle table is loaded once per CTA)
+    const long long ntile = (a.nrows + NROWS - 1) / NROWS;
+    for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const long long row0 = tile * NROWS;
     // ---- global rows -> row tile (one warp per row at a time, lanes along x)
     for (int lrow = warp; lrow < NROWS; lrow += nwarps) {
         const long long li = row0 + lrow;
@@ -401,6 +404,8 @@ __global__ void __launch_bounds__(THREADS, (IsBigPlan<PL>::value ? 1 : (THREADS 
             if (k < g.xcp) dst[k] = (lane & 1) ? make_float2(oy, v.y) : make_float2(v.x, ox);
         }
     }
+    __syncthreads();   // the tiles are free for the next rows
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -423,12 +428,14 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
     const int t = threadIdx.x;
     const int cp = t % TXP, w = t / TXP, W = blockDim.x / TXP;
     const int lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
-    const long long row0 = (long long)blockIdx.x * NROWS;
 
     pdl_launch_dependents();
     load_twiddles(sm.tw, a.P.tw, L);
     pdl_wait();
 
+    const long long ntile = (a.nrows + NROWS - 1) / NROWS;
+    for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {   // persistent, see x_fwd_kernel
+    const long long row0 = tile * NROWS;
     // ---- spectrum rows (pair-planar) -> row tile (interleaved); loads are issued XLB at a time
     for (int lrow = warp; lrow < NROWS; lrow += nwarps) {
         const long long grow = row0 + lrow;
@@ -547,6 +554,8 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
             float2* dst = reinterpret_cast<float2*>(a.out_real + grow * g.nx);
             for (int pos = lane; pos < L; pos += 32) dst[pos] = src[pos];
         }
+    }
+    __syncthreads();   // the tiles are free for the next rows
     }
 }
 
