@@ -116,14 +116,16 @@ static bool try_xrowg(const XArgs& a, bool inverse, cudaStream_t st)
     if (grid == 0) return true;
     if (grid > 0x7fffffffLL) return false;
     const size_t smem = (size_t)(G::TW1 + G::TW2 + RP * G::PADM) * sizeof(float4);
-    // persistent for the long rows (M >= 512: the twiddle tables are as large as the rows of a CTA): as many CTAs as fit,
+    // persistent for rows of 384 voxels and more (M >= 192; nx = 2048: the twiddle tables are as large as the rows of a CTA;
+    // 384^3: x passes 0.106 / 0.099 -> 0.099 / 0.096 ms; no effect at M = 128): as many CTAs as fit,
     // each walking over blocks of RP row pairs.  FCB200_XROWG_PERSIST=0: one block of rows per CTA.
     static const int persist = env_int("FCB200_XROWG_PERSIST", 1);
+    static const int persist_min_m = env_int("FCB200_XROWG_PERSIST_MINM", 192);
     auto go = [&](auto kernel) {
         if (smem > 48 * 1024)
             FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long launch = grid;
-        if (persist && G::M >= 512) {
+        if (persist && G::M >= persist_min_m) {
             int per_sm = 1, dev = 0, sms = 148;
             FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
             cudaGetDevice(&dev);
