@@ -146,6 +146,8 @@ static bool try_xrowg_all(const XArgs& a, bool inverse, cudaStream_t st)
     if (x384 == 64 && try_xrowg<24, 8, 1, 64>(a, inverse, st)) return true;
     if (x384 == 256 && try_xrowg<24, 8, 1, 256>(a, inverse, st)) return true;
     if (x384 != 0 && try_xrowg<24, 8, 1, 128>(a, inverse, st)) return true;   // nx = 384
+    // nx = 256: CTA sizes 32 / 128 / 256 and persistent launches were measured (256^3: x passes 0.045 / 0.033 ms with every
+    // variant, profiles/r02_notes.md): the pass is L2-resident and launch-bound, 64 threads stay
     return try_xrowg<16, 8, 1, 64>(a, inverse, st) ||      // nx = 256
            try_xrowg<16, 4, 8, 128>(a, inverse, st) ||     // nx = 1024 (x-axis planning style)
            try_xrowg<8, 8, 8, 128>(a, inverse, st) ||
