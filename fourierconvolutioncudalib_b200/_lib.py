@@ -28,7 +28,7 @@ EXT_SYMBOLS = (
     "fcb200_padded_extents", "fcb200_convolve_padded", "fcb200_convolve_padded_device_async",
     "fcb200_convolve_batch_padded",
     "fcb200_convolve_slab", "fcb200_convolve_slab_device", "fcb200_slab_last_timing", "fcb200_slab_devices",
-    "fcb200_convolve_batch_multi", "fcb200_psf_window_planes",
+    "fcb200_convolve_batch_multi", "fcb200_psf_window_planes", "fcb200_plan_rader",
 )
 
 
@@ -106,6 +106,7 @@ def load():
         "fcb200_slab_devices": (i, [ip, i, ip, i]),
         "fcb200_convolve_batch_multi": (None, [vp, i, ip, vp, ip, ip, i, ip]),
         "fcb200_psf_window_planes": (i, [ip, ip, i]),
+        "fcb200_plan_rader": (i, [i, ip, ip, ip, fp, fp]),
         "fcb200_release": (None, []),
         "fcb200_launch_count": (ctypes.c_longlong, []),
         "fcb200_profile_enable": (None, [i]),

@@ -244,6 +244,19 @@ def plan_tables(L, style=0):
     return rev, pos, tw[0::2] + 1j * tw[1::2]
 
 
+def plan_rader(p):
+    """extension (fcb200_plan_rader): Rader tables of the prime p, or None when p - 1 is not smooth enough"""
+    n = int(p) - 1
+    rad = (ctypes.c_int * 8)()
+    perm, iperm = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    bf, bi = np.zeros(2 * n, np.float32), np.zeros(2 * n, np.float32)
+    ip = ctypes.POINTER(ctypes.c_int)
+    ns = _load().fcb200_plan_rader(int(p), rad, perm.ctypes.data_as(ip), iperm.ctypes.data_as(ip), _f(bf), _f(bi))
+    if ns == 0:
+        return None
+    return {"radices": list(rad[:ns]), "perm": perm, "iperm": iperm, "bf": bf[0::2] + 1j * bf[1::2], "bi": bi[0::2] + 1j * bi[1::2]}
+
+
 def spectrum_pitch(nx):
     return _load().fcb200_spectrum_pitch(int(nx))
 

@@ -882,6 +882,21 @@ void fcb200_plan_tables_style(int L, int style, int* rev, int* pos, float* tw)
     });
 }
 
+int fcb200_plan_rader(int p, int* radices, int* perm, int* iperm, float* bf, float* bi)
+{
+    return guarded([&] {
+        RaderTables r;
+        if (!build_rader(p, r)) return 0;
+        if (radices)
+            for (size_t i = 0; i < r.radix.size(); ++i) radices[i] = r.radix[i];
+        if (perm) std::memcpy(perm, r.perm.data(), sizeof(int) * r.n);
+        if (iperm) std::memcpy(iperm, r.iperm.data(), sizeof(int) * r.n);
+        if (bf) std::memcpy(bf, r.bf.data(), sizeof(float2) * r.n);
+        if (bi) std::memcpy(bi, r.bi.data(), sizeof(float2) * r.n);
+        return (int)r.radix.size();
+    });
+}
+
 int fcb200_spectrum_pitch(int nx) { return make_geometry(nx, 1, 1).xcp; }
 
 long long fcb200_psf_active_rows(const int* imDim, const int* kernelDim, int* rows, long long cap)

@@ -23,6 +23,17 @@ struct AxisPlanDev {
     const float2* tw;         // L roots: exp(-2*pi*i*t/L), computed in double
     const int* rev;           // rev[p]  = frequency held at position p after the forward transform
     const int* pos;           // pos[k]  = position that holds frequency k (inverse permutation)
+    // Rader stage for the LAST radix when it is a large prime p (fft_engine.cuh: stage_rader): the length-p DFT of a
+    // contiguous block becomes a cyclic convolution of length n = p - 1, done with an n-point FFT of smooth radices.
+    int rader_p;              // 0: none
+    int rader_n;              // p - 1
+    int rader_ns;             // stages of the n-point transform (all register radices)
+    int rader_radix[8];
+    const float2* rader_tw;   // n roots exp(-2*pi*i*t/n)
+    const int* rader_perm;    // perm[m]  = g^m mod p,    m = 0 .. n-1
+    const int* rader_iperm;   // iperm[q] = g^(-q) mod p, q = 0 .. n-1
+    const float2* rader_bf;   // spectrum of b[t] = exp(-2*pi*i*g^(-t)/p), / n, in POSITION order of the n-point DIF
+    const float2* rader_bi;   // the same for the inverse (conjugate roots)
 };
 
 // Geometry of one convolution problem as the kernels see it.

@@ -235,6 +235,101 @@ struct PassTimer {
     }
 };
 
+bool build_rader(int p, RaderTables& r)
+{
+    r = RaderTables();
+    if (p < 3) return false;
+    const int n = p - 1;
+    bool gen = false;
+    std::vector<int> radix = factorize(n, &gen, 0);
+    for (int R : radix)
+        if (!(R == 2 || R == 3 || R == 4 || R == 5 || R == 6 || R == 7 || R == 8 || R == 9 || R == 10 || R == 11 || R == 12 ||
+              R == 13 || R == 15 || R == 16))
+            return false;
+    if (gen || radix.size() > 8) return false;
+    // smallest primitive root g of p
+    auto powmod = [&](long long b, long long e) {
+        long long x = 1 % p;
+        b %= p;
+        while (e > 0) {
+            if (e & 1) x = x * b % p;
+            b = b * b % p;
+            e >>= 1;
+        }
+        return x;
+    };
+    std::vector<int> prime_factors;
+    {
+        int m = n;
+        for (int q = 2; (long long)q * q <= m; ++q)
+            if (m % q == 0) {
+                prime_factors.push_back(q);
+                while (m % q == 0) m /= q;
+            }
+        if (m > 1) prime_factors.push_back(m);
+    }
+    int g = 0;
+    for (int c = 2; c < p && !g; ++c) {
+        bool ok = true;
+        for (int q : prime_factors) ok = ok && powmod(c, n / q) != 1;
+        if (ok) g = c;
+    }
+    if (!g) return false;
+    r.p = p;
+    r.n = n;
+    r.radix = radix;
+    r.perm.resize(n);
+    r.iperm.resize(n);
+    const long long ginv = powmod(g, p - 2);
+    long long x = 1, y = 1;
+    for (int m = 0; m < n; ++m) {
+        r.perm[m] = (int)x;
+        r.iperm[m] = (int)y;
+        x = x * g % p;
+        y = y * ginv % p;
+    }
+    std::vector<int> rev, pos;
+    build_tables(n, radix, rev, pos, r.tw);
+    // spectra of b[t] = exp(-+2*pi*i*g^(-t)/p), divided by n, stored by POSITION of the n-point DIF (position q holds
+    // frequency rev[q]); direct O(n^2) sums in double (n < 5000)
+    const double two_pi = 6.283185307179586476925286766559;
+    std::vector<double> br(n), bim(n);
+    for (int t = 0; t < n; ++t) {
+        const double ang = two_pi * (double)r.iperm[t] / (double)p;
+        br[t] = std::cos(ang);
+        bim[t] = -std::sin(ang);   // forward: exp(-i ang)
+    }
+    r.bf.resize(n);
+    r.bi.resize(n);
+    for (int q = 0; q < n; ++q) {
+        const int f = rev[q];
+        double fr = 0, fi = 0, ir = 0, ii = 0;
+        for (int t = 0; t < n; ++t) {
+            const long long e = ((long long)f * t) % n;
+            const double a = two_pi * (double)e / (double)n, c = std::cos(a), sn = -std::sin(a);   // exp(-2 pi i f t / n)
+            // forward b = (br, bim); inverse b = conj = (br, -bim)
+            fr += br[t] * c - bim[t] * sn;
+            fi += br[t] * sn + bim[t] * c;
+            ir += br[t] * c + bim[t] * sn;
+            ii += br[t] * sn - bim[t] * c;
+        }
+        r.bf[q] = make_float2((float)(fr / n), (float)(fi / n));
+        r.bi[q] = make_float2((float)(ir / n), (float)(ii / n));
+    }
+    return true;
+}
+
+static int rader_min_prime()
+{
+    static const int v = [] {
+        // measured (profiles/r02_odd_sizes.jsonl): 79 / 109 are faster as direct sums (158x158x218: 0.50 against 1.05 ms),
+        // 271 is faster with Rader (542x542x296: 9.6 -> 6.7 ms); 0 turns Rader off
+        const char* e = std::getenv("FCB200_RADER_MIN");
+        return e ? std::atoi(e) : 160;
+    }();
+    return v;
+}
+
 static void make_axis(AxisPlan& a, int L, int style)
 {
     a.L = L;
@@ -258,6 +353,33 @@ static void make_axis(AxisPlan& a, int L, int style)
     a.dev.tw = a.d_tw;
     a.dev.rev = a.d_rev;
     a.dev.pos = a.d_pos;
+    // Rader for a large prime as the LAST radix (the planner puts the primes last, ascending)
+    a.dev.rader_p = a.dev.rader_n = a.dev.rader_ns = 0;
+    const int plast = a.radix.empty() ? 1 : a.radix.back();
+    RaderTables rt;
+    if (a.generic && plast > 23 && plast >= rader_min_prime() && rader_min_prime() > 0 && build_rader(plast, rt)) {
+        const int n = rt.n;
+        FC_CUDA(cudaMalloc(&a.d_rtw, sizeof(float2) * n));
+        FC_CUDA(cudaMalloc(&a.d_rbf, sizeof(float2) * n));
+        FC_CUDA(cudaMalloc(&a.d_rbi, sizeof(float2) * n));
+        FC_CUDA(cudaMalloc(&a.d_rperm, sizeof(int) * n));
+        FC_CUDA(cudaMalloc(&a.d_riperm, sizeof(int) * n));
+        FC_CUDA(cudaMemcpy(a.d_rtw, rt.tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+        FC_CUDA(cudaMemcpy(a.d_rbf, rt.bf.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+        FC_CUDA(cudaMemcpy(a.d_rbi, rt.bi.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+        FC_CUDA(cudaMemcpy(a.d_rperm, rt.perm.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        FC_CUDA(cudaMemcpy(a.d_riperm, rt.iperm.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        a.dev.rader_p = plast;
+        a.dev.rader_n = n;
+        a.dev.rader_ns = (int)rt.radix.size();
+        for (int i = 0; i < 8; ++i) a.dev.rader_radix[i] = i < a.dev.rader_ns ? rt.radix[(size_t)i] : 1;
+        a.dev.rader_tw = a.d_rtw;
+        a.dev.rader_perm = a.d_rperm;
+        a.dev.rader_iperm = a.d_riperm;
+        a.dev.rader_bf = a.d_rbf;
+        a.dev.rader_bi = a.d_rbi;
+        a.dev.big = 1;   // the Rader stage (and the radices 11 / 13 of its n-point transform) live in the "big" kernel builds
+    }
 }
 
 static void free_axis(AxisPlan& a)
@@ -265,6 +387,13 @@ static void free_axis(AxisPlan& a)
     cudaFree(a.d_tw);
     cudaFree(a.d_rev);
     cudaFree(a.d_pos);
+    cudaFree(a.d_rtw);
+    cudaFree(a.d_rbf);
+    cudaFree(a.d_rbi);
+    cudaFree(a.d_rperm);
+    cudaFree(a.d_riperm);
+    a.d_rtw = a.d_rbf = a.d_rbi = nullptr;
+    a.d_rperm = a.d_riperm = nullptr;
     a.d_tw = nullptr;
     a.d_rev = a.d_pos = nullptr;
 }

@@ -28,8 +28,21 @@ struct AxisPlan {
     float2* d_tw = nullptr;
     int* d_rev = nullptr;
     int* d_pos = nullptr;
+    // Rader tables (device), when the last radix is a large prime whose p - 1 is smooth
+    float2 *d_rtw = nullptr, *d_rbf = nullptr, *d_rbi = nullptr;
+    int *d_rperm = nullptr, *d_riperm = nullptr;
     AxisPlanDev dev{};
 };
+
+// Host-side Rader tables for a prime p (pure host code; unit-tested on the CPU through fcb200_plan_rader).
+struct RaderTables {
+    int p = 0, n = 0;
+    std::vector<int> radix;            // stages of the n-point transform (register radices only)
+    std::vector<int> perm, iperm;      // g^m mod p, g^(-q) mod p
+    std::vector<float2> tw, bf, bi;    // n roots; spectra of b (forward / inverse), / n, in position order of the n-point DIF
+};
+// false when p - 1 needs a prime factor above 16 other than 13 / 11 (then the direct sum stays)
+bool build_rader(int p, RaderTables& r);
 
 struct ConvPlan {
     int device = 0;

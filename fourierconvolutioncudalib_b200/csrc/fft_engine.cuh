@@ -33,6 +33,16 @@ __device__ __forceinline__ void load_twiddles(float4* tw_s, const float2* tw_g, 
     }
 }
 
+// roots of the n-point transform of a Rader stage (after the L main roots in shared memory)
+__device__ __forceinline__ void load_rader_twiddles(float4* rtw_s, const AxisPlanDev& P)
+{
+    if (P.rader_p)
+        for (int i = threadIdx.x; i < P.rader_n; i += blockDim.x) {
+            const float2 t = __ldg(P.rader_tw + i);
+            rtw_s[i] = make_float4(t.x, t.x, t.y, t.y);
+        }
+}
+
 template <int R>
 __device__ __forceinline__ void load_pairs(const float4* __restrict__ buf, int idx0, int step, p2* r, p2* i)
 {
@@ -185,12 +195,124 @@ __device__ __forceinline__ bool is_fast_radix(int R)
            R == 15 || R == 16 || R == 11 || R == 13 || R == 17 || R == 19 || R == 23;
 }
 
+// ---- Rader stage: a prime radix p as a cyclic convolution of length n = p - 1 ------------------------------------
+// Only for the LAST radix (S = 1: pure DFTs of contiguous blocks of p positions, no stage twiddles), forward or inverse.
+//   X[0] = sum_n x[n],   X[g^-q] = x[0] + (a (*) b)[q],   a[m] = x[g^m],   b[t] = w_p^(+-g^-t)
+// Per block beta of the tile: gather a into the OTHER tile buffer (positions beta*p+1 .. beta*p+n), n-point DIF there
+// (position order), multiply by the precomputed spectrum of b (stored in position order, 1/n folded in; x[0] is added to
+// the DC term so that it reaches every output, and x[0] + A[0] is X[0]), n-point DIT back, scatter c[q] to position
+// g^-q of the original buffer.  Result in `cur` again: in place as far as the engine is concerned.
+// Cost: two n-point FFTs and three passes over the tile instead of (p-1)^2 / 2 multiply-adds per block.
+template <bool INV>
+__device__ __forceinline__ void rader_substage(int R, float4* buf, const float4* tw, int n, int Li, int cp, int w, int W,
+                                               int txp)
+{
+    switch (R) {
+        case 2: stage_smem<2, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 3: stage_smem<3, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 4: stage_smem<4, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 5: stage_smem<5, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 6: stage_smem<6, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 7: stage_smem<7, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 8: stage_smem<8, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 9: stage_smem<9, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 10: stage_smem<10, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 11: stage_smem<11, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 12: stage_smem<12, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 13: stage_smem<13, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 15: stage_smem<15, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        case 16: stage_smem<16, INV>(buf, tw, n, Li, cp, w, W, txp); break;
+        default: break;   // the host only builds Rader plans whose n has these radices
+    }
+}
+
+template <bool INV>
+__device__ __forceinline__ void stage_rader(const AxisPlanDev& P, float4* __restrict__ cur, float4* __restrict__ oth,
+                                            const float4* __restrict__ rtw, int cp, int w, int W, int txp, bool active)
+{
+    const int p = P.rader_p, n = P.rader_n, nsub = P.L / p;
+    const float invn = 1.0f / (float)n;
+    // 1. gather a[m] = x[g^m] into the other buffer
+    if (active)
+        for (int idx = w; idx < nsub * n; idx += W) {
+            const int beta = __float2int_rz(((float)idx + 0.5f) * invn), m = idx - beta * n;
+            oth[(beta * p + 1 + m) * txp + cp] = cur[(beta * p + __ldg(P.rader_perm + m)) * txp + cp];
+        }
+    __syncthreads();
+    // 2. n-point forward transforms (DIF, in place, digit-reversed positions)
+    {
+        int Li = n;
+        for (int s = 0; s < P.rader_ns; ++s) {
+            const int R = P.rader_radix[s];
+            // the butterflies of all blocks are dealt over the workers as ONE sequence (block beta starts where beta-1 ended)
+            if (active)
+                for (int beta = 0, nb = n / R; beta < nsub; ++beta)
+                    rader_substage<false>(R, oth + (size_t)(beta * p + 1) * txp, rtw, n, Li, cp,
+                                          ((w - (beta * nb) % W) + W) % W, W, txp);
+            Li /= R;
+            __syncthreads();
+        }
+    }
+    // 3. multiply by the spectrum of b; DC: X[0] = x[0] + A[0], and x[0] joins the DC term of the product
+    if (active) {
+        const float2* B = INV ? P.rader_bi : P.rader_bf;
+        for (int idx = w; idx < nsub * n; idx += W) {
+            const int beta = __float2int_rz(((float)idx + 0.5f) * invn), pp = idx - beta * n;
+            float4* slot = oth + (size_t)(beta * p + 1 + pp) * txp + cp;
+            const float4 v = *slot;
+            const float2 b = __ldg(B + pp);
+            float4 o;
+            o.x = v.x * b.x - v.z * b.y;
+            o.y = v.y * b.x - v.w * b.y;
+            o.z = v.x * b.y + v.z * b.x;
+            o.w = v.y * b.y + v.w * b.x;
+            if (pp == 0) {
+                float4* x0p = cur + (size_t)(beta * p) * txp + cp;
+                const float4 x0 = *x0p;
+                *x0p = make_float4(x0.x + v.x, x0.y + v.y, x0.z + v.z, x0.w + v.w);
+                o.x += x0.x;
+                o.y += x0.y;
+                o.z += x0.z;
+                o.w += x0.w;
+            }
+            *slot = o;
+        }
+    }
+    __syncthreads();
+    // 4. n-point inverse transforms (DIT from the digit-reversed positions, unnormalised: 1/n is folded into B)
+    {
+        int Li = 1;
+        for (int s = P.rader_ns - 1; s >= 0; --s) {
+            const int R = P.rader_radix[s];
+            Li *= R;
+            if (active)
+                for (int beta = 0, nb = n / R; beta < nsub; ++beta)
+                    rader_substage<true>(R, oth + (size_t)(beta * p + 1) * txp, rtw, n, Li, cp,
+                                         ((w - (beta * nb) % W) + W) % W, W, txp);
+            __syncthreads();
+        }
+    }
+    // 5. scatter X[g^-q] = c[q]
+    if (active)
+        for (int idx = w; idx < nsub * n; idx += W) {
+            const int beta = __float2int_rz(((float)idx + 0.5f) * invn), q = idx - beta * n;
+            cur[(beta * p + __ldg(P.rader_iperm + q)) * txp + cp] = oth[(beta * p + 1 + q) * txp + cp];
+        }
+}
+
 // BIG: the kernel is compiled with the register butterflies of the primes 11..23 (they cost registers, so plans
 // without such a radix run kernels compiled without them; AxisPlanDev::big tells the launcher which)
 template <bool INV, bool BIG = false>
 __device__ __forceinline__ void stage_dispatch(int R, float4*& cur, float4*& oth, const float4* tw, int L, int Li,
-                                               int cp, int w, int W, int txp, bool active)
+                                               int cp, int w, int W, int txp, bool active,
+                                               const AxisPlanDev* P = nullptr, const float4* rtw = nullptr)
 {
+    if constexpr (BIG) {
+        if (P != nullptr && P->rader_p == R && Li == R && rtw != nullptr) {   // last radix, S = 1 (uniform branch)
+            stage_rader<INV>(*P, cur, oth, rtw, cp, w, W, txp, active);
+            return;   // result is in `cur`: no buffer swap
+        }
+    }
     if (active) {
         if constexpr (BIG) {
             switch (R) {
@@ -232,7 +354,7 @@ __device__ __forceinline__ void stage_dispatch(int R, float4*& cur, float4*& oth
 //   inverse: the mirror image (scaled by L, like cuFFT's unnormalised inverse)
 template <bool INV, bool BIG = false>
 __device__ __forceinline__ float4* engine_run(const AxisPlanDev& P, float4* A, float4* B, const float4* tw, int cp,
-                                              int w, int W, int txp, bool active)
+                                              int w, int W, int txp, bool active, const float4* rtw = nullptr)
 {
     float4* cur = A;
     float4* oth = B;
@@ -240,7 +362,7 @@ __device__ __forceinline__ float4* engine_run(const AxisPlanDev& P, float4* A, f
         int Li = P.L;
         for (int s = 0; s < P.ns; ++s) {
             const int R = P.radix[s];
-            stage_dispatch<false, BIG>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active);
+            stage_dispatch<false, BIG>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active, &P, rtw);
             Li /= R;
             __syncthreads();
         }
@@ -249,7 +371,7 @@ __device__ __forceinline__ float4* engine_run(const AxisPlanDev& P, float4* A, f
         for (int s = P.ns - 1; s >= 0; --s) {
             const int R = P.radix[s];
             Li *= R;
-            stage_dispatch<true, BIG>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active);
+            stage_dispatch<true, BIG>(R, cur, oth, tw, P.L, Li, cp, w, W, txp, active, &P, rtw);
             __syncthreads();
         }
     }

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
     float4* A = smem;
     float4* B = a.P.generic ? (A + (size_t)L * txp) : nullptr;
     float4* tw_s = A + (size_t)L * txp * (a.P.generic ? 2 : 1);
+    float4* rtw_s = tw_s + L;   // roots of the Rader n-point transform (BIG builds, plans with a Rader stage)
 
     const int t = threadIdx.x;
     const int cp = t % txp, w = t / txp, W = blockDim.x / txp;
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
     };
 
     load_twiddles(tw_s, a.P.tw, L);
+    if constexpr (BIG) load_rader_twiddles(rtw_s, a.P);
 
     if (active) {
         for (int r = w; r < L; r += W) {
@@ -65,9 +67,9 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
 
     float4* cur;
     if (MODE == 1) {
-        cur = engine_run<true, BIG>(a.P, A, B, tw_s, cp, w, W, txp, active);
+        cur = engine_run<true, BIG>(a.P, A, B, tw_s, cp, w, W, txp, active, rtw_s);
     } else {
-        cur = engine_run<false, BIG>(a.P, A, B, tw_s, cp, w, W, txp, active);
+        cur = engine_run<false, BIG>(a.P, A, B, tw_s, cp, w, W, txp, active, rtw_s);
     }
 
     if (MODE == 2) {
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
         }
         __syncthreads();
         float4* oth = (cur == A) ? B : A;
-        cur = engine_run<true, BIG>(a.P, cur, oth, tw_s, cp, w, W, txp, active);
+        cur = engine_run<true, BIG>(a.P, cur, oth, tw_s, cp, w, W, txp, active, rtw_s);
     }
 
     if (active) {
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
 size_t x_smem_bytes(const Geometry& g, const AxisPlanDev& P, int txp)
 {
     const size_t rowt = 2 * (size_t)txp * (size_t)x_row_pitch(P.L, g.xcp) * sizeof(float2);
-    return (size_t)P.L * txp * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)P.L * sizeof(float4) + rowt;
+    return (size_t)P.L * txp * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)(P.L + P.rader_n) * sizeof(float4) + rowt;
 }
 
 int x_pick_txp(const Geometry& g, const AxisPlanDev& P)
@@ -124,7 +126,7 @@ bool x_pass_supported(const Geometry& g, const AxisPlanDev& P) { return x_pick_t
 int col_pick_txp(const AxisPlanDev& P)
 {
     for (int txp = 8; txp >= 1; txp >>= 1) {
-        size_t need = (size_t)P.L * txp * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)P.L * sizeof(float4);
+        size_t need = (size_t)P.L * txp * sizeof(float4) * (P.generic ? 2 : 1) + (size_t)(P.L + P.rader_n) * sizeof(float4);
         if (need <= (size_t)kMaxDynSmem) return txp;
     }
     return 0;
@@ -191,7 +193,7 @@ void launch_x_inv(const XArgs& a, cudaStream_t st)
 
 void launch_col(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
-    const size_t smem = (size_t)a.P.L * a.txp * sizeof(float4) * (a.P.generic ? 2 : 1) + (size_t)a.P.L * sizeof(float4);
+    const size_t smem = (size_t)a.P.L * a.txp * sizeof(float4) * (a.P.generic ? 2 : 1) + (size_t)(a.P.L + a.P.rader_n) * sizeof(float4);
     const long long grid = ngroups * a.tilesPerGroup;
     if (grid == 0) return;
     if (grid > 0x7fffffffLL) throw std::runtime_error("fcb200: volume too large for one launch");

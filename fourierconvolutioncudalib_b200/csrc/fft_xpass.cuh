@@ -155,6 +155,7 @@ struct XSmem {
     float4* A;
     float4* B;
     float4* tw;
+    float4* rtw;    // roots of the Rader n-point transform (run-time plans with a Rader stage)
     float2* rowt;
     int P;
 };
@@ -166,7 +167,8 @@ __device__ __forceinline__ XSmem x_carve(float4* smem, const Geometry& g, const 
     s.A = smem;
     s.B = pl.generic ? (s.A + (size_t)L * txp) : nullptr;
     s.tw = s.A + (size_t)L * txp * (pl.generic ? 2 : 1);
-    s.rowt = reinterpret_cast<float2*>(s.tw + L);
+    s.rtw = s.tw + L;
+    s.rowt = reinterpret_cast<float2*>(s.rtw + pl.rader_n);
     return s;
 }
 
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(THREADS, (IsBigPlan<PL>::value ? 1 : (THREADS 
 
     pdl_launch_dependents();
     load_twiddles(sm.tw, a.P.tw, L);
+    if constexpr (IsBigPlan<PL>::value) load_rader_twiddles(sm.rtw, a.P);
     pdl_wait();
 
     // grid-stride over tiles of NROWS rows (persistent launch: the twiddle table is loaded once per CTA)
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, (IsBigPlan<PL>::value ? 1 : (THREADS 
             sm.A[pos * TXP + cp] = make_float4(u.x, v.x, u.y, v.y);
         }
         __syncthreads();
-        cur = engine_run<false, IsBigPlan<PL>::value>(a.P, sm.A, sm.B, sm.tw, cp, w, W, TXP, true);
+        cur = engine_run<false, IsBigPlan<PL>::value>(a.P, sm.A, sm.B, sm.tw, cp, w, W, TXP, true, sm.rtw);
     }
 
     // ---- engine tile -> row tile (interleaved spectrum rows, natural kx); even nx: split the packed
@@ -431,6 +434,7 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
 
     pdl_launch_dependents();
     load_twiddles(sm.tw, a.P.tw, L);
+    if constexpr (IsBigPlan<PL>::value) load_rader_twiddles(sm.rtw, a.P);
     pdl_wait();
 
     const long long ntile = (a.nrows + NROWS - 1) / NROWS;
@@ -519,7 +523,7 @@ __global__ void __launch_bounds__(THREADS) x_inv_kernel(XArgs a)
         __syncthreads();
         sstage_rows_last_inv<PL::R0, PL::L, NW>(sm.A, rowt, P, sm.tw, cp, w);
     } else {
-        float4* cur = engine_run<true, IsBigPlan<PL>::value>(a.P, sm.A, sm.B, sm.tw, cp, w, W, TXP, true);
+        float4* cur = engine_run<true, IsBigPlan<PL>::value>(a.P, sm.A, sm.B, sm.tw, cp, w, W, TXP, true, sm.rtw);
         for (int pos = w; pos < L; pos += W) {
             const float4 v = cur[pos * TXP + cp];
             rowt[(2 * cp) * P + pos] = make_float2(v.x, v.z);

@@ -54,6 +54,12 @@ FUNCTION_PREFIX void fcb200_plan_tables(int L, int* rev, int* pos, float* tw);
  * (8,8,4) instead of (16,16);  2 = x axis: L = 1024 is planned as (16,8,8) for the row-wise kernel. */
 FUNCTION_PREFIX int fcb200_plan_radices_style(int L, int style, int* radices, int* generic);
 FUNCTION_PREFIX void fcb200_plan_tables_style(int L, int style, int* rev, int* pos, float* tw);
+/* Rader tables of a prime p (pure host code): the length-p DFT as a cyclic convolution of length n = p - 1 done with an
+ * n-point transform of register radices.  Returns the number of stages of that transform (0: p - 1 is not smooth enough,
+ * the direct sum is used) and writes, when the pointers are not NULL: its radices (at most 8), perm[m] = g^m mod p,
+ * iperm[q] = g^(-q) mod p, and the spectra (n interleaved complex values each, divided by n, in the position order of the
+ * n-point decimation-in-frequency transform, see fcb200_plan_tables(n)) of b[t] = exp(-+2*pi*i*g^(-t)/p). */
+FUNCTION_PREFIX int fcb200_plan_rader(int p, int* radices, int* perm, int* iperm, float* bf, float* bi);
 /* Spectrum row pitch (complex elements) used for a volume whose fastest extent is nx. */
 FUNCTION_PREFIX int fcb200_spectrum_pitch(int nx);
 /* Bytes of device workspace a cached plan for imDim holds (spectrum + PSF spectrum + tables). */

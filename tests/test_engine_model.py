@@ -91,3 +91,40 @@ def test_c_planner_matches_model_exhaustively_up_to_1200(fc):
             assert len(r0) <= 5, (L, r0)
     rev, pos, _ = fc.plan_tables(270)
     assert sorted(rev.tolist()) == list(range(270)) and np.array_equal(pos[rev], np.arange(270))
+
+
+@pytest.mark.parametrize("p", [37, 53, 79, 109, 271, 281, 163, 61])
+def test_rader_tables_reproduce_the_dft(fc, p):
+    """numpy walk through the device Rader stage (fft_engine.cuh: stage_rader) with the tables the C planner builds:
+    gather a[m] = x[g^m], n-point DIF (position order), multiply by the stored spectrum of b (x[0] joins the DC term,
+    X[0] = x[0] + A[0]), unnormalised n-point inverse, scatter to g^-q -- must equal numpy's DFT, forward and inverse"""
+    r = fc.plan_rader(p)
+    assert r is not None, p
+    n = p - 1
+    assert int(np.prod(r["radices"])) == n
+    radices, generic = fc.plan_radices(n, 0)
+    assert radices == r["radices"] and not generic
+    rev, pos, _ = fc.plan_tables(n, 0)
+    assert sorted(r["perm"].tolist()) == list(range(1, p)) and sorted(r["iperm"].tolist()) == list(range(1, p))
+    assert all((int(a) * int(b)) % p == 1 for a, b in zip(r["perm"], r["iperm"]))
+    rng = np.random.default_rng(p)
+    x = rng.standard_normal(p) + 1j * rng.standard_normal(p)
+    for B, want in ((r["bf"], np.fft.fft(x)), (r["bi"], np.fft.ifft(x) * p)):
+        a = x[r["perm"]]
+        A = np.fft.fft(a)
+        Apos = A[rev]                       # position q holds frequency rev[q]
+        Cpos = Apos * B
+        X0 = x[0] + Apos[0]
+        Cpos[0] += x[0]
+        C = np.zeros(n, complex)
+        C[rev] = Cpos
+        c = np.fft.ifft(C) * n              # unnormalised inverse (1/n is folded into B)
+        X = np.zeros(p, complex)
+        X[0] = X0
+        X[r["iperm"]] = c
+        assert np.abs(X - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_rader_is_declined_when_p_minus_1_is_not_smooth(fc):
+    assert fc.plan_rader(173) is None       # 172 = 4 * 43
+    assert fc.plan_rader(47) is None        # 46 = 2 * 23: radix 23 is not among the n-point transform's radices

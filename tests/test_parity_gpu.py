@@ -48,6 +48,9 @@ CASES = [  # (imDim, kernelDim): cubic, non-cubic (placement quirk), odd, generi
     ((420, 448, 16), (7, 7, 5)),
     ((1024, 64, 16), (9, 5, 7)),          # row-wise x kernel, 3 stages
     ((2048, 16, 8), (5, 3, 3)),           # row-wise x kernel, (16,8,8)
+    ((158, 158, 24), (5, 5, 5)),          # Rader stages: x half-length 79, y = 2 * 79
+    ((542, 20, 218), (3, 3, 3)),          # x half-length 271 (270 = 2*15*9), fused z pass with 2 * 109 (108 = 12*9)
+    ((148, 74, 106), (5, 3, 3)),          # primes 37 / 53 below the Rader threshold: symmetric direct sum
 ]
 
 
