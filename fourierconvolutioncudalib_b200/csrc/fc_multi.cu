@@ -59,6 +59,8 @@ struct SlabRank {
     cudaStream_t s_x[4] = {nullptr, nullptr, nullptr, nullptr};   // exchange copies (several copy engines at once)
     float* real = nullptr;            // host-pointer calls: this rank's z slab
     float2 *zslab = nullptr, *recv = nullptr, *yslab = nullptr, *H = nullptr, *scratch = nullptr;
+    float2* send = nullptr;           // pull exchange: exchange-layout output of my y pass, read by the peers' fused z pass
+    float2** d_peer_send = nullptr;   // entry q: rank q's send buffer at MY block
     size_t scratch_cap = 0;
     float* d_kernel = nullptr;
     size_t kernel_cap = 0;
@@ -80,7 +82,7 @@ struct SlabCall {
     HostMem im_kind = HostMem::Device;
     bool psf_cached = false;
     int pdims[6] = {0, 0, 0, 0, 0, 0};
-    bool copy_exchange = false;   // forward exchange by copy engines (see run_call)
+    int exchange = 1;   // forward exchange: 0 peer stores from the y pass, 1 copy engines, 2 pulled by the fused z pass
 };
 
 struct SlabContext {
@@ -145,7 +147,8 @@ void SlabContext::run_call(int r)
     // 6.3 ms for 2.5 ms of local work.  With copy_exchange the y pass writes the exchange layout LOCALLY ([P][nzp][nyl][xcp],
     // into the receive buffer, which is idle until the fused z pass of the peers) and the copy engines move block q to
     // rank q in one contiguous transfer per chunk of planes, while the next chunk is being transformed.
-    const bool copy_x = c.copy_exchange && P > 1;
+    const bool pull_x = c.exchange == 2 && P > 1 && k.send != nullptr;
+    const bool copy_x = (c.exchange == 1 || (c.exchange == 2 && !pull_x)) && P > 1;
     static const int xchunks = [] {
         const char* e = std::getenv("FCB200_SLAB_XCHUNKS");
         return std::max(1, std::min(8, e ? std::atoi(e) : 4));
@@ -183,6 +186,10 @@ void SlabContext::run_call(int r)
                 FC_CUDA(cudaEventRecord(k.ev_chunk[ch], k.s_h2d));
                 FC_CUDA(cudaStreamWaitEvent(k.st, k.ev_chunk[ch], 0));
             }
+            if (pull_x) {   // the y pass only writes the exchange layout; the peers' fused z pass fetches it
+                run_slab_xy_forward(p, real, k.zslab, k.send, k.nzl, nyl, k.st, nullptr, r, nzp, z0, n);
+                continue;
+            }
             if (!copy_x) {
                 run_slab_xy_forward(p, real, k.zslab, nullptr, k.nzl, nyl, k.st, k.d_peer_yslab, r, nzp, z0, n);
                 continue;
@@ -218,7 +225,7 @@ void SlabContext::run_call(int r)
     phase(r, [&] {
         for (SlabRank& q : ranks) FC_CUDA(cudaStreamWaitEvent(k.st, q.ev_fwd, 0));
         if (!c.psf_cached) FC_CUDA(cudaStreamWaitEvent(k.st, k.ev_psf, 0));
-        run_slab_z_fused(p, k.yslab, k.H, nyl, k.st, k.d_peer_recv, r, nzp);
+        run_slab_z_fused(p, k.yslab, k.H, nyl, k.st, k.d_peer_recv, r, nzp, pull_x ? k.d_peer_send : nullptr);
         FC_CUDA(cudaEventRecord(k.ev_z, k.st));
         FC_CUDA(cudaEventRecord(k.ev_t[2], k.st));
     });
@@ -297,6 +304,8 @@ SlabContext::~SlabContext()
         cudaFree(k.d_kernel);
         cudaFree(k.d_peer_yslab);
         cudaFree(k.d_peer_recv);
+        cudaFree(k.send);
+        cudaFree(k.d_peer_send);
         k.stager.reset();
         for (cudaEvent_t e : {k.ev_fwd, k.ev_z, k.ev_done, k.ev_psf, k.ev_d2h, k.ev_x[0], k.ev_x[1], k.ev_x[2], k.ev_x[3], k.ev_t[0],
                               k.ev_t[1], k.ev_t[2], k.ev_t[3]})
@@ -450,8 +459,27 @@ void slab_convolve(float* im, float* const* slabs, const int* imDim, const float
     else cudaGetLastError();
     static const bool cache_on = env_flag("FCB200_PSF_CACHE", true);
     {
-        const char* e = std::getenv("FCB200_SLAB_EXCHANGE");   // 1 (default): copy engines for the forward exchange, 0: peer stores
-        call.copy_exchange = !(e && std::atoi(e) == 0);
+        // forward exchange: 1 (default) copy engines, 0 peer stores from the y pass, 2 pulled by the fused z pass
+        const char* e = std::getenv("FCB200_SLAB_EXCHANGE");
+        call.exchange = e ? std::atoi(e) : 1;
+        if (call.exchange == 2 && ndev > 1) {   // the pull form needs one more exchange-sized buffer per rank and the peer tables
+            std::vector<float2*> blocks((size_t)ndev);
+            const size_t spec_bytes = c.slab_spec_elems() * sizeof(float2);
+            for (SlabRank& k : c.ranks)
+                if (!k.send) {
+                    FC_CUDA(cudaSetDevice(k.dev));
+                    FC_CUDA(cudaMalloc(&k.send, spec_bytes));
+                    FC_CUDA(cudaMemset(k.send, 0, spec_bytes));
+                }
+            for (SlabRank& k : c.ranks)
+                if (!k.d_peer_send) {
+                    FC_CUDA(cudaSetDevice(k.dev));
+                    for (int q = 0; q < ndev; ++q)
+                        blocks[(size_t)q] = c.ranks[(size_t)q].send + (size_t)k.rank * c.nzp * c.nyl * c.xcp;
+                    FC_CUDA(cudaMalloc(&k.d_peer_send, sizeof(float2*) * ndev));
+                    FC_CUDA(cudaMemcpy(k.d_peer_send, blocks.data(), sizeof(float2*) * ndev, cudaMemcpyHostToDevice));
+                }
+        }
     }
     call.psf_cached = !k_dev && cache_on && c.h_valid && std::memcmp(c.h_dims, pdims, sizeof(pdims)) == 0 &&
                       c.h_taps.size() == ktaps && std::memcmp(c.h_taps.data(), kernel, ktaps * sizeof(float)) == 0;

@@ -16,10 +16,69 @@ namespace fcb200 {
 // ------------------------------------------------------------------------------------------------
 // pure host planning
 // ------------------------------------------------------------------------------------------------
+// FCB200_PLAN="z300=20.15,x280=20.14,...": radix sequence of one axis style (y, z, x) and length, for tuning runs.
+// Lengths without a compile-time kernel for the given sequence run on the run-time-radix kernels.
+static bool plan_override(int L, int style, std::vector<int>& out, bool& gen)
+{
+    const char* e = std::getenv("FCB200_PLAN");
+    if (!e) return false;
+    const char tag = style == 1 ? 'z' : (style == 2 ? 'x' : 'y');
+    std::string all(e);
+    size_t at = 0;
+    while (at < all.size()) {
+        size_t end = all.find(',', at);
+        if (end == std::string::npos) end = all.size();
+        const std::string item = all.substr(at, end - at);
+        at = end + 1;
+        const size_t eq = item.find('=');
+        if (item.size() < 3 || item[0] != tag || eq == std::string::npos || std::atoi(item.c_str() + 1) != L) continue;
+        std::vector<int> rad;
+        long long prod = 1;
+        size_t q = eq + 1;
+        while (q < item.size()) {
+            const int r = std::atoi(item.c_str() + q);
+            if (r < 2) break;
+            rad.push_back(r);
+            prod *= r;
+            q = item.find('.', q);
+            if (q == std::string::npos) break;
+            ++q;
+        }
+        if (prod != L || rad.empty() || (int)rad.size() > kMaxStages) continue;
+        static const int fast[] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 11, 13, 17, 19, 23, 14, 18, 20, 21, 25, 28};
+        gen = false;
+        for (int r : rad)
+            if (std::find(std::begin(fast), std::end(fast), r) == std::end(fast)) gen = true;
+        out = rad;
+        return true;
+    }
+    return false;
+}
+
 std::vector<int> factorize(int L, bool* generic, int style)
 {
     std::vector<int> out;
     bool gen = false;
+    if (plan_override(L, style, out, gen)) {
+        if (generic) *generic = gen;
+        return out;
+    }
+    // Two stages of FAT composite radices (fft_butterflies.cuh: Dft<14> .. Dft<28>, Cooley-Tukey inside the registers of one
+    // thread) for the extents of the caller-padded configurations whose prime-by-prime plans need three or four shared-memory
+    // round trips -- each measured against the plan it replaces (profiles/r02_plan_ab.jsonl; y passes / fused z pass):
+    //   L = 300 (4,3,5,5) -> (20,15): 0.101 -> 0.065 / 0.289 -> 0.215 ms    L = 420 (4,3,5,7) -> (20,21): 0.153 -> 0.102 / 0.318 -> 0.181 ms
+    //   L = 270 (2,15,9)  -> (18,15): 0.041 -> 0.027 / 0.064 -> 0.056 ms    L = 448 y only (8,8,7) -> (16,28): 0.109 -> 0.085 ms
+    //   L = 560 fused z only (16,5,7) -> (28,20): 0.205 -> 0.177 ms          x half-lengths 150 -> (10,15), 135 -> (9,15): -3..8 %
+    // (a radix-28 butterfly around the spectrum multiply loses: z 448 stays (8,8,7); the tiled x kernels lose with
+    // (20,14) / (16,14) / (14,15): 280, 224, 210 keep their primes.)
+    struct FatPlan { int L, styles, r0, r1; };   // styles: bit 0 y axis, bit 1 fused z axis, bit 2 x axis
+    static const FatPlan fat[] = {{300, 3, 20, 15}, {420, 3, 20, 21}, {270, 3, 18, 15}, {448, 1, 16, 28},
+                                  {560, 2, 28, 20}, {150, 4, 10, 15}, {135, 4, 9, 15}};
+    for (const FatPlan& f : fat)
+        if (f.L == L && ((f.styles >> style) & 1)) {
+            if (generic) *generic = false;
+            return {f.r0, f.r1};
+        }
     int n = L;
     // power-of-two part: fewest stages with radices <= 16, never a trailing radix 2 when avoidable
     int e = 0;
@@ -241,7 +300,7 @@ bool build_rader(int p, RaderTables& r)
     if (p < 3) return false;
     const int n = p - 1;
     bool gen = false;
-    std::vector<int> radix = factorize(n, &gen, 0);
+    std::vector<int> radix = factorize(n, &gen, 3);   // style 3: y-axis planning without the two-stage fat plans
     for (int R : radix)
         if (!(R == 2 || R == 3 || R == 4 || R == 5 || R == 6 || R == 7 || R == 8 || R == 9 || R == 10 || R == 11 || R == 12 ||
               R == 13 || R == 15 || R == 16))
@@ -349,7 +408,8 @@ static void make_axis(AxisPlan& a, int L, int style)
     a.dev.generic = a.generic ? 1 : 0;
     a.dev.big = 0;
     for (int r : a.radix)
-        if (r == 11 || r == 13 || r == 17 || r == 19 || r == 23) a.dev.big = 1;
+        if (r == 11 || r == 13 || r == 17 || r == 19 || r == 23 || r == 14 || r == 18 || r == 20 || r == 21 || r == 25 || r == 28)
+            a.dev.big = 1;   // butterflies that only the "big" builds of the run-time-radix kernels carry
     a.dev.tw = a.d_tw;
     a.dev.rev = a.d_rev;
     a.dev.pos = a.d_pos;
@@ -645,6 +705,7 @@ static ColArgs y_args(ConvPlan& p, float2* data)
     a.winPlanes = 0;
     a.splitPeers = nullptr;
     a.splitPeerOffset = 0;
+    a.splitInPeers = nullptr;
     return a;
 }
 
@@ -684,6 +745,7 @@ static ColArgs z_args(ConvPlan& p, float2* data)
     a.winPlanes = 0;
     a.splitPeers = nullptr;
     a.splitPeerOffset = 0;
+    a.splitInPeers = nullptr;
     return a;
 }
 
@@ -1150,7 +1212,7 @@ void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2
 }
 
 void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, cudaStream_t st,
-                      float2* const* peers, int rank, int nzl)
+                      float2* const* peers, int rank, int nzl, float2* const* in_peers)
 {
     check_slab(p, 1, nyl);
     ColArgs za = z_args(p, yslab);
@@ -1165,6 +1227,9 @@ void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, 
         za.splitRows = nzl;
         za.splitPeerOffset = (long long)rank * nzl * C;
         za.splitGroup = 0;
+        za.splitInPeers = in_peers;   // pull exchange: input planes straight from the ranks that hold them
+    } else if (in_peers) {
+        throw std::runtime_error("fcb200: the pull exchange needs the peer form of the fused z pass");
     }
     PassTimer t(kPassZFused, st);
     col_pass(za, 2, 1, st);

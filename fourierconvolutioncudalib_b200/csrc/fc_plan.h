@@ -182,8 +182,9 @@ void run_slab_xy_forward(ConvPlan& p, const float* d_real, float2* zslab, float2
                          cudaStream_t st, float2* const* peers, int rank, int nzp, int z0 = 0, int nz_run = -1);
 // fused z pass on the y-slab spectrum (in place) with the y-slab of the PSF spectrum
 // peers != nullptr: the last inverse stage stores each output plane straight into its owner's receive buffer
+// in_peers != nullptr (with peers): pull exchange -- input plane z is read from in_peers[z / nzl] + (z % nzl) * nyl * xcp
 void run_slab_z_fused(ConvPlan& p, float2* yslab, const float2* Hslab, int nyl, cudaStream_t st,
-                      float2* const* peers = nullptr, int rank = 0, int nzl = 0);
+                      float2* const* peers = nullptr, int rank = 0, int nzl = 0, float2* const* in_peers = nullptr);
 // y + x inverse; the y pass reads the exchange (receive) buffer directly
 void run_slab_yx_inverse(ConvPlan& p, const float2* recv, float2* zslab, float* d_real, int nzl, int nyl,
                          cudaStream_t st, int nzp, int z0 = 0, int nz_run = -1);

@@ -386,6 +386,14 @@ template <> struct Dft<9> : DftCT<3, 3> {};
 template <> struct Dft<10> : DftCT<2, 5> {};
 template <> struct Dft<12> : DftCT<4, 3> {};
 template <> struct Dft<15> : DftCT<3, 5> {};
+// fat radices of the two-stage plans (300 = 20 * 15, 420 = 20 * 21, 280 = 20 * 14 ...): one shared-memory round trip
+// instead of three for lengths with four small prime factors
+template <> struct Dft<14> : DftCT<2, 7> {};
+template <> struct Dft<18> : DftCT<2, 9> {};
+template <> struct Dft<20> : DftCT<4, 5> {};
+template <> struct Dft<21> : DftCT<3, 7> {};
+template <> struct Dft<25> : DftCT<5, 5> {};
+template <> struct Dft<28> : DftCT<4, 7> {};
 
 // ---- odd primes 11, 13, 17, 19, 23 in registers ----------------------------------------------------------------
 // The extents reference callers pad to by image + kernel - 1 are rarely 7-smooth (its own tests use 130 = 2*5*13,

@@ -279,8 +279,7 @@ __global__ void __launch_bounds__(MAXT, MINB) col_fast_kernel(ColArgs a)
 bool col_fast_supported(const AxisPlanDev& P)
 {
     if (P.generic || P.ns < 2) return false;
-    for (int s = 0; s < P.ns; ++s)   // the odd primes 11..23 run on the all-shared-memory kernel (fft_kernels.cu)
-        if (P.radix[s] == 11 || P.radix[s] == 13 || P.radix[s] == 17 || P.radix[s] == 19 || P.radix[s] == 23) return false;
+    if (P.big) return false;   // the odd primes 11..23 and the fat composite radices run on the all-shared-memory kernel (fft_kernels.cu)
     const size_t need = (size_t)P.L * 8 * sizeof(float4) + (size_t)P.L * sizeof(float4);
     return need <= (size_t)kMaxDynSmem;
 }

@@ -545,9 +545,11 @@ int sm_count_of_current_device()
     return cache[dev];
 }
 
-template <class P, int THREADS, int NBUF, int TXP>
+// MODES: which kernels get compiled for this configuration (1 = plain passes, 2 = fused z pass, 3 = both)
+template <class P, int THREADS, int NBUF, int TXP, int MODES = 3>
 bool run_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
+    if (mode == 2 ? !(MODES & 2) : !(MODES & 1)) return false;
     constexpr int L = P::L;
     if (a.split || a.splitPeers || a.rowMask || a.groupList || a.winSlot) return false;
     if (!encode_fn()) return false;
@@ -587,14 +589,17 @@ bool run_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
         launch_pdl(a.pdl != 0, kernel, dim3(grid), dim3(THREADS + 32), smem, st, nat, perm, hmap, ta);
         FC_CUDA_KERNEL();
     };
-    if (ngroups > 1) {
-        if (mode == 0) go(col_tma_kernel<0, P, THREADS, NBUF, TXP, true>);
-        else if (mode == 1) go(col_tma_kernel<1, P, THREADS, NBUF, TXP, true>);
-        else return false;   // the fused pass runs along z: one group
-    } else {
-        if (mode == 0) go(col_tma_kernel<0, P, THREADS, NBUF, TXP, false>);
-        else if (mode == 1) go(col_tma_kernel<1, P, THREADS, NBUF, TXP, false>);
-        else go(col_tma_kernel<2, P, THREADS, NBUF, TXP, false>);
+    if (mode == 2) {
+        if (ngroups > 1) return false;   // the fused pass runs along z: one group
+        if constexpr ((MODES & 2) != 0) go(col_tma_kernel<2, P, THREADS, NBUF, TXP, false>);
+    } else if constexpr ((MODES & 1) != 0) {
+        if (ngroups > 1) {
+            if (mode == 0) go(col_tma_kernel<0, P, THREADS, NBUF, TXP, true>);
+            else go(col_tma_kernel<1, P, THREADS, NBUF, TXP, true>);
+        } else {
+            if (mode == 0) go(col_tma_kernel<0, P, THREADS, NBUF, TXP, false>);
+            else go(col_tma_kernel<1, P, THREADS, NBUF, TXP, false>);
+        }
     }
     return true;
 }
@@ -686,14 +691,18 @@ bool launch_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t 
     if (plan_matches<P384>(a.P) && mode != 2) return run_col_tma<P384, 192, 3, 8>(a, mode, ngroups, st);
     if (plan_matches<P384>(a.P) && mode == 2) return run_col_tma<P384, 192, 2, 8>(a, mode, ngroups, st);
     if (plan_matches<P1024>(a.P) && mode != 2) return run_col_tma<P1024, 256, 3, 4>(a, mode, ngroups, st);
-    // 7-smooth extents of the caller-padded configurations: 560^2 y passes 0.164 -> 0.136 ms, 270^3 y passes 0.052 -> 0.041
-    // and fused z 0.090 -> 0.064 ms, L = 300 fused z 0.294 -> 0.288 ms
-    if (plan_matches<P560>(a.P) && mode != 2) return run_col_tma<P560, 320, 3, 8>(a, mode, ngroups, st);
-    if (plan_matches<P300>(a.P) && mode == 2) return run_col_tma<P300, 256, 2, 8>(a, mode, ngroups, st);
-    if (plan_matches<P270>(a.P) && mode != 2) return run_col_tma<P270, 256, 3, 8>(a, mode, ngroups, st);
-    if (plan_matches<P270>(a.P) && mode == 2) return run_col_tma<P270, 256, 2, 8>(a, mode, ngroups, st);
+    // 7-smooth extents of the caller-padded configurations: 560^2 y passes 0.164 -> 0.136 ms; the two-stage plans
+    // (300, 420, 270, 448 on the y axis) with one consumer per butterfly of the larger stage
+    if (plan_matches<P560>(a.P) && mode != 2) return run_col_tma<P560, 320, 3, 8, 1>(a, mode, ngroups, st);
+    if (plan_matches<P300>(a.P) && mode != 2) return run_col_tma<P300, 160, 3, 8, 1>(a, mode, ngroups, st);
+    if (plan_matches<P300>(a.P) && mode == 2) return run_col_tma<P300, 160, 2, 8, 2>(a, mode, ngroups, st);
+    if (plan_matches<P420>(a.P) && mode != 2) return run_col_tma<P420, 192, 3, 8, 1>(a, mode, ngroups, st);
+    if (plan_matches<P420>(a.P) && mode == 2) return run_col_tma<P420, 192, 2, 8, 2>(a, mode, ngroups, st);
+    if (plan_matches<P270>(a.P) && mode != 2) return run_col_tma<P270, 160, 3, 8, 1>(a, mode, ngroups, st);
+    if (plan_matches<P270>(a.P) && mode == 2) return run_col_tma<P270, 160, 2, 8, 2>(a, mode, ngroups, st);
+    if (plan_matches<P448y>(a.P) && mode != 2) return run_col_tma<P448y, 224, 3, 8, 1>(a, mode, ngroups, st);
     if (on >= 2) {
-        if (plan_matches<P448>(a.P) && mode != 2) return run_col_tma<P448, 512, 3, 8>(a, mode, ngroups, st);
+        if (plan_matches<P448>(a.P) && mode != 2) return run_col_tma<P448, 512, 3, 8, 1>(a, mode, ngroups, st);
         if (plan_matches<P1024>(a.P) && mode == 2) return run_col_tma<P1024, 128, 3, 2>(a, mode, ngroups, st);
     }
     return false;

@@ -192,7 +192,8 @@ __device__ __forceinline__ void stage_generic(const float4* __restrict__ src, fl
 __device__ __forceinline__ bool is_fast_radix(int R)
 {
     return R == 1 || R == 2 || R == 3 || R == 4 || R == 5 || R == 6 || R == 7 || R == 8 || R == 9 || R == 10 || R == 12 ||
-           R == 15 || R == 16 || R == 11 || R == 13 || R == 17 || R == 19 || R == 23;
+           R == 15 || R == 16 || R == 11 || R == 13 || R == 17 || R == 19 || R == 23 || R == 14 || R == 18 || R == 20 ||
+           R == 21 || R == 25 || R == 28;
 }
 
 // ---- Rader stage: a prime radix p as a cyclic convolution of length n = p - 1 ------------------------------------
@@ -321,6 +322,14 @@ __device__ __forceinline__ void stage_dispatch(int R, float4*& cur, float4*& oth
                 case 17: stage_smem<17, INV>(cur, tw, L, Li, cp, w, W, txp); return;
                 case 19: stage_smem<19, INV>(cur, tw, L, Li, cp, w, W, txp); return;
                 case 23: stage_smem<23, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                // fat composite radices of the two-stage plans (fft_butterflies.cuh), for the passes of such a plan that
+                // have no compile-time kernel
+                case 14: stage_smem<14, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                case 18: stage_smem<18, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                case 20: stage_smem<20, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                case 21: stage_smem<21, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                case 25: stage_smem<25, INV>(cur, tw, L, Li, cp, w, W, txp); return;
+                case 28: stage_smem<28, INV>(cur, tw, L, Li, cp, w, W, txp); return;
                 default: break;
             }
         }

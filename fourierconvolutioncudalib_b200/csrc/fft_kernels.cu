@@ -59,7 +59,11 @@ __global__ void __launch_bounds__(kColThreads) col_kernel(ColArgs a)
         for (int r = w; r < L; r += W) {
             const int p = (MODE == 1) ? __ldg(a.P.pos + r) : r;
             if (a.rowMask != nullptr && a.rowMask[r] == 0) A[p * txp + cp] = make_float4(0.f, 0.f, 0.f, 0.f);
-            else cp_async16(&A[p * txp + cp], (MODE == 1 && sbase) ? split_row(r) : base + (size_t)r * a.stride);
+            else if (MODE == 2 && a.splitInPeers != nullptr) {
+                const int blk = r / a.splitRows;
+                cp_async16(&A[p * txp + cp], a.splitInPeers[blk] + (size_t)group * a.splitGroup + col0 + 2 * cp +
+                                                 (size_t)(r - blk * a.splitRows) * a.stride);
+            } else cp_async16(&A[p * txp + cp], (MODE == 1 && sbase) ? split_row(r) : base + (size_t)r * a.stride);
         }
     }
     cp_async_wait_all();

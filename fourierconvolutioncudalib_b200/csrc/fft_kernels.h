@@ -58,6 +58,10 @@ struct ColArgs {
     // Mode 0 and mode 2 (fused z) write their output rows there; mode 1 reads from the plain split buffer.
     float2* const* splitPeers;
     long long splitPeerOffset;
+    // Pull form of the forward exchange (mode 2 only): INPUT row r of the transform axis is read from
+    //   splitInPeers[r / splitRows] + (r % splitRows) * stride + column
+    // i.e. the fused z pass fetches the planes straight out of the GPUs that produced them (128-byte loads over NVLink).
+    float2* const* splitInPeers;
     int pdl;                // launch with programmatic stream serialization (fc_common.h: launch_pdl)
 };
 

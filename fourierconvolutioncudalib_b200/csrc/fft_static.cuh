@@ -160,6 +160,37 @@ __device__ __forceinline__ void sfirst_fwd(const float2* __restrict__ base, size
     }
 }
 
+// the same with the rows addressed through a functor (split / peer layout on the INPUT side: pull exchange)
+template <int R, int L, int NW, int U, int TXP, class ROWS>
+__device__ __forceinline__ void sfirst_fwd_rows(const ROWS& rows, float4* __restrict__ sm, const float4* __restrict__ tw,
+                                                int cp, int w)
+{
+    constexpr int S = L / R;
+    constexpr int ITER = (S + NW * U - 1) / (NW * U);
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        float4 v[U][R];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = w + (it * U + u) * NW;
+            if ((S % (NW * U)) != 0 && j >= S) continue;
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[u][k] = sld(rows(j, k * S));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = w + (it * U + u) * NW;
+            if ((S % (NW * U)) != 0 && j >= S) continue;
+            p2 r[R], i[R];
+            ssplit<R>(v[u], r, i);
+            Dft<R>::run(r, i);
+#pragma unroll
+            for (int m = 1; m < R; ++m) cmul(r[m], i[m], tw[j * m]);
+            store_pairs<R>(sm, j * TXP + cp, S * TXP, r, i);
+        }
+    }
+}
+
 // ---- first inverse stage: global rows rev(b*R) + k*(L/R) -> smem positions b*R + k ----------------
 template <int R, int L, int NW, int U, int TXP = 8, class ROWS>
 __device__ __forceinline__ void sfirst_inv(const ROWS& rows, float4* __restrict__ sm, const int* __restrict__ rev, int cp,

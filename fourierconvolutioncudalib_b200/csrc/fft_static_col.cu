@@ -44,7 +44,16 @@ __global__ void __launch_bounds__(THREADS) col_static_kernel(ColArgs a, int tile
     // pass (which continues from digit-reversed positions) and the split / peer input layout.
     constexpr bool SWAP = (MODE == 1 && !SPLIT);
     if (MODE == 0 || MODE == 2 || SWAP) {
-        if (active) sfirst_fwd<P::R0, L, NW, U, MASKED, TXP, SWAP>(base, stride, sm, tw, cp, w, a.rowMask);
+        bool pulled = false;
+        if constexpr (SPLIT && MODE == 2) {
+            if (a.splitInPeers != nullptr) {   // pull exchange: the planes are read out of the GPUs that produced them
+                const RowsSplit irows{a.splitInPeers, nullptr, 0, (long long)group * a.splitGroup + col0 + 2 * cp, a.splitRows,
+                                      1.0f / (float)a.splitRows, stride};
+                if (active) sfirst_fwd_rows<P::R0, L, NW, U, TXP>(irows, sm, tw, cp, w);
+                pulled = true;
+            }
+        }
+        if (!pulled && active) sfirst_fwd<P::R0, L, NW, U, MASKED, TXP, SWAP>(base, stride, sm, tw, cp, w, a.rowMask);
         __syncthreads();
         if constexpr (P::ns >= 3) {
             if (active) sstage<P::R1, L, L / P::R0, NW, false, TXP>(sm, tw, cp, w);
@@ -564,17 +573,19 @@ bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream
         if (mode == 2) run_col<P256b, 128, 4, 8, 4>(a, mode, ngroups, st);
         else run_col<P256b, 128, 2, 8, 3>(a, mode, ngroups, st);
     }
-    else if (plan_matches<P560>(a.P)) run_col<P560, 320, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P560>(a.P) && mode != 2) run_col<P560, 320, 1, 8, 3>(a, mode, ngroups, st);   // y axis only
     else if (plan_matches<P448>(a.P)) {
         // fused pass: 256-thread CTAs, two PSF-spectrum batches in flight (420x420x448: 0.365 -> 0.219 ms,
         // profiles/r01_sweep_z448.jsonl); the plain passes keep 512 threads
         if (mode == 2) run_col<P448, 256, 2, 8, 4>(a, mode, ngroups, st);
         else run_col<P448, 512, 1, 8, 3>(a, mode, ngroups, st);
     }
-    // 420 and 300: other CTA sizes / load batches were measured and lost (profiles/r01_sweep_c420.jsonl, r01_sweep_z300.jsonl)
-    else if (plan_matches<P270>(a.P) && env_int("FCB200_S270", 1) != 0) run_col<P270, 256, 1, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P420>(a.P)) run_col<P420, 384, 1, 8>(a, mode, ngroups, st);
-    else if (plan_matches<P300>(a.P)) run_col<P300, 256, 1, 8>(a, mode, ngroups, st);
+    // two-stage plans with fat radices: one worker per butterfly of the larger stage (L / 15 = 20, L / 20 = 21, ...)
+    else if (plan_matches<P270>(a.P)) run_col<P270, 160, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P420>(a.P)) run_col<P420, 192, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P300>(a.P)) run_col<P300, 160, 1, 8>(a, mode, ngroups, st);
+    else if (plan_matches<P448y>(a.P) && mode != 2) run_col<P448y, 224, 1, 8, 3>(a, mode, ngroups, st);   // y axis only
+    else if (plan_matches<P560z>(a.P)) run_col<P560z, 224, 1, 8>(a, mode, ngroups, st);
     else if (plan_matches<P1024>(a.P)) {
         // plain passes: 64-byte row segments, two 256-thread CTAs per SM (1024x1024x256: 0.568 -> 0.529 ms)
         if (mode == 2) run_col<P1024, 512, 1, 8, 4>(a, mode, ngroups, st);

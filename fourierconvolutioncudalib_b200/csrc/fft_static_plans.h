@@ -54,17 +54,20 @@ typedef SPlan<256, 8, 8, 4> P256b;
 // planning style 2 (x axis): half-length 512 of nx = 1024 rows as (16,4,8)
 typedef SPlan<512, 16, 4, 8> P512x;
 // 7-smooth extents of caller-padded volumes (BASELINE configs 2-4 padded: 270, 300, 420, 448, 560) and
-// the half-lengths of their x transforms
-typedef SPlan<560, 16, 5, 7> P560;
-typedef SPlan<448, 8, 8, 7> P448;
-typedef SPlan<420, 4, 3, 5, 7> P420;
-typedef SPlan<300, 4, 3, 5, 5> P300;
-typedef SPlan<270, 2, 15, 9> P270;      // composite register radices (15 = 3*5, 9 = 3*3): three stages instead of five
+// the half-lengths of their x transforms.  Lengths with four small prime factors run as two stages of fat composite
+// radices (fc_plan.cu: factorize has the measurements).
+typedef SPlan<560, 16, 5, 7> P560;      // y axis
+typedef SPlan<560, 28, 20> P560z;       // fused z axis
+typedef SPlan<448, 8, 8, 7> P448;       // fused z axis
+typedef SPlan<448, 16, 28> P448y;       // y axis
+typedef SPlan<420, 20, 21> P420;
+typedef SPlan<300, 20, 15> P300;
+typedef SPlan<270, 18, 15> P270;
 typedef SPlan<280, 8, 5, 7> P280;
 typedef SPlan<224, 8, 4, 7> P224;
 typedef SPlan<210, 2, 3, 5, 7> P210;
-typedef SPlan<150, 2, 3, 5, 5> P150;
-typedef SPlan<135, 3, 3, 3, 5> P135;
+typedef SPlan<150, 10, 15> P150;
+typedef SPlan<135, 9, 15> P135;
 
 
 }  // namespace

@@ -179,8 +179,9 @@ bool launch_x_fwd_static(const XArgs& a, bool psf, cudaStream_t st)
            try_x_fwd<P256, 256>(a, psf, tiles, st) || try_x_fwd<P512, 256>(a, psf, tiles, st) ||
            try_x_fwd<P512x, 256>(a, psf, tiles, st) ||
            try_x_fwd<P1024, 512>(a, psf, tiles, st) || try_x_fwd<P280, 256>(a, psf, tiles, st) ||
+
            try_x_fwd<P224, 256>(a, psf, tiles, st) || try_x_fwd<P210, 256>(a, psf, tiles, st) ||
-           try_x_fwd<P150, 256>(a, psf, tiles, st) || try_x_fwd<P135, 256>(a, psf, tiles, st);
+           try_x_fwd<P150, 128>(a, psf, tiles, st) || try_x_fwd<P135, 128>(a, psf, tiles, st);
 }
 
 bool launch_x_inv_static(const XArgs& a, cudaStream_t st)
@@ -199,7 +200,8 @@ bool launch_x_inv_static(const XArgs& a, cudaStream_t st)
            (xt256() == 512 && try_x_inv<P256, 512>(a, tiles, st)) || try_x_inv<P256, 256>(a, tiles, st) ||
            try_x_inv<P512, 256>(a, tiles, st) || try_x_inv<P512x, 256>(a, tiles, st) || try_x_inv<P1024, 512>(a, tiles, st) ||
            try_x_inv<P280, 256>(a, tiles, st) || try_x_inv<P224, 256>(a, tiles, st) || try_x_inv<P210, 256>(a, tiles, st) ||
-           try_x_inv<P150, 256>(a, tiles, st) || try_x_inv<P135, 256>(a, tiles, st);
+
+           try_x_inv<P150, 128>(a, tiles, st) || try_x_inv<P135, 128>(a, tiles, st);
 }
 
 

@@ -44,14 +44,17 @@ FUNCTION_PREFIX void fcb200_convolve_padded_device_async(imageType* im_dev, cons
 /* Planner introspection (pure host code; callable without a GPU).
  * fcb200_plan_radices: writes the stage radices of a length-L transform (at most 16), returns the
  * number of stages; *generic is 1 when a prime factor above 23 is present (those stages run as direct sums between
- * two tile buffers; 2..16 and the primes 11, 13, 17, 19, 23 run as register butterflies). */
+ * two tile buffers; 2..16, the primes 11, 13, 17, 19, 23 and the composite radices 14, 18, 20, 21, 25, 28 of the
+ * two-stage plans run as register butterflies). */
 FUNCTION_PREFIX int fcb200_plan_radices(int L, int* radices, int* generic);
 /* rev[p]: frequency at position p after the forward transform; pos = inverse permutation;
  * tw: L interleaved (re,im) roots exp(-2*pi*i*t/L).  Any pointer may be NULL. */
 FUNCTION_PREFIX void fcb200_plan_tables(int L, int* rev, int* pos, float* tw);
 /* Same with an explicit planning style: 0 = fewest stages, radix 16 allowed (x and y axes);
  * 1 = z axis, whose fused forward-multiply-inverse kernel is register-bound: L = 256 is planned as
- * (8,8,4) instead of (16,16);  2 = x axis: L = 1024 is planned as (16,8,8) for the row-wise kernel. */
+ * (8,8,4) instead of (16,16);  2 = x axis: L = 1024 is planned as (16,8,8) for the row-wise kernel;
+ * 3 = like 0 without the measured two-stage plans (300 = 20 * 15, 420 = 20 * 21, ...): sub-transforms of the Rader stage.
+ * Styles 0, 1 and 2 each carry their own measured exceptions (csrc/fc_plan.cu: factorize). */
 FUNCTION_PREFIX int fcb200_plan_radices_style(int L, int style, int* radices, int* generic);
 FUNCTION_PREFIX void fcb200_plan_tables_style(int L, int style, int* rev, int* pos, float* tw);
 /* Rader tables of a prime p (pure host code): the length-p DFT as a cyclic convolution of length n = p - 1 done with an

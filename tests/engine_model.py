@@ -18,6 +18,11 @@ def factorize(L, style=0):
     """Same result as the C planner (fc_plan.cu: factorize): fewest stages for the power-of-two part
     with radices <= 16, then the odd 7-smooth part (composite radices 15 / 9 / 6 / 12 / 10 where factors pair up), then
     the remaining primes (generic stages)."""
+    # two stages of fat composite radices for the measured lengths (bit 0: y axis, bit 1: fused z axis, bit 2: x axis)
+    for fl, styles, r0, r1 in ((300, 3, 20, 15), (420, 3, 20, 21), (270, 3, 18, 15), (448, 1, 16, 28), (560, 2, 28, 20),
+                               (150, 4, 10, 15), (135, 4, 9, 15)):
+        if fl == L and (styles >> style) & 1:
+            return [r0, r1]
     out = []
     n = L
     e = 0

@@ -9,12 +9,17 @@ LENGTHS = [1024, 2048, 4096, 8192, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 19
 
 
 def test_composite_radix_plans():
-    want = {270: [2, 15, 9], 1125: [15, 15, 5], 2160: [16, 15, 9], 1080: [8, 15, 9], 810: [6, 15, 9], 540: [4, 15, 9],
+    want = {1125: [15, 15, 5], 2160: [16, 15, 9], 1080: [8, 15, 9], 810: [6, 15, 9], 540: [4, 15, 9],
             # up to four stages: one register stage per prime, as measured
-            300: [4, 3, 5, 5], 420: [4, 3, 5, 7], 150: [2, 3, 5, 5], 135: [3, 3, 3, 5], 210: [2, 3, 5, 7], 96: [8, 4, 3],
-            384: [16, 8, 3], 192: [8, 8, 3], 560: [16, 5, 7], 448: [8, 8, 7], 280: [8, 5, 7], 224: [8, 4, 7]}
+            150: [2, 3, 5, 5], 135: [3, 3, 3, 5], 210: [2, 3, 5, 7], 96: [8, 4, 3],
+            384: [16, 8, 3], 192: [8, 8, 3], 560: [16, 5, 7], 280: [8, 5, 7], 224: [8, 4, 7],
+            # two stages of fat composite radices where they were measured to win (y axis)
+            270: [18, 15], 300: [20, 15], 420: [20, 21], 448: [16, 28]}
     for L, r in want.items():
         assert em.factorize(L) == r, L
+    # fused z axis / x axis variants
+    assert em.factorize(448, 1) == [8, 8, 7] and em.factorize(560, 1) == [28, 20] and em.factorize(300, 1) == [20, 15]
+    assert em.factorize(150, 2) == [10, 15] and em.factorize(135, 2) == [9, 15] and em.factorize(300, 2) == [4, 3, 5, 5]
 
 
 @pytest.mark.parametrize("L", [2, 3, 4, 5, 7, 8, 12, 30, 35, 64, 66, 130, 158, 300, 270, 420, 1125, 90])
@@ -51,7 +56,8 @@ def test_c_planner_matches_model(fc, L, style):
     radices, generic = fc.plan_radices(L, style)
     assert radices == em.factorize(L, style)
     assert int(np.prod(radices)) == L
-    assert generic == any(r not in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 19, 23) for r in radices)
+    assert generic == any(r not in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 23, 25, 28)
+                          for r in radices)
     rev, pos, tw = fc.plan_tables(L, style)
     assert np.array_equal(rev, em.rev_positions(L, radices))
     assert np.array_equal(pos[rev], np.arange(L))
@@ -75,8 +81,8 @@ def test_psf_active_rows_match_oracle_placement(fc):
 def test_c_planner_matches_model_exhaustively_up_to_1200(fc):
     """every length a caller can pass on an axis (up to 1200, plus the padded config-5 extents): same radix
     sequence as the numpy model, product == L, stages bounded, digit reversal a permutation"""
-    fast = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 19, 23)     # register butterflies
-    smooth7 = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16)
+    fast = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 23, 25, 28)     # register butterflies
+    smooth7 = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 18, 20, 21, 25, 28)
     for L in list(range(1, 1201)) + [1125, 2048, 2160, 4096]:
         for style in (0, 1, 2):
             radices, generic = fc.plan_radices(L, style)
@@ -102,9 +108,9 @@ def test_rader_tables_reproduce_the_dft(fc, p):
     assert r is not None, p
     n = p - 1
     assert int(np.prod(r["radices"])) == n
-    radices, generic = fc.plan_radices(n, 0)
+    radices, generic = fc.plan_radices(n, 3)    # style 3: the sub-transform never uses the two-stage fat plans
     assert radices == r["radices"] and not generic
-    rev, pos, _ = fc.plan_tables(n, 0)
+    rev, pos, _ = fc.plan_tables(n, 3)
     assert sorted(r["perm"].tolist()) == list(range(1, p)) and sorted(r["iperm"].tolist()) == list(range(1, p))
     assert all((int(a) * int(b)) % p == 1 for a, b in zip(r["perm"], r["iperm"]))
     rng = np.random.default_rng(p)

@@ -16,6 +16,8 @@ SHAPES = [  # imDim = (d0 fastest, d1, d2)
     # composite register radices 6, 9, 10, 12, 15 (fft_butterflies.cuh: DftCT) on every axis
     (12, 6, 9), (30, 18, 12), (20, 10, 15), (90, 45, 36), (150, 135, 10), (24, 96, 75), (2160, 4, 2),
     (4, 1080, 2), (6, 4, 1125), (540, 12, 6), (36, 540, 3), (10, 6, 810),
+    # two-stage plans with fat composite radices 18, 20, 21, 28 (fc_plan.cu: factorize) on the axes they are planned for
+    (32, 270, 6), (16, 6, 420), (32, 8, 270), (272, 300, 3), (272, 420, 2),
 ]
 
 

@@ -49,7 +49,9 @@ def test_cpp_caller_of_the_multi_gpu_entry_points(fc, world, tmp_path):
                                               ((256, 256, 64), (15, 15, 15), 8), ((64, 2048, 64), (5, 7, 5), 2),
                                               # ragged slabs and non-power-of-two extents
                                               ((64, 70, 45), (5, 5, 5), 2), ((128, 100, 75), (7, 5, 5), 8),
-                                              ((72, 135, 90), (5, 5, 5), 4), ((70, 66, 46), (3, 3, 5), 3)])
+                                              ((72, 135, 90), (5, 5, 5), 4), ((70, 66, 46), (3, 3, 5), 3),
+                                              # two-stage plans with fat radices on the split-layout run-time kernels
+                                              ((64, 270, 300), (5, 5, 5), 4)])
 @pytest.mark.parametrize("kind", ["pageable", "pinned", "device"])
 def test_slab_matches_single_device(fc, dev, imDim, kDim, world, kind):
     import torch
@@ -84,10 +86,11 @@ def test_slab_matches_single_device(fc, dev, imDim, kDim, world, kind):
     check(got, want)
 
 
-@pytest.mark.parametrize("exchange", ["0", "1"])
+@pytest.mark.parametrize("exchange", ["0", "1", "2"])
 def test_both_forward_exchanges(fc, dev, monkeypatch, exchange):
     """FCB200_SLAB_EXCHANGE=1 (default): the y pass writes the exchange layout locally and the copy engines move the
-    blocks, chunk by chunk; =0: the y pass stores straight into the peers' buffers.  Same result either way."""
+    blocks, chunk by chunk; =0: the y pass stores straight into the peers' buffers; =2: the peers' fused z pass reads the
+    planes out of the producer's exchange buffer (no separate exchange step).  Same result every way."""
     import torch
     monkeypatch.setenv("FCB200_SLAB_EXCHANGE", exchange)
     imDim, kDim, world = (128, 96, 160), (7, 5, 9), 4          # 40 planes per rank: the copy exchange runs in 4 chunks

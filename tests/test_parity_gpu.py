@@ -51,6 +51,10 @@ CASES = [  # (imDim, kernelDim): cubic, non-cubic (placement quirk), odd, generi
     ((158, 158, 24), (5, 5, 5)),          # Rader stages: x half-length 79, y = 2 * 79
     ((542, 20, 218), (3, 3, 3)),          # x half-length 271 (270 = 2*15*9), fused z pass with 2 * 109 (108 = 12*9)
     ((148, 74, 106), (5, 3, 3)),          # primes 37 / 53 below the Rader threshold: symmetric direct sum
+    ((64, 48, 300), (5, 3, 9)),           # fused z pass with the two-stage plans (20,15) / (20,21) / (28,20)
+    ((48, 32, 420), (3, 3, 7)),
+    ((40, 24, 560), (3, 3, 5)),
+    ((270, 270, 270), (5, 5, 5)),         # config 2 padded: x half-length 135 = 9 * 15, y and z 270 = 18 * 15 (TMA pipeline)
 ]
 
 

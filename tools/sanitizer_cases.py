@@ -54,7 +54,7 @@ rng = np.random.default_rng(3)
 im = (rng.random(int(np.prod(im_dim)), dtype=np.float32) * 100).astype(np.float32)
 k = rng.random(int(np.prod(k_dim)), dtype=np.float32)
 want = fo.convolve_inplace_ref(im, im_dim, k, k_dim)
-for x in ("1", "0"):
+for x in ("1", "0", "2"):
     os.environ["FCB200_SLAB_EXCHANGE"] = x
     got = im.copy()
     fc.convolve_slab(got, im_dim, k, k_dim, [0, 0, 0, 0])
