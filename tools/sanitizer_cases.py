@@ -22,7 +22,12 @@ CASES = [
     ((32, 2048, 4), (3, 3, 3), "TMA plain y, L = 2048, 32-byte rows"),
     ((64, 16, 512), (5, 3, 3), "TMA fused z, L = 512, 64-byte rows"),
     ((40, 560, 6), (3, 5, 3), "TMA plain y, L = 560"),
-    ((30, 270, 270), (3, 3, 3), "TMA y and fused z, L = 270"),
+    ((30, 270, 270), (3, 3, 3), "TMA y and fused z, L = 270 = 18 * 15"),
+    ((60, 300, 300), (3, 5, 3), "two-stage plans: TMA y and fused z with 300 = 20 * 15, masked PSF z pass"),
+    ((300, 12, 10), (3, 3, 3), "tiled x kernel, half-length 150 = 10 * 15"),
+    ((24, 420, 420), (3, 3, 5), "TMA y and fused z, L = 420 = 20 * 21"),
+    ((24, 448, 560), (3, 3, 3), "TMA y with 448 = 16 * 28, fused z with 560 = 28 * 20 (register kernel)"),
+    ((270, 12, 10), (3, 3, 3), "tiled x kernel, half-length 135 = 9 * 15"),
     ((66, 66, 26), (3, 3, 3), "register butterflies 11, 13"),
     ((46, 34, 38), (3, 3, 3), "register butterflies 23, 17, 19"),
     ((148, 74, 106), (5, 3, 3), "symmetric direct sum, primes 37 and 53"),
