@@ -115,7 +115,10 @@ std::vector<int> factorize(int L, bool* generic, int style)
     while (n % 3 == 0) { n /= 3; ++n3; }
     while (n % 5 == 0) { n /= 5; ++n5; }
     while (n % 7 == 0) { n /= 7; ++n7; }
-    if ((int)out.size() + n3 + n5 + n7 > 4) {
+    // (x axis: the tiled kernels keep one stage per prime up to four stages, they lose with composite radices; y / z
+    // axes: at most three stages where pairing allows it -- 360 = (8,15,3), 480 = (8,4,15), 288 = (8,4,9), 350 = (10,5,7) --
+    // which is also what lets their digit reversal fit the five dimensions of a tensor map, fft_col_tma.cu)
+    if ((int)out.size() + n3 + n5 + n7 > (style == 2 ? 4 : 3)) {
         std::vector<int> comp;
         while (n3 >= 1 && n5 >= 1) { comp.push_back(15); --n3; --n5; }
         if ((n3 & 1) && !out.empty() && (out.back() == 2 || out.back() == 4)) { out.back() *= 3; --n3; }

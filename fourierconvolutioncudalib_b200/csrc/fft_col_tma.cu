@@ -604,6 +604,235 @@ bool run_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same pipeline for the PLAIN passes of long lengths WITHOUT a compile-time plan (7-smooth lengths of two or three
+// register stages: 400, 480, 600, 640 ...): the producer warp is identical -- the tensor maps are built on the host from
+// the plan's run-time radices -- and the consumers run the run-time-radix stages of fft_engine.cuh (one switch per stage)
+// in place.  The one-tile-per-CTA kernels these lengths ran on are latency-bound (ncu, 400^3 y pass: 16 warps per SM, 33 %
+// SM throughput, 3.1 TB/s).  Measured (profiles/r02_tma_dyn_ab.jsonl): y passes 400: 0.163 -> 0.150 ms, 480: 0.274 -> 0.238,
+// 600: 0.183 -> 0.138, 640: 0.172 -> 0.128; shorter lengths (160, 200) lose and a fused variant (forward stages, multiply,
+// inverse stages: 2 ns + 1 round trips with two slots) lost on every length, so those stay where they were.
+//   MODE 0 forward: natural-order load, digit-reversing store.   MODE 1 inverse (mirrored stages): digit-reversing LOAD,
+//   natural-order store.
+constexpr int kDynMaxThreads = 352;
+constexpr int kDynMaxBuf = 4;
+
+template <int MODE, bool GROUPS>
+__global__ void __launch_bounds__(kDynMaxThreads + 32, 1)
+    col_tma_dyn_kernel(const __grid_constant__ CUtensorMap nat_map, const __grid_constant__ CUtensorMap perm_map, TmaArgs a,
+                       AxisPlanDev P, int nbuf)
+{
+    constexpr int TXP = 8;
+    const int L = P.L, ns = P.ns, TILE = L * TXP;
+    const int SLOT = TILE;
+    const unsigned slot_bytes = (unsigned)SLOT * sizeof(float4);
+    extern __shared__ __align__(128) float4 smem[];
+    float4* bufs = smem;
+    float4* tw = bufs + (size_t)nbuf * SLOT;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(tw + L);
+    unsigned long long* done = full + kDynMaxBuf;
+
+    const int t = threadIdx.x;
+    const int nthreads = (int)blockDim.x - 32;   // consumers
+    const int stride = (int)gridDim.x;
+
+    if (t == 0) {
+        for (int i = 0; i < nbuf; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(done + i, nthreads);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_launch_dependents();
+    load_twiddles(tw, a.tw, L);
+    __syncthreads();
+    pdl_wait();
+
+    if (t >= nthreads) {
+        // ---------------- producer warp ----------------
+        if (t != nthreads) return;
+        auto perm_ld = [&](void* dst, const CUtensorMap* map, int c0, int gi, unsigned long long* bar) {
+            if (ns == 2) {
+                if (GROUPS) tma_load_4d(dst, map, c0, 0, 0, gi, bar);
+                else tma_load_3d(dst, map, c0, 0, 0, bar);
+            } else if (ns == 3) {
+                if (GROUPS) tma_load_5d(dst, map, c0, 0, 0, 0, gi, bar);
+                else tma_load_4d(dst, map, c0, 0, 0, 0, bar);
+            } else {
+                tma_load_5d(dst, map, c0, 0, 0, 0, 0, bar);
+            }
+        };
+        auto perm_st = [&](const CUtensorMap* map, int c0, int gi, const void* src) {
+            if (ns == 2) {
+                if (GROUPS) tma_store_4d(map, c0, 0, 0, gi, src);
+                else tma_store_3d(map, c0, 0, 0, src);
+            } else if (ns == 3) {
+                if (GROUPS) tma_store_5d(map, c0, 0, 0, 0, gi, src);
+                else tma_store_4d(map, c0, 0, 0, 0, src);
+            } else {
+                tma_store_5d(map, c0, 0, 0, 0, 0, src);
+            }
+        };
+        auto issue_load = [&](int tile, int slot) {
+            if (a.reverse) tile = a.totalTiles - 1 - tile;
+            const int gi = tile / a.tilesPerGroup;
+            const int tt = tile - gi * a.tilesPerGroup;
+            float4* dst = bufs + (size_t)slot * SLOT;
+            mbar_expect_tx(full + slot, slot_bytes);
+            if (MODE == 1) {
+                perm_ld(dst, &perm_map, tt * 4 * TXP, gi, full + slot);
+            } else {
+                for (int r0 = 0; r0 < L; r0 += a.boxRows)
+                    tma_load_3d(dst + (size_t)r0 * TXP, &nat_map, tt * 4 * TXP, r0, gi, full + slot);
+            }
+        };
+        for (int k = 0; k < nbuf; ++k) {
+            const int tile = (int)blockIdx.x + k * stride;
+            if (tile < a.totalTiles) issue_load(tile, k);
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.totalTiles; tile += stride, ++it) {
+            const int slot = it % nbuf;
+            float4* sm = bufs + (size_t)slot * SLOT;
+            mbar_wait(done + slot, (unsigned)((it / nbuf) & 1));
+            const int tq = a.reverse ? a.totalTiles - 1 - tile : tile;
+            const int gi = tq / a.tilesPerGroup;
+            const int tt = tq - gi * a.tilesPerGroup;
+            if (MODE == 0) {
+                perm_st(&perm_map, tt * 4 * TXP, gi, sm);
+            } else {
+                for (int r0 = 0; r0 < L; r0 += a.boxRows)
+                    tma_store_3d(&nat_map, tt * 4 * TXP, r0, gi, sm + (size_t)r0 * TXP);
+            }
+            tma_commit();
+            const int next = tile + nbuf * stride;
+            if (next < a.totalTiles) {
+                tma_wait_read<0>();
+                issue_load(next, slot);
+            }
+        }
+        tma_wait_read<0>();
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int cp = t % TXP, w = t / TXP, W = nthreads / TXP;
+    auto csync = [&] { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.totalTiles; tile += stride, ++it) {
+        const int slot = it % nbuf;
+        float4* sm = bufs + (size_t)slot * SLOT;
+        float4* none = nullptr;
+        mbar_wait(full + slot, (unsigned)((it / nbuf) & 1));
+        if (MODE == 0) {
+            int Li = L;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {   // (unrolled: the radices stay in registers)
+                if (s < ns) {
+                    const int R = P.radix[s];
+                    stage_dispatch<false, false>(R, sm, none, tw, L, Li, cp, w, W, TXP, true);
+                    Li /= R;
+                    if (s + 1 < ns) csync();
+                }
+            }
+        }
+        if (MODE == 1) {
+            int Li = 1;
+#pragma unroll
+            for (int s = 3; s >= 0; --s) {
+                if (s < ns) {
+                    const int R = P.radix[s];
+                    Li *= R;
+                    stage_dispatch<true, false>(R, sm, none, tw, L, Li, cp, w, W, TXP, true);
+                    if (s > 0) csync();
+                }
+            }
+        }
+        fence_async_smem();
+        mbar_arrive(done + slot);
+    }
+}
+
+bool permuted_spec_dyn(const ColArgs& a, long long ngroups, int boxFloats, MapSpec& s)
+{
+    const int ns = a.P.ns;
+    const bool with_groups = ngroups > 1;
+    s.rank = 1 + ns + (with_groups ? 1 : 0);
+    if (ns < 2 || s.rank > 5) return false;
+    s.dims[0] = (cuuint64_t)a.rowLen * 2;
+    s.box[0] = (cuuint32_t)boxFloats;
+    const cuuint64_t row = (cuuint64_t)a.stride * sizeof(float2);
+    cuuint64_t kstride[4], acc = 1;
+    for (int i = 0; i < ns; ++i) {
+        if (a.P.radix[i] > 256) return false;
+        kstride[i] = acc;
+        acc *= (cuuint64_t)a.P.radix[i];
+    }
+    for (int d = 0; d < ns; ++d) {
+        const int st = ns - 1 - d;
+        s.dims[1 + d] = (cuuint64_t)a.P.radix[st];
+        s.strides[d] = kstride[st] * row;
+        s.box[1 + d] = (cuuint32_t)a.P.radix[st];
+    }
+    if (with_groups) {
+        s.dims[1 + ns] = (cuuint64_t)ngroups;
+        s.strides[ns] = (cuuint64_t)a.groupStride * sizeof(float2);
+        s.box[1 + ns] = 1;
+    }
+    return true;
+}
+
+bool run_col_tma_dyn(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
+{
+    const int L = a.P.L;
+    static const int min_len = env_int("FCB200_TMA_DYN_MINLEN", 384);
+    if (mode == 2 || a.P.generic || a.P.big || a.P.ns < 2 || a.P.ns > 4 || L < min_len) return false;
+    if (a.split || a.splitPeers || a.rowMask || a.groupList || a.winSlot || a.txp != 8) return false;
+    if (!encode_fn()) return false;
+    const int boxFloats = 32;
+    const int tpg = (a.rowLen * 2 + boxFloats - 1) / boxFloats;
+    const long long total = ngroups * tpg;
+    if (total == 0) return true;
+    if (total > 0x7fffffffLL) return false;
+    if (ngroups > 1 && (a.groupStride % 2) != 0) return false;
+    if ((a.stride % 2) != 0 || (reinterpret_cast<uintptr_t>(a.data) & 15) != 0) return false;
+    int boxRows = std::min(L, 256);
+    while (L % boxRows) --boxRows;
+    if (L / boxRows > 16) return false;   // (a prime-ish length would need one box per few rows)
+    const size_t slot = (size_t)L * 8 * sizeof(float4);
+    const size_t fixed = (size_t)L * sizeof(float4) + 2 * kDynMaxBuf * sizeof(unsigned long long);
+    int nbuf = (int)std::min<size_t>(3, ((size_t)kMaxDynSmem - fixed) / slot);
+    if (nbuf < 2) return false;
+    const size_t smem = (size_t)nbuf * slot + fixed;
+    // one consumer per butterfly of the stage with the most butterflies
+    int most = 0;
+    for (int s = 0; s < a.P.ns; ++s) most = std::max(most, L / a.P.radix[s]);
+    const int threads = std::min(kDynMaxThreads, std::max(64, ((most * 8 + 31) / 32) * 32));
+
+    CUtensorMap nat, perm;
+    if (!encode(&nat, a.data, natural_spec(a, ngroups, L, boxRows, boxFloats))) return false;
+    MapSpec ps;
+    if (!permuted_spec_dyn(a, ngroups, boxFloats, ps)) return false;
+    if (!encode(&perm, a.data, ps)) return false;
+    static const int rev_env = env_int("FCB200_TMA_REVERSE", 1);
+    const int reverse = (rev_env == 1 && ngroups > 1) ? 1 : (rev_env == 2 ? 1 : 0);
+    TmaArgs ta{a.P.tw, tpg, (int)total, boxRows, a.scale, reverse, nullptr, 0};
+    auto go = [&](auto kernel) {
+        FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = (int)std::min<long long>(total, (long long)sm_count_of_current_device());
+        launch_pdl(a.pdl != 0, kernel, dim3(grid), dim3(threads + 32), smem, st, nat, perm, ta, a.P, nbuf);
+        FC_CUDA_KERNEL();
+    };
+    if (ngroups > 1) {
+        if (mode == 0) go(col_tma_dyn_kernel<0, true>);
+        else go(col_tma_dyn_kernel<1, true>);
+    } else {
+        if (mode == 0) go(col_tma_dyn_kernel<0, false>);
+        else go(col_tma_dyn_kernel<1, false>);
+    }
+    return true;
+}
+
 // fused z pass with the PSF spectrum derived on the fly from the window planes in a.H ([winPlanes][ny][xcp])
 template <class P, int THREADS, int NBUF, int TXP>
 bool run_col_otf_tma(const ColArgs& a, long long ngroups, int z0, cudaStream_t st, bool probe)
@@ -701,6 +930,10 @@ bool launch_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t 
     if (plan_matches<P270>(a.P) && mode != 2) return run_col_tma<P270, 160, 3, 8, 1>(a, mode, ngroups, st);
     if (plan_matches<P270>(a.P) && mode == 2) return run_col_tma<P270, 160, 2, 8, 2>(a, mode, ngroups, st);
     if (plan_matches<P448y>(a.P) && mode != 2) return run_col_tma<P448y, 224, 3, 8, 1>(a, mode, ngroups, st);
+    // plain passes of long lengths without a compile-time plan: the same pipeline with run-time radices
+    // (FCB200_TMA_DYN=0: the one-tile-per-CTA kernels)
+    static const int dyn = env_int("FCB200_TMA_DYN", 1);
+    if (dyn && !col_static_has_plan(a.P) && run_col_tma_dyn(a, mode, ngroups, st)) return true;
     if (on >= 2) {
         if (plan_matches<P448>(a.P) && mode != 2) return run_col_tma<P448, 512, 3, 8, 1>(a, mode, ngroups, st);
         if (plan_matches<P1024>(a.P) && mode == 2) return run_col_tma<P1024, 128, 3, 2>(a, mode, ngroups, st);

@@ -83,6 +83,7 @@ void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t
 // tensor map; return false when no configuration matches (plan, layout, mode)
 bool launch_col_tma(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
 // compile-time specialised kernels (fft_static.cu); return false when none matches the plan
+bool col_static_has_plan(const AxisPlanDev& P);
 bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream_t st);
 // fused z pass that derives the PSF-spectrum tile on the fly from the <=16 window planes starting at z0;
 // a.H = buffer holding those planes (after the x and y passes); probe = only test applicability

@@ -537,6 +537,15 @@ static bool try_pipe_plain(const ColArgs& a, int mode, long long ngroups, cudaSt
 }
 
 
+// true when a compile-time column kernel exists for the plan (the run-time-radix TMA pipeline leaves those alone)
+bool col_static_has_plan(const AxisPlanDev& P)
+{
+    return plan_matches<P64>(P) || plan_matches<P128>(P) || plan_matches<P256>(P) || plan_matches<P256b>(P) ||
+           plan_matches<P384>(P) || plan_matches<P512>(P) || plan_matches<P1024>(P) || plan_matches<P2048>(P) ||
+           plan_matches<P560>(P) || plan_matches<P560z>(P) || plan_matches<P448>(P) || plan_matches<P448y>(P) ||
+           plan_matches<P420>(P) || plan_matches<P300>(P) || plan_matches<P270>(P);
+}
+
 bool launch_col_static(const ColArgs& a, int mode, long long ngroups, cudaStream_t st)
 {
     if (!static_enabled()) return false;

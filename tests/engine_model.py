@@ -48,7 +48,7 @@ def factorize(L, style=0):
             cnt[r] += 1
             n //= r
     comp = []
-    if len(out) + cnt[3] + cnt[5] + cnt[7] > 4:      # only lengths that would need five or more stages
+    if len(out) + cnt[3] + cnt[5] + cnt[7] > (4 if style == 2 else 3):   # x axis: up to four stages of primes; y / z: three
         while cnt[3] >= 1 and cnt[5] >= 1:
             comp.append(15)
             cnt[3] -= 1

@@ -10,9 +10,10 @@ LENGTHS = [1024, 2048, 4096, 8192, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 19
 
 def test_composite_radix_plans():
     want = {1125: [15, 15, 5], 2160: [16, 15, 9], 1080: [8, 15, 9], 810: [6, 15, 9], 540: [4, 15, 9],
-            # up to four stages: one register stage per prime, as measured
-            150: [2, 3, 5, 5], 135: [3, 3, 3, 5], 210: [2, 3, 5, 7], 96: [8, 4, 3],
-            384: [16, 8, 3], 192: [8, 8, 3], 560: [16, 5, 7], 280: [8, 5, 7], 224: [8, 4, 7],
+            # y / z axes: at most three stages where small primes pair into composite radices
+            150: [10, 15], 135: [15, 9], 210: [2, 15, 7], 360: [8, 15, 3], 480: [8, 4, 15], 288: [8, 4, 9], 350: [10, 5, 7],
+            600: [8, 15, 5], 96: [8, 4, 3], 384: [16, 8, 3], 192: [8, 8, 3], 560: [16, 5, 7], 280: [8, 5, 7], 224: [8, 4, 7],
+            400: [16, 5, 5],
             # two stages of fat composite radices where they were measured to win (y axis)
             270: [18, 15], 300: [20, 15], 420: [20, 21], 448: [16, 28]}
     for L, r in want.items():
@@ -20,6 +21,8 @@ def test_composite_radix_plans():
     # fused z axis / x axis variants
     assert em.factorize(448, 1) == [8, 8, 7] and em.factorize(560, 1) == [28, 20] and em.factorize(300, 1) == [20, 15]
     assert em.factorize(150, 2) == [10, 15] and em.factorize(135, 2) == [9, 15] and em.factorize(300, 2) == [4, 3, 5, 5]
+    # x axis: one stage per prime up to four stages (the tiled kernels lose with composite radices)
+    assert em.factorize(210, 2) == [2, 3, 5, 7] and em.factorize(360, 2) == [8, 3, 3, 5] and em.factorize(350, 2) == [2, 5, 5, 7]
 
 
 @pytest.mark.parametrize("L", [2, 3, 4, 5, 7, 8, 12, 30, 35, 64, 66, 130, 158, 300, 270, 420, 1125, 90])

@@ -18,6 +18,8 @@ SHAPES = [  # imDim = (d0 fastest, d1, d2)
     (4, 1080, 2), (6, 4, 1125), (540, 12, 6), (36, 540, 3), (10, 6, 810),
     # two-stage plans with fat composite radices 18, 20, 21, 28 (fc_plan.cu: factorize) on the axes they are planned for
     (32, 270, 6), (16, 6, 420), (32, 8, 270), (272, 300, 3), (272, 420, 2),
+    # lengths without a compile-time plan on the run-time-radix TMA pipeline (two and three stages, with and without planes)
+    (32, 400, 6), (16, 6, 360), (32, 288, 4), (16, 4, 350), (16, 480, 3), (48, 160, 5), (20, 200, 1), (272, 640, 2), (16, 2, 600),
 ]
 
 

@@ -54,6 +54,8 @@ CASES = [  # (imDim, kernelDim): cubic, non-cubic (placement quirk), odd, generi
     ((64, 48, 300), (5, 3, 9)),           # fused z pass with the two-stage plans (20,15) / (20,21) / (28,20)
     ((48, 32, 420), (3, 3, 7)),
     ((40, 24, 560), (3, 3, 5)),
+    ((64, 400, 360), (5, 5, 5)),          # run-time-radix TMA pipeline: y = (16,5,5), fused z = (8,15,3)
+    ((48, 288, 350), (3, 5, 5)),          # y = (8,4,9), fused z = (10,5,7)
     ((270, 270, 270), (5, 5, 5)),         # config 2 padded: x half-length 135 = 9 * 15, y and z 270 = 18 * 15 (TMA pipeline)
 ]
 
