@@ -330,8 +330,10 @@ void launch_col_fast(const ColArgs& a, int mode, long long ngroups, cudaStream_t
 // i.e. one radix-16 butterfly per output residue k2 on the 16 twiddled inputs: no shared-memory
 // stages, no barriers after the 2 KB window is staged.  L % 16 == 0.
 // ------------------------------------------------------------------------------------------------
-template <int NH>   // window of 16 * NH planes
-__global__ void __launch_bounds__(1024) psf_z_pruned_kernel(ColArgs a, int z0)
+// MAXT: largest CTA (L / 2 threads): 512 for L <= 1024 leaves 128 registers per thread (the 64 of a 1024-thread bound
+// spilled 150-380 bytes of the 16-point butterfly)
+template <int NH, int MAXT>   // window of 16 * NH planes
+__global__ void __launch_bounds__(MAXT) psf_z_pruned_kernel(ColArgs a, int z0)
 {
     __shared__ float4 win[16 * NH * 8];
     const int L = a.P.L, Q = L / 16;
@@ -402,9 +404,16 @@ bool launch_psf_z_pruned(const ColArgs& a, int z0, int planes, cudaStream_t st)
     if ((planes != 16 && planes != 32 && planes != 64) || planes > L) return false;
     const int tiles = (a.rowLen + 15) / 16;
     if (tiles == 0) return true;
-    if (planes == 16) psf_z_pruned_kernel<1><<<tiles, L / 16 * 8, 0, st>>>(a, z0);
-    else if (planes == 32) psf_z_pruned_kernel<2><<<tiles, L / 16 * 8, 0, st>>>(a, z0);
-    else psf_z_pruned_kernel<4><<<tiles, L / 16 * 8, 0, st>>>(a, z0);
+    const int threads = L / 16 * 8;
+    if (threads <= 512) {
+        if (planes == 16) psf_z_pruned_kernel<1, 512><<<tiles, threads, 0, st>>>(a, z0);
+        else if (planes == 32) psf_z_pruned_kernel<2, 512><<<tiles, threads, 0, st>>>(a, z0);
+        else psf_z_pruned_kernel<4, 512><<<tiles, threads, 0, st>>>(a, z0);
+    } else {
+        if (planes == 16) psf_z_pruned_kernel<1, 1024><<<tiles, threads, 0, st>>>(a, z0);
+        else if (planes == 32) psf_z_pruned_kernel<2, 1024><<<tiles, threads, 0, st>>>(a, z0);
+        else psf_z_pruned_kernel<4, 1024><<<tiles, threads, 0, st>>>(a, z0);
+    }
     FC_CUDA_KERNEL();
     return true;
 }
