@@ -403,7 +403,14 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
     pdl_launch_dependents();
     load_twiddles(tw, a.tw, L);
     if constexpr (MODE == 3)
-        for (int r = t; r < L; r += THREADS + 32) pos_s[r] = __ldg(a.pos + r);
+        for (int k = t; k < L; k += THREADS + 32) {   // position of frequency k for THIS kernel's radix sequence
+            const int m0 = k % P::R0, q = k / P::R0;
+            int pk;
+            if (P::ns == 2) pk = m0 * P::R1 + q;
+            else if (P::ns == 3) pk = (m0 * P::R1 + q % P::R1) * P::R2 + q / P::R1;
+            else pk = ((m0 * P::R1 + q % P::R1) * P::R2 + (q / P::R1) % P::R2) * P::R3 + q / (P::R1 * P::R2);
+            pos_s[k] = pk;
+        }
     __syncthreads();
     pdl_wait();   // everything below reads what the previous pass wrote
 
@@ -839,7 +846,8 @@ bool run_col_otf_tma(const ColArgs& a, long long ngroups, int z0, cudaStream_t s
 {
     constexpr int L = P::L;
     static_assert(L % 16 == 0, "on-the-fly PSF spectrum needs L % 16 == 0");
-    if (!plan_matches<P>(a.P)) return false;
+    // natural order in and out and no planner table: the kernel's radix sequence need not be the planner's
+    if (a.P.L != L) return false;
     if (a.split || a.splitPeers || a.rowMask || a.groupList || ngroups != 1) return false;
     const int nh = a.winPlanes / 16;
     if (a.winPlanes % 16 != 0 || (nh != 1 && nh != 2 && nh != 4) || a.winPlanes > L) return false;
@@ -869,10 +877,12 @@ bool run_col_otf_tma(const ColArgs& a, long long ngroups, int z0, cudaStream_t s
     ws.box[1] = (cuuint32_t)a.winPlanes;
     ws.box[2] = 1;
     if (!encode(&wmap, const_cast<float2*>(a.H), ws)) return false;
-    TmaArgs ta{a.P.tw, tpg, tpg, boxRows, a.scale, 0, a.P.pos, z0};
+    TmaArgs ta{a.P.tw, tpg, tpg, boxRows, a.scale, 0, nullptr, z0};
     auto go = [&](auto kernel) {
         FC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = std::min(tpg, sm_count_of_current_device());
+        int per_sm = 1;   // two-slot configurations of the short lengths fit twice: the pass is bound by its butterflies
+        FC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS + 32, smem));
+        const int grid = std::min(tpg, sm_count_of_current_device() * std::max(1, per_sm));
         launch_pdl(a.pdl != 0, kernel, dim3(grid), dim3(THREADS + 32), smem, st, nat, nat, wmap, ta);
         FC_CUDA_KERNEL();
     };
@@ -891,7 +901,12 @@ bool launch_col_otf_tma(const ColArgs& a, long long ngroups, int z0, cudaStream_
     if (!on || !otf_on || !static_enabled() || a.txp != 8) return false;
     static const long long max_stride = (long long)env_int("FCB200_TMA_MAXSTRIDE_KB", 2048) << 10;
     if (a.stride * (long long)sizeof(float2) > max_stride) return false;
-    return run_col_otf_tma<P256b, 256, 4, 8>(a, ngroups, z0, st, probe) || run_col_otf_tma<P384, 192, 3, 8>(a, ngroups, z0, st, probe) ||
+    // L = 256 runs as (16,16) -- one shared-memory round trip instead of two next to the H derivation -- with two slots,
+    // so that two CTAs fit an SM (the pass is bound by its butterflies): C3 0.195 -> 0.134 ms, below the pass that
+    // reads a materialised spectrum (0.142 ms)
+    static const int v = env_int("FCB200_OTF_VARIANT", 0);
+    if (v == 1 && run_col_otf_tma<P256, 128, 1, 8>(a, ngroups, z0, st, probe)) return true;
+    return run_col_otf_tma<P256, 128, 2, 8>(a, ngroups, z0, st, probe) || run_col_otf_tma<P384, 192, 3, 8>(a, ngroups, z0, st, probe) ||
            run_col_otf_tma<P512, 256, 4, 4>(a, ngroups, z0, st, probe) || run_col_otf_tma<P448, 512, 2, 8>(a, ngroups, z0, st, probe);
 }
 

@@ -54,8 +54,10 @@ def test_full_size_matches_reference_build(fc, dev, reflib, name, imDim, kDim, e
 
 
 def test_tma_kernels_equal_the_register_kernels_bit_for_bit(fc, dev, monkeypatch):
-    """FCB200_TMA=0 routes the y / z passes through the cp.async / register kernels: same arithmetic, same order"""
+    """FCB200_TMA=0 routes the y / z passes through the cp.async / register kernels: same arithmetic, same order
+    (materialised PSF spectrum on both sides: the on-the-fly fused pass uses a radix sequence of its own)"""
     import torch
+    monkeypatch.setenv("FCB200_OTF_INPLACE", "0")
     imDim, kDim = (512, 512, 256), (31, 31, 41)
     n = int(np.prod(imDim))
     g = torch.Generator(device=f"cuda:{dev}")
@@ -70,6 +72,12 @@ def test_tma_kernels_equal_the_register_kernels_bit_for_bit(fc, dev, monkeypatch
         torch.cuda.synchronize()
         outs.append(x)
     assert torch.equal(outs[0], outs[1])
+    # the default for this shape (device PSF, nz = 256, 16-plane window) is the on-the-fly path: same result to round-off
+    monkeypatch.delenv("FCB200_OTF_INPLACE")
+    x = base.clone()
+    fc.convolve_device_async(x, imDim, d_k, kDim, dev, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert float((x - outs[1]).abs().max() / outs[1].abs().max()) <= 2e-6
 
 
 def test_eight_rank_slab_of_a_2gib_volume_matches_single_gpu(fc, dev):

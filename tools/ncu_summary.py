@@ -82,7 +82,13 @@ for r in rows[2:]:
         "top_stalls_warps_per_issue": [[n, round(v, 2)] for v, n in top],
     })
 json.dump(summary, open(out, "w"), indent=1)
-json.dump(traffic, open(out.rsplit("/", 1)[0] + "/ncu_traffic.json", "w"), indent=1)
+tpath = out.rsplit("/", 1)[0] + "/ncu_traffic.json"
+try:
+    merged = json.load(open(tpath))     # keep the passes of earlier captures (e.g. the on-the-fly fused pass)
+except Exception:
+    merged = {}
+merged.update(traffic)
+json.dump(merged, open(tpath, "w"), indent=1)
 print(json.dumps(traffic))
 for s in summary:
     print(s["kernel"], s["us"], s["dram_GBps"], s["regs"], s["warps_active_pct"], s["issue_active_pct"], s["top_stalls_warps_per_issue"])
