@@ -904,9 +904,9 @@ bool launch_col_otf_tma(const ColArgs& a, long long ngroups, int z0, cudaStream_
     // L = 256 runs as (16,16) -- one shared-memory round trip instead of two next to the H derivation -- with two slots,
     // so that two CTAs fit an SM (the pass is bound by its butterflies): C3 0.195 -> 0.134 ms, below the pass that
     // reads a materialised spectrum (0.142 ms)
-    static const int v = env_int("FCB200_OTF_VARIANT", 0);
-    if (v == 1 && run_col_otf_tma<P256, 128, 1, 8>(a, ngroups, z0, st, probe)) return true;
-    return run_col_otf_tma<P256, 128, 2, 8>(a, ngroups, z0, st, probe) || run_col_otf_tma<P384, 192, 3, 8>(a, ngroups, z0, st, probe) ||
+    // L = 384 as (24,16) for the same reason (one CTA per SM, three slots): 384^3 0.182 -> 0.156 ms ((16,24): 0.164)
+    return run_col_otf_tma<P256, 128, 2, 8>(a, ngroups, z0, st, probe) ||
+           run_col_otf_tma<SPlan<384, 24, 16>, 192, 3, 8>(a, ngroups, z0, st, probe) ||
            run_col_otf_tma<P512, 256, 4, 4>(a, ngroups, z0, st, probe) || run_col_otf_tma<P448, 512, 2, 8>(a, ngroups, z0, st, probe);
 }
 
