@@ -48,18 +48,20 @@ bool prepare_psf(ConvPlan& p, const float* kernel, bool k_dev, const int* pdims,
 {
     static const bool cache_on = env_flag("FCB200_PSF_CACHE", true);
     // On-the-fly PSF spectrum (windows of 16 / 32 / 64 PSF planes) is the SaveMemory path, and InPlace takes it too where
-    // the on-the-fly fused pass ITSELF is the faster one (FCB200_OTF_INPLACE: unset = this rule, 0 = never, 1 = wherever a
-    // window exists; read per call): nz = 256 with a 16-plane window (C3) -- 0.133 ms against 0.142 ms for the pass that
-    // reads a materialised spectrum, and no PSF z pass: C3 0.588 -> 0.517 ms, 256^3 0.182 -> 0.157 ms.  Elsewhere the
-    // materialised spectrum stays: it is cached across calls with the same host taps (the deconvolution pattern) and its
-    // fused pass is the faster one (384: 0.144 against 0.181 ms; without the cache the on-the-fly path would win by
-    // 3-7 %: 384^3 0.574 -> 0.533 ms, 512^3 1.305 -> 1.271).  The rule depends on the shapes only, so host and device
-    // pointers give bit-identical results.
+    // the on-the-fly fused pass ITSELF is as fast as the one that reads a materialised spectrum (FCB200_OTF_INPLACE: unset =
+    // this rule, 0 = never, 1 = wherever a window exists; read per call):
+    //   nz = 256, 16-plane window (C3): 0.132 against 0.142 ms, and no PSF z pass: C3 0.588 -> 0.517 ms, 256^3 0.182 -> 0.156
+    //   nz = 384, window <= 32 planes (a C4 block): 0.147 against 0.144 ms: 384^3 0.574 -> 0.500 ms when the spectrum has to
+    //   be built, within 1 % of a cached materialised spectrum when it has not -- and 231 MB less memory
+    // Elsewhere the materialised spectrum stays: it is cached across calls with the same host taps (the deconvolution
+    // pattern) and its fused pass is the faster one (512: 0.367 against 0.469 ms).  The rule depends on the shapes only, so
+    // host and device pointers give bit-identical results.
     bool otf_inplace = false;
     if (!save_memory) {
         const char* e = std::getenv("FCB200_OTF_INPLACE");
         if (e) otf_inplace = std::atoi(e) != 0;
-        else otf_inplace = p.g.nz == 256 && psf_window_applies(p, pdims, st) && p.psf_window_planes == 16;
+        else if (p.g.nz == 256 || p.g.nz == 384)
+            otf_inplace = psf_window_applies(p, pdims, st) && p.psf_window_planes <= (p.g.nz == 256 ? 16 : 32);
     }
     const size_t ktaps = (size_t)pdims[0] * pdims[1] * pdims[2];
     auto same_taps = [&](bool valid, const int* dims, const std::vector<float>& taps) {

@@ -353,6 +353,64 @@ __device__ __forceinline__ void otf_h_tile(const float4* __restrict__ win, float
     }
 }
 
+// Two-stage plans whose last radix is 16: the frequencies of last-stage butterfly b are k2 + m * (L / 16) with k2 = b, i.e.
+// exactly the 16 outputs k1 = m of ONE butterfly of the H derivation above.  The thread that runs the fused middle stage on
+// butterfly b therefore derives its 16 H values in registers -- no H tile in shared memory, no position table, one barrier
+// less -- then: last forward stage, x H x c, first inverse stage, as smid_fused_tma.
+template <int L, int NH, int NW, int TXP>
+__device__ __forceinline__ void smid_fused_otf16(const float4* __restrict__ win, float4* __restrict__ sm,
+                                                 const float4* __restrict__ tw, int z0, int cp, int w, float c)
+{
+    constexpr int Q = L / 16, ITER = (Q + NW - 1) / NW;
+    const int s16 = z0 & 15;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int k2 = w + it * NW;
+        if ((Q % NW) != 0 && k2 >= Q) break;
+        p2 hr[16], hi[16];
+        int e = (z0 * k2) % L;
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+            const float4 v = win[n * TXP + cp];
+            hr[n] = make_float2(v.x, v.y);
+            hi[n] = make_float2(v.z, v.w);
+            cmul(hr[n], hi[n], tw[e]);
+            e += k2;
+            if (e >= L) e -= L;
+        }
+#pragma unroll
+        for (int h = 1; h < NH; ++h) {
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+                const float4 v = win[(16 * h + n) * TXP + cp];
+                p2 tr = make_float2(v.x, v.y), ti = make_float2(v.z, v.w);
+                cmul(tr, ti, tw[e]);
+                hr[n] = padd(hr[n], tr);
+                hi[n] = padd(hi[n], ti);
+                e += k2;
+                if (e >= L) e -= L;
+            }
+        }
+        Dft<16>::run(hr, hi);
+        if (s16 != 0) {
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) cmul(hr[k1], hi[k1], tw[((s16 * k1) & 15) * Q]);
+        }
+        p2 r[16], i[16];
+        load_pairs<16>(sm, k2 * 16 * TXP + cp, TXP, r, i);
+        Dft<16>::run(r, i);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const p2 xr = pmuls(pfma(hr[m], r[m], pneg(pmul(hi[m], i[m]))), c);
+            const p2 xi = pmuls(pfma(hi[m], r[m], pmul(hr[m], i[m])), c);
+            r[m] = xr;
+            i[m] = xi;
+        }
+        Dft<16>::run(i, r);
+        store_pairs<16>(sm, k2 * 16 * TXP + cp, TXP, r, i);
+    }
+}
+
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -383,10 +441,14 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
     constexpr unsigned SLOT_BYTES = (unsigned)SLOT * sizeof(float4);
     extern __shared__ __align__(128) float4 smem[];
     float4* bufs = smem;
+    // MODE 3 with a two-stage plan whose last radix is 16: H stays in registers (smid_fused_otf16), no H tile, no table.
+    // Measured: L = 384 0.156 -> 0.148 ms; L = 256, which runs two CTAs per SM either way, 0.132 -> 0.150 ms (196 registers,
+    // the H derivation and the data butterflies no longer overlap): only the longer length uses it.
+    constexpr bool HREG = MODE == 3 && P::ns == 2 && P::RL == 16 && P::L >= 384;
     float4* hbuf = bufs + (size_t)NBUF * SLOT;                  // MODE 3 only
-    float4* tw = hbuf + (MODE == 3 ? TILE : 0);
+    float4* tw = hbuf + ((MODE == 3 && !HREG) ? TILE : 0);
     int* pos_s = reinterpret_cast<int*>(tw + L);                // MODE 3 only
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(pos_s + (MODE == 3 ? L : 0));
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(pos_s + ((MODE == 3 && !HREG) ? L : 0));
     unsigned long long* done = full + NBUF;
 
     const int t = threadIdx.x;
@@ -402,7 +464,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
     }
     pdl_launch_dependents();
     load_twiddles(tw, a.tw, L);
-    if constexpr (MODE == 3)
+    if constexpr (MODE == 3 && !HREG)
         for (int k = t; k < L; k += THREADS + 32) {   // position of frequency k for THIS kernel's radix sequence
             const int m0 = k % P::R0, q = k / P::R0;
             int pk;
@@ -507,7 +569,7 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
             }
         } else {
             sstage<P::R0, L, L, NW, false, TXP>(sm, tw, cp, w);
-            if constexpr (MODE == 3) otf_h_tile<L, NH, NW, TXP>(sm + TILE, hbuf, tw, pos_s, a.z0, cp, w);
+            if constexpr (MODE == 3 && !HREG) otf_h_tile<L, NH, NW, TXP>(sm + TILE, hbuf, tw, pos_s, a.z0, cp, w);
             consumer_sync<THREADS>();
             if constexpr (P::ns >= 3) {
                 if constexpr (REG2) sstage_regtw<P::R1, L, L / P::R0, NW, false, TXP>(sm, cp, w, tc2, ts2);
@@ -518,7 +580,8 @@ __global__ void __launch_bounds__(THREADS + 32, 1)
                 sstage<P::R2, L, L / (P::R0 * P::R1), NW, false, TXP>(sm, tw, cp, w);
                 consumer_sync<THREADS>();
             }
-            smid_fused_tma<P::RL, L, NW, TXP>(MODE == 3 ? hbuf : sm + TILE, sm, cp, w, a.scale);
+            if constexpr (HREG) smid_fused_otf16<L, NH, NW, TXP>(sm + TILE, sm, tw, a.z0, cp, w, a.scale);
+            else smid_fused_tma<P::RL, L, NW, TXP>(MODE == 3 ? hbuf : sm + TILE, sm, cp, w, a.scale);
             consumer_sync<THREADS>();
             if constexpr (P::ns >= 4) {
                 sstage<P::R2, L, P::R2 * P::R3, NW, true, TXP>(sm, tw, cp, w);
@@ -858,7 +921,8 @@ bool run_col_otf_tma(const ColArgs& a, long long ngroups, int z0, cudaStream_t s
     int boxRows = std::min(L, 256);
     while (L % boxRows) --boxRows;
     const size_t tile = (size_t)L * TXP * sizeof(float4), win = (size_t)a.winPlanes * TXP * sizeof(float4);
-    const size_t smem = (size_t)NBUF * (tile + win) + tile + (size_t)L * (sizeof(float4) + sizeof(int)) +
+    constexpr bool hreg = P::ns == 2 && P::RL == 16 && P::L >= 384;   // H in registers: no H tile, no position table (col_tma_kernel)
+    const size_t smem = (size_t)NBUF * (tile + win) + (hreg ? 0 : tile + (size_t)L * sizeof(int)) + (size_t)L * sizeof(float4) +
                         2 * NBUF * sizeof(unsigned long long);
     if (smem > (size_t)kMaxDynSmem) return false;
     if (probe) return true;
