@@ -150,3 +150,68 @@ def test_misaligned_device_pointers_are_rejected_not_faulted(fc, dev):
         fc.convolve_batch([buf[1:]], imDim, k, kDim, dev)         # 4-byte aligned slice
     fc.convolve_batch([buf[:n]], imDim, k, kDim, dev)             # the context is still healthy
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("plan", ["y300=12.5.5", "z300=4.3.5.5,y300=4.3.5.5", "x150=2.3.5.5", "y300=20.15,z300=15.20"])
+def test_plan_override_changes_the_radix_sequence_not_the_result(fc, dev, monkeypatch, plan):
+    """FCB200_PLAN (tuning runs) picks the radix sequence of an axis and length; sequences without a compile-time kernel
+    run on the run-time-radix kernels -- the result must be the planner's own to fp32 round-off"""
+    imDim, kDim = (300, 300, 300), (5, 3, 7)
+    rng = np.random.default_rng(77)
+    im = (rng.random(int(np.prod(imDim)), dtype=np.float32) * 1000).astype(np.float32)
+    k = rng.random(int(np.prod(kDim)), dtype=np.float32)
+    k /= k.sum()
+    fc.release()
+    want = im.copy()
+    fc.convolution3DfftCUDAInPlace(want, imDim, k, kDim, dev)
+    assert fc.plan_radices(300, 0)[0] == [20, 15] and fc.plan_radices(150, 2)[0] == [10, 15]
+    fc.release()
+    monkeypatch.setenv("FCB200_PLAN", plan)
+    try:
+        first = plan.split(",")[0]
+        style = {"y": 0, "z": 1, "x": 2}[first[0]]
+        L, rad = first[1:].split("=")
+        assert fc.plan_radices(int(L), style)[0] == [int(r) for r in rad.split(".")]
+        got = im.copy()
+        fc.convolution3DfftCUDAInPlace(got, imDim, k, kDim, dev)
+    finally:
+        monkeypatch.delenv("FCB200_PLAN")
+        fc.release()
+    check(got, want, max_rel=2e-6, l2_rel=1e-6)
+
+
+def test_run_time_radix_tma_pipeline_equals_the_one_tile_kernels(fc, dev, monkeypatch):
+    """plain passes of long lengths without a compile-time plan: FCB200_TMA_DYN=0 routes them through the one-tile-per-CTA
+    run-time-radix kernels -- same radix sequence, same result to fp32 round-off"""
+    import torch
+    imDim, kDim = (64, 400, 480), (5, 5, 5)     # y = 400 = (16,5,5), z = 480 = (8,4,15) (fused: not on the pipeline)
+    n = int(np.prod(imDim))
+    g = torch.Generator(device=f"cuda:{dev}")
+    g.manual_seed(11)
+    base = torch.rand(n, device=f"cuda:{dev}", generator=g) * 1000
+    d_k = torch.rand(int(np.prod(kDim)), device=f"cuda:{dev}", generator=g)
+    d_k /= d_k.sum()
+    x = base.clone()
+    fc.convolve_device_async(x, imDim, d_k, kDim, dev, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    # FCB200_TMA_DYN is read once per process: the comparison runs in a child process
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        np.save(os.path.join(tmp, "im.npy"), base.cpu().numpy())
+        np.save(os.path.join(tmp, "k.npy"), d_k.cpu().numpy())
+        code = (
+            "import sys, numpy as np, torch\n"
+            f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+            "import fourierconvolutioncudalib_b200 as fc\n"
+            f"im = torch.from_numpy(np.load({os.path.join(tmp, 'im.npy')!r})).cuda({dev})\n"
+            f"k = torch.from_numpy(np.load({os.path.join(tmp, 'k.npy')!r})).cuda({dev})\n"
+            f"fc.convolve_device_async(im, {imDim!r}, k, {kDim!r}, {dev}, torch.cuda.current_stream().cuda_stream)\n"
+            "torch.cuda.synchronize()\n"
+            f"np.save({os.path.join(tmp, 'out.npy')!r}, im.cpu().numpy())\n")
+        env = dict(os.environ, FCB200_TMA_DYN="0")
+        subprocess.run([sys.executable, "-c", code], check=True, env=env)
+        other = np.load(os.path.join(tmp, "out.npy"))
+    check(x.cpu().numpy(), other, max_rel=2e-6, l2_rel=1e-6)
