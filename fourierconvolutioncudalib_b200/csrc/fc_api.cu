@@ -53,6 +53,8 @@ bool prepare_psf(ConvPlan& p, const float* kernel, bool k_dev, const int* pdims,
     //   nz = 256, 16-plane window (C3): 0.132 against 0.142 ms, and no PSF z pass: C3 0.588 -> 0.517 ms, 256^3 0.182 -> 0.156
     //   nz = 384, window <= 32 planes (a C4 block): 0.147 against 0.144 ms: 384^3 0.574 -> 0.500 ms when the spectrum has to
     //   be built, within 1 % of a cached materialised spectrum when it has not -- and 231 MB less memory
+    //   nz <= 128, 16-plane window (launch-bound volumes, C1): the PSF chain on the side stream -- three small launches -- is
+    //   longer than the image's x and y passes it runs next to; without the PSF z launch 64^3 45.5 -> 38.7 us, 128^3 49.9 -> 45.5
     // Elsewhere the materialised spectrum stays: it is cached across calls with the same host taps (the deconvolution
     // pattern) and its fused pass is the faster one (512: 0.367 against 0.469 ms).  The rule depends on the shapes only, so
     // host and device pointers give bit-identical results.
@@ -60,8 +62,8 @@ bool prepare_psf(ConvPlan& p, const float* kernel, bool k_dev, const int* pdims,
     if (!save_memory) {
         const char* e = std::getenv("FCB200_OTF_INPLACE");
         if (e) otf_inplace = std::atoi(e) != 0;
-        else if (p.g.nz == 256 || p.g.nz == 384)
-            otf_inplace = psf_window_applies(p, pdims, st) && p.psf_window_planes <= (p.g.nz == 256 ? 16 : 32);
+        else if (p.g.nz <= 128 || p.g.nz == 256 || p.g.nz == 384)
+            otf_inplace = psf_window_applies(p, pdims, st) && p.psf_window_planes <= (p.g.nz == 384 ? 32 : 16);
     }
     const size_t ktaps = (size_t)pdims[0] * pdims[1] * pdims[2];
     auto same_taps = [&](bool valid, const int* dims, const std::vector<float>& taps) {
