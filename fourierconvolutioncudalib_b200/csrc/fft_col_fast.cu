@@ -395,11 +395,92 @@ __global__ void __launch_bounds__(MAXT) psf_z_pruned_kernel(ColArgs a, int z0)
     }
 }
 
+// The same for lengths that are not multiples of 16 (the caller-padded 300, 420, 270, 350 ...): L = R * Q with a register
+// radix R (20, 18, 24, 28, 21, 25) and a window of WP = 16 / 32 / 64 planes; inputs that are R planes apart share their
+// w_R^(n k1), so they are summed (twiddled) into one butterfly input first, inputs beyond the window are zero:
+//   X[k1*Q + k2] = w_R^(z0 k1) * sum_{m<R} [ sum_{n = m mod R, n < WP} x[z0+n] w_L^((z0+n) k2) ] w_R^(m k1)
+// (these lengths ran a full masked z pass before: 560x560x300 PSF z pass 0.134 ms for 382 MB written)
+template <int R, int WP>
+__global__ void __launch_bounds__(256) psf_z_pruned_r_kernel(ColArgs a, int z0)
+{
+    __shared__ float4 win[WP * 8];
+    const int L = a.P.L, Q = L / R;
+    const int t = threadIdx.x, cp = t & 7, w = t >> 3;   // w = residue k2 in [0, Q)
+    const int col0 = blockIdx.x * 16;
+    const int npairs = min(8, (a.rowLen - col0) >> 1);
+    const bool active = cp < npairs;
+    float2* base = a.data + col0 + 2 * cp;
+    const size_t stride = (size_t)a.stride;
+    for (int q = t; q < WP * 8; q += blockDim.x) {
+        int z = z0 + (q >> 3);
+        if (z >= L) z -= L;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((q & 7) < npairs && (a.rowMask == nullptr || a.rowMask[z]))
+            v = *reinterpret_cast<const float4*>(a.data + col0 + 2 * (q & 7) + (size_t)z * stride);
+        win[q] = v;
+    }
+    __syncthreads();
+    if (!active || w >= Q) return;
+    p2 r[R], i[R];
+    int e = (int)(((long long)z0 * w) % L);
+#pragma unroll
+    for (int n = 0; n < (WP > R ? WP : R); ++n) {
+        if (n < WP) {
+            const float4 v = win[n * 8 + cp];
+            const float2 tw = __ldg(a.P.tw + e);
+            p2 tr = make_float2(v.x, v.y), ti = make_float2(v.z, v.w);
+            cmul(tr, ti, make_float4(tw.x, tw.x, tw.y, tw.y));
+            if (n < R) {
+                r[n] = tr;
+                i[n] = ti;
+            } else {
+                r[n % R] = padd(r[n % R], tr);
+                i[n % R] = padd(i[n % R], ti);
+            }
+            e += w;
+            if (e >= L) e -= L;
+        } else {
+            r[n] = make_float2(0.f, 0.f);
+            i[n] = make_float2(0.f, 0.f);
+        }
+    }
+    Dft<R>::run(r, i);
+    const int sR = z0 % R;   // w_R^(z0 k1) = w_L^(((z0 k1) mod R) * Q)
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) {
+        if (sR != 0 && k1 != 0) {
+            const float2 tw = __ldg(a.P.tw + ((sR * k1) % R) * Q);
+            cmul(r[k1], i[k1], make_float4(tw.x, tw.x, tw.y, tw.y));
+        }
+        *reinterpret_cast<float4*>(base + (size_t)(k1 * Q + w) * stride) = make_float4(r[k1].x, r[k1].y, i[k1].x, i[k1].y);
+    }
+}
+
+template <int R>
+static bool try_psf_z_pruned_r(const ColArgs& a, int z0, int planes, cudaStream_t st)
+{
+    const int L = a.P.L;
+    if (L % R != 0 || planes > L) return false;
+    const int threads = ((L / R * 8 + 31) / 32) * 32;
+    if (threads > 256 || L / R < 2) return false;
+    const int grid = (a.rowLen + 15) / 16;
+    if (planes == 16) psf_z_pruned_r_kernel<R, 16><<<grid, threads, 0, st>>>(a, z0);
+    else if (planes == 32) psf_z_pruned_r_kernel<R, 32><<<grid, threads, 0, st>>>(a, z0);
+    else if (planes == 64) psf_z_pruned_r_kernel<R, 64><<<grid, threads, 0, st>>>(a, z0);
+    else return false;
+    FC_CUDA_KERNEL();
+    return true;
+}
+
 // planes: size of the window (16, 32 or 64 consecutive planes from z0, mod L) that holds every non-zero input plane
 bool launch_psf_z_pruned(const ColArgs& a, int z0, int planes, cudaStream_t st)
 {
     static const bool on = env_int("FCB200_PSF_PRUNED", 1) != 0;
     const int L = a.P.L;
+    if (on && L % 16 != 0 && a.groupStride == 0 && a.rowLen > 0)
+        return try_psf_z_pruned_r<20>(a, z0, planes, st) || try_psf_z_pruned_r<18>(a, z0, planes, st) ||
+               try_psf_z_pruned_r<24>(a, z0, planes, st) || try_psf_z_pruned_r<28>(a, z0, planes, st) ||
+               try_psf_z_pruned_r<21>(a, z0, planes, st) || try_psf_z_pruned_r<25>(a, z0, planes, st);
     if (!on || L % 16 != 0 || L / 16 * 8 > 1024 || L / 16 * 8 < 128 || a.groupStride != 0) return false;
     if ((planes != 16 && planes != 32 && planes != 64) || planes > L) return false;
     const int tiles = (a.rowLen + 15) / 16;
