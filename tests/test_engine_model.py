@@ -137,3 +137,21 @@ def test_rader_tables_reproduce_the_dft(fc, p):
 def test_rader_is_declined_when_p_minus_1_is_not_smooth(fc):
     assert fc.plan_rader(173) is None       # 172 = 4 * 43
     assert fc.plan_rader(47) is None        # 46 = 2 * 23: radix 23 is not among the n-point transform's radices
+
+
+def test_plan_override_parsing(fc, monkeypatch):
+    """FCB200_PLAN (tuning runs, fc_plan.cu: plan_override): '<axis><length>=r0.r1...' entries, comma separated; an entry
+    applies to its axis style and length only, products that do not match and unknown axes are ignored"""
+    monkeypatch.setenv("FCB200_PLAN", "z300=15.20,y420=12.5.7,x280=20.14,y512=8.8,q64=8.8,y96=")
+    assert fc.plan_radices(300, 1) == ([15, 20], False)
+    assert fc.plan_radices(300, 0) == ([20, 15], False)            # other axis: the planner's own
+    assert fc.plan_radices(420, 0) == ([12, 5, 7], False)
+    assert fc.plan_radices(280, 2) == ([20, 14], False)
+    assert fc.plan_radices(512, 0) == ([8, 8, 8], False)           # 8 * 8 != 512: ignored
+    assert fc.plan_radices(64, 0) == ([8, 8], False) and fc.plan_radices(96, 0) == ([8, 4, 3], False)
+    monkeypatch.setenv("FCB200_PLAN", "y158=2.79")
+    assert fc.plan_radices(158, 0) == ([2, 79], True)              # a prime above 23 still means the direct-sum stage
+    rev, pos, _ = fc.plan_tables(158, 0)
+    assert np.array_equal(pos[rev], np.arange(158))
+    monkeypatch.delenv("FCB200_PLAN")
+    assert fc.plan_radices(300, 1) == ([20, 15], False)
