@@ -489,6 +489,7 @@ def run_ours(args):
 
     # the same loop with the PSF spectrum MATERIALISED (the default call derives it on the fly inside the fused z kernel
     # for this shape, fc_api.cu: prepare_psf): the HBM-bound form of the fused pass, reported next to the default one
+    otf_before = os.environ.get("FCB200_OTF_INPLACE")
     os.environ["FCB200_OTF_INPLACE"] = "0"
     for _ in range(2):
         step()
@@ -500,7 +501,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     prof_mat = fc.profile_read()
     fc.profile_enable(False)
-    del os.environ["FCB200_OTF_INPLACE"]
+    if otf_before is None:
+        del os.environ["FCB200_OTF_INPLACE"]
+    else:
+        os.environ["FCB200_OTF_INPLACE"] = otf_before
     for _ in range(2):
         step()
     torch.cuda.synchronize()
